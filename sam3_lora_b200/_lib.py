@@ -1,0 +1,133 @@
+"""ctypes binding of libsam3b.so (C ABI declared in include/sam3b.h).
+
+The product path has no CPU fallback: if the shared library is missing, or a CUDA entry point
+is called without a GPU, the call raises.  PyTorch is used only to own device memory and
+streams; every kernel behind these entry points is hand-written sm_100a CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libsam3b.so"
+
+F16, BF16 = 0, 1
+EPI_STORE16, EPI_QKV_ROPE, EPI_RESIDUAL_F32, EPI_GELU, EPI_DGELU, EPI_ATOMIC_F32, EPI_STORE32 = range(7)
+
+
+class Sam3bError(RuntimeError):
+    pass
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_mn", C.c_int32),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("b_mn", C.c_int32),
+        ("dtype", C.c_int32), ("epilogue", C.c_int32),
+        ("C", C.c_void_p), ("ldc", C.c_int64),
+        ("C2", C.c_void_p), ("ldc2", C.c_int64),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ldres", C.c_int64), ("res_row_mod", C.c_int32),
+        ("aux", C.c_void_p), ("ldaux", C.c_int64),
+        ("rope", C.c_void_p), ("rope_period", C.c_int32), ("rope_cols", C.c_int32),
+        ("alpha", C.c_float),
+        ("splitk", C.c_int32), ("c_trans", C.c_int32), ("bn", C.c_int32),
+        ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32), ("max_ctas", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libsam3b.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("SAM3B_LIB", LIB_PATH))
+    if not path.exists():
+        raise Sam3bError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the hot path)")
+    lib = C.CDLL(str(path))
+    lib.sam3b_last_error.restype = C.c_char_p
+    lib.sam3b_abi_version.restype = C.c_int
+    lib.sam3b_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    lib.sam3b_gemm.restype = C.c_int
+    _declare_optional(lib)
+    _lib = lib
+    return lib
+
+
+def _declare_optional(lib: C.CDLL) -> None:
+    """Signatures of the remaining entry points (declared as they are added to sam3b.h)."""
+    from . import _abi  # noqa: PLC0415  (keeps this file small)
+
+    _abi.declare(lib)
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().sam3b_last_error()
+        raise Sam3bError(f"libsam3b error {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None passes NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch  # noqa: PLC0415
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def torch_dtype_code(dt) -> int:
+    import torch  # noqa: PLC0415
+
+    if dt == torch.float16:
+        return F16
+    if dt == torch.bfloat16:
+        return BF16
+    raise Sam3bError(f"unsupported operand dtype {dt}")
+
+
+def gemm(A, B, C_out, *, epilogue=EPI_STORE16, a_mn=False, b_mn=False, M=None, N=None, K=None,
+         bias=None, residual=None, res_row_mod=0, aux=None, rope=None, rope_period=1, rope_cols=0,
+         C2=None, alpha=1.0, splitk=1, c_trans=False, bn=0, dbg_lbo=0, dbg_sbo=0, max_ctas=0):
+    """C = epilogue(alpha * A @ B^T).  A:[M,K] (or [K,M] if a_mn), B:[N,K] (or [K,N] if b_mn).
+
+    Tensors may be column-slices of wider buffers: leading dimensions are taken from stride(0).
+    """
+    lib = load()
+    if M is None:
+        M = A.shape[1] if a_mn else A.shape[0]
+    if K is None:
+        K = A.shape[0] if a_mn else A.shape[1]
+    if N is None:
+        N = B.shape[1] if b_mn else B.shape[0]
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.a_mn = ptr(A), A.stride(0), int(a_mn)
+    d.B, d.ldb, d.b_mn = ptr(B), B.stride(0), int(b_mn)
+    d.dtype = torch_dtype_code(A.dtype)
+    d.epilogue = epilogue
+    d.C, d.ldc = ptr(C_out), C_out.stride(0)
+    if C2 is not None:
+        d.C2, d.ldc2 = ptr(C2), C2.stride(0)
+    d.bias = ptr(bias)
+    if residual is not None:
+        d.residual, d.ldres, d.res_row_mod = ptr(residual), residual.stride(0), res_row_mod
+    if aux is not None:
+        d.aux, d.ldaux = ptr(aux), aux.stride(0)
+    if rope is not None:
+        d.rope, d.rope_period, d.rope_cols = ptr(rope), rope_period, rope_cols
+    d.alpha = alpha
+    d.splitk, d.c_trans, d.bn = splitk, int(c_trans), bn
+    d.dbg_lbo, d.dbg_sbo, d.max_ctas = dbg_lbo, dbg_sbo, max_ctas
+    check(lib.sam3b_gemm(C.byref(d), current_stream()))
+    return C_out

@@ -1,0 +1,36 @@
+// Host-side helpers shared by the launchers: error reporting for the C ABI (no exceptions
+// cross the boundary; every entry point returns 0 or a negative code and the message is
+// fetched with sam3b_last_error()), TMA tensor-map construction, device properties.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace sam3b {
+
+// Records a message (thread-local) and returns `code` (negative).
+int fail(int code, const char* fmt, ...);
+const char* last_error_message();
+
+#define SAM3B_CHECK_CUDA(expr)                                                                     \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::sam3b::fail(-2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                           __LINE__);                                                              \
+  } while (0)
+
+#define SAM3B_REQUIRE(cond, ...)                                  \
+  do {                                                            \
+    if (!(cond)) return ::sam3b::fail(-1, __VA_ARGS__);           \
+  } while (0)
+
+// 2-D row-major tensor [rows][cols] of 16-bit (or 32-bit) elements, leading dimension ld
+// (elements); box = [box_rows][box_cols]; SWIZZLE_128B; out-of-bounds reads are zero-filled.
+// Returns 0 on success.
+int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols, int elem_bytes = 2);
+
+int num_sms();
+
+}  // namespace sam3b

@@ -1,0 +1,405 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M][N] = epilogue( alpha * A[M][K] . B[N][K]^T )
+//
+// This one kernel carries every dense contraction of the SAM3 ViT trunk (qkv / proj / fc1 /
+// fc2 forward, their dgrads, the skinny LoRA down-projections and the LoRA weight-gradients):
+// reference call sites sam3/model/vitdet.py:480,513 (qkv, proj), timm Mlp fc1/fc2
+// (vitdet.py:585-590), lora_layers.py:54-55,91 (x@A@B*alpha/r added to the base Linear).
+// The LoRA up-projection never runs as its own Linear: the caller appends s*(x.A) as extra K
+// columns of A and lora_B as extra K columns of the weight, so it rides the same K loop.
+//
+// Structure (one CTA per SM, 256 threads):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1   : MMA issuer     (one elected lane, tcgen05.mma cta_group::1 kind::f16, M=128,N=BN,K=16)
+//   warp 2   : TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), and a static
+// persistent tile schedule (tile = blockIdx.x + i*gridDim.x, n fastest so CTAs running
+// together share the A row-panel in L2).
+#include "gemm.cuh"
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace sam3b {
+
+struct GemmParams {
+  int M, N, K, splitk;
+  void* C; int64_t ldc;
+  void* C2; int64_t ldc2;
+  const float* bias;
+  const float* res; int64_t ldres; int res_row_mod;
+  const void* aux; int64_t ldaux;
+  const float2* rope; int rope_period; int rope_cols;
+  float alpha;
+  int c_trans;
+  uint32_t mn_lbo, mn_sbo;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TCOLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
+};
+
+__device__ __forceinline__ float gelu_erf(float h) { return 0.5f * h * (1.f + erff(h * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float h) {
+  return 0.5f * (1.f + erff(h * 0.70710678118654752f)) + h * 0.39894228040143268f * __expf(-0.5f * h * h);
+}
+
+template <int DT>
+__device__ __forceinline__ void store16x32(void* base, int64_t off, const float (&v)[32], int ncols_valid) {
+  // 32 consecutive 16-bit outputs = 64 B = 4 x 16 B; each 16 B vector is predicated on N.
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + off);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (q * 8 < ncols_valid) {
+      uint4 u;
+      u.x = pack2<DT>(v[q * 8 + 0], v[q * 8 + 1]);
+      u.y = pack2<DT>(v[q * 8 + 2], v[q * 8 + 3]);
+      u.z = pack2<DT>(v[q * 8 + 4], v[q * 8 + 5]);
+      u.w = pack2<DT>(v[q * 8 + 6], v[q * 8 + 7]);
+      dst[q] = u;
+    }
+  }
+}
+__device__ __forceinline__ void store32x32(float* base, int64_t off, const float (&v)[32], int ncols_valid) {
+  float4* dst = reinterpret_cast<float4*>(base + off);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (q * 4 < ncols_valid) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+  }
+}
+
+// One epilogue step: this thread owns output row `row`, columns [col, col+32).
+template <int EPI, int DT>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col, const uint32_t (&r)[32]) {
+  if (row >= p.M || col >= p.N) return;
+  const int nvalid = min(32, p.N - col);  // multiple of 8 (host-checked)
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+
+  if constexpr (EPI != EPI_ATOMIC_F32 && EPI != EPI_DGELU) {
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q * 4 < nvalid) {
+          float4 b = __ldg(b4 + q);
+          v[q * 4] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+        }
+      }
+    }
+  }
+
+  if constexpr (EPI == EPI_STORE16) {
+    store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
+  } else if constexpr (EPI == EPI_STORE32) {
+    store32x32(reinterpret_cast<float*>(p.C), (int64_t)row * p.ldc + col, v, nvalid);
+  } else if constexpr (EPI == EPI_QKV_ROPE) {
+    // 2-D axial RoPE on adjacent pairs (vitdet.py:68-90): (a,b) -> (a*cos - b*sin, a*sin + b*cos).
+    // The table row is the token's position inside its rope period (window or image); the pair
+    // index is (col % 64)/2 inside the 64-wide head. v (cols >= rope_cols) is stored unrotated.
+    if (col < p.rope_cols) {
+      const float4* t4 =
+          reinterpret_cast<const float4*>(p.rope + (int64_t)(row % p.rope_period) * 32 + ((col & 63) >> 1));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 cs = __ldg(t4 + q);  // (cos0, sin0, cos1, sin1)
+        float a0 = v[q * 4], b0 = v[q * 4 + 1], a1 = v[q * 4 + 2], b1 = v[q * 4 + 3];
+        v[q * 4] = a0 * cs.x - b0 * cs.y;
+        v[q * 4 + 1] = a0 * cs.y + b0 * cs.x;
+        v[q * 4 + 2] = a1 * cs.z - b1 * cs.w;
+        v[q * 4 + 3] = a1 * cs.w + b1 * cs.z;
+      }
+    }
+    store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
+  } else if constexpr (EPI == EPI_RESIDUAL_F32) {
+    const int rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
+    const float4* r4 = reinterpret_cast<const float4*>(p.res + (int64_t)rr * p.ldres + col);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q * 4 < nvalid) {
+        float4 x = r4[q];
+        v[q * 4] += x.x; v[q * 4 + 1] += x.y; v[q * 4 + 2] += x.z; v[q * 4 + 3] += x.w;
+      }
+    }
+    store32x32(reinterpret_cast<float*>(p.C), (int64_t)row * p.ldc + col, v, nvalid);
+  } else if constexpr (EPI == EPI_GELU) {
+    store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    store16x32<DT>(p.C2, (int64_t)row * p.ldc2 + col, v, nvalid);
+  } else if constexpr (EPI == EPI_DGELU) {
+    const uint4* h4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux) +
+                                                     (int64_t)row * p.ldaux + col);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q * 8 < nvalid) {
+        uint4 u = h4[q];
+        float2 h0 = unpack2<DT>(u.x), h1 = unpack2<DT>(u.y), h2 = unpack2<DT>(u.z), h3 = unpack2<DT>(u.w);
+        v[q * 8 + 0] *= dgelu_erf(h0.x); v[q * 8 + 1] *= dgelu_erf(h0.y);
+        v[q * 8 + 2] *= dgelu_erf(h1.x); v[q * 8 + 3] *= dgelu_erf(h1.y);
+        v[q * 8 + 4] *= dgelu_erf(h2.x); v[q * 8 + 5] *= dgelu_erf(h2.y);
+        v[q * 8 + 6] *= dgelu_erf(h3.x); v[q * 8 + 7] *= dgelu_erf(h3.y);
+      }
+    }
+    store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
+  } else if constexpr (EPI == EPI_ATOMIC_F32) {
+    float* C = reinterpret_cast<float*>(p.C);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < nvalid) {
+        int64_t off = p.c_trans ? ((int64_t)(col + i) * p.ldc + row) : ((int64_t)row * p.ldc + col + i);
+        atomicAdd(C + off, v[i]);
+      }
+    }
+  }
+}
+
+template <int BN, int EPI, int DT, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (p.M + 127) / 128;
+  const int kb_total = (p.K + 63) / 64;
+  const int kb_per_split = (kb_total + p.splitk - 1) / p.splitk;
+  const int total_work = m_tiles * n_tiles * p.splitk;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TCOLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.splitk;
+        const int tile = w / p.splitk;
+        const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
+          mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          uint8_t* a_dst = sA + stage * Cfg::A_BYTES;
+          uint8_t* b_dst = sB + stage * Cfg::B_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d(a_dst, &tmA, &full[stage], kb * 64, m_blk * 128);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d(a_dst + c * 8192, &tmA, &full[stage], m_blk * 128 + c * 64, kb * 64);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * 8192, &tmB, &full[stage], n_blk * BN + c * 64, kb * 64);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BN, DT, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.splitk;
+        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+          const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+          for (int k = 0; k < ksteps; ++k) {
+            uint64_t da, db;
+            if constexpr (!A_MN) da = make_desc_kmajor(a_addr + k * 32);
+            else da = make_smem_desc_sw128(a_addr + k * 2048, p.mn_lbo, p.mn_sbo);
+            if constexpr (!B_MN) db = make_desc_kmajor(b_addr + k * 32);
+            else db = make_smem_desc_sw128(b_addr + k * 2048, p.mn_lbo, p.mn_sbo);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // smem slot is free once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int tile = w / p.splitk;
+      const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
+      mbar_wait(&tfull[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+      const int row = m_blk * 128 + ew * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c, r);
+        tmem_ld_wait();
+        epilogue_chunk<EPI, DT>(p, row, n_blk * BN + c, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TCOLS);
+}
+
+// ---------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------
+template <int BN, int EPI, int DT, bool A_MN, bool B_MN>
+static int launch_one(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!A_MN) rc = make_tmap_2d(&tmA, a.A, a.M, a.K, a.lda, 128, 64);
+  else rc = make_tmap_2d(&tmA, a.A, a.K, a.M, a.lda, 64, 64);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_2d(&tmB, a.B, a.N, a.K, a.ldb, BN, 64);
+  else rc = make_tmap_2d(&tmB, a.B, a.K, a.N, a.ldb, 64, 64);
+  if (rc) return rc;
+  auto kern = gemm_kernel<BN, EPI, DT, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    SAM3B_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  const int m_tiles = (a.M + 127) / 128, n_tiles = (a.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles * p.splitk;
+  int ctas = a.max_ctas > 0 ? a.max_ctas : num_sms();
+  if (ctas > total) ctas = total;
+  kern<<<ctas, 256, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  SAM3B_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN, int EPI, bool A_MN, bool B_MN>
+static int launch_dt(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
+  if (a.dtype == 0) return launch_one<BN, EPI, 0, A_MN, B_MN>(a, p, stream);
+  return launch_one<BN, EPI, 1, A_MN, B_MN>(a, p, stream);
+}
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
+  SAM3B_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
+  SAM3B_REQUIRE(a.N % 8 == 0, "gemm: N=%d must be a multiple of 8", a.N);
+  SAM3B_REQUIRE(a.K % 16 == 0, "gemm: K=%d must be a multiple of 16", a.K);
+  SAM3B_REQUIRE(a.dtype == 0 || a.dtype == 1, "gemm: dtype %d (0 fp16, 1 bf16)", a.dtype);
+  SAM3B_REQUIRE(a.A && a.B && a.C, "gemm: null operand");
+  SAM3B_REQUIRE(a.a_mn == a.b_mn, "gemm: mixed operand majors are not instantiated");
+  const int kb_total = (a.K + 63) / 64;
+  int splitk = a.splitk < 1 ? 1 : a.splitk;
+  if (splitk > kb_total) splitk = kb_total;
+  // every split must own at least one k-block
+  while (splitk > 1 && ((kb_total + splitk - 1) / splitk) * (splitk - 1) >= kb_total) --splitk;
+  SAM3B_REQUIRE(splitk == 1 || a.epilogue == EPI_ATOMIC_F32, "gemm: split-K needs the atomic epilogue");
+
+  GemmParams p{};
+  p.M = a.M; p.N = a.N; p.K = a.K; p.splitk = splitk;
+  p.C = a.C; p.ldc = a.ldc; p.C2 = a.C2; p.ldc2 = a.ldc2;
+  p.bias = a.bias;
+  p.res = a.residual; p.ldres = a.ldres; p.res_row_mod = a.res_row_mod;
+  p.aux = a.aux; p.ldaux = a.ldaux;
+  p.rope = reinterpret_cast<const float2*>(a.rope); p.rope_period = a.rope_period > 0 ? a.rope_period : 1;
+  p.rope_cols = a.rope_cols;
+  p.alpha = a.alpha; p.c_trans = a.c_trans;
+  p.mn_lbo = a.dbg_lbo > 0 ? a.dbg_lbo : 8192;
+  p.mn_sbo = a.dbg_sbo > 0 ? a.dbg_sbo : 1024;
+
+  const bool is16 = (a.epilogue == EPI_STORE16 || a.epilogue == EPI_QKV_ROPE || a.epilogue == EPI_GELU ||
+                     a.epilogue == EPI_DGELU);
+  if (a.epilogue != EPI_ATOMIC_F32) {
+    SAM3B_REQUIRE(a.ldc % (is16 ? 8 : 4) == 0, "gemm: ldc=%lld breaks 16-byte store alignment", (long long)a.ldc);
+    SAM3B_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "gemm: C not 16-byte aligned");
+  }
+  if (a.epilogue == EPI_QKV_ROPE) {
+    SAM3B_REQUIRE(a.rope != nullptr && a.rope_cols % 64 == 0, "gemm: rope epilogue needs a table and 64-aligned rope_cols");
+  }
+  if (a.epilogue == EPI_RESIDUAL_F32) SAM3B_REQUIRE(a.residual != nullptr && a.ldres % 4 == 0, "gemm: residual epilogue needs residual with ld %% 4 == 0");
+  if (a.epilogue == EPI_GELU) SAM3B_REQUIRE(a.C2 != nullptr && a.ldc2 % 8 == 0, "gemm: gelu epilogue needs C2");
+  if (a.epilogue == EPI_DGELU) SAM3B_REQUIRE(a.aux != nullptr && a.ldaux % 8 == 0, "gemm: dgelu epilogue needs aux");
+  if (a.bias) SAM3B_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias not 16-byte aligned");
+
+  if (a.a_mn) {
+    SAM3B_REQUIRE(a.epilogue == EPI_ATOMIC_F32, "gemm: MN-major operands are instantiated for the atomic epilogue only");
+    return launch_dt<64, EPI_ATOMIC_F32, true, true>(a, p, stream);
+  }
+  int bn = a.bn;
+  if (bn == 0) bn = (a.N <= 64) ? 64 : 256;
+  if (bn == 64) {
+    switch (a.epilogue) {
+      case EPI_STORE16: return launch_dt<64, EPI_STORE16, false, false>(a, p, stream);
+      case EPI_STORE32: return launch_dt<64, EPI_STORE32, false, false>(a, p, stream);
+      case EPI_ATOMIC_F32: return launch_dt<64, EPI_ATOMIC_F32, false, false>(a, p, stream);
+      default: return fail(-1, "gemm: epilogue %d not instantiated for BN=64", a.epilogue);
+    }
+  }
+  SAM3B_REQUIRE(bn == 256, "gemm: bn must be 64 or 256 (got %d)", bn);
+  switch (a.epilogue) {
+    case EPI_STORE16: return launch_dt<256, EPI_STORE16, false, false>(a, p, stream);
+    case EPI_QKV_ROPE: return launch_dt<256, EPI_QKV_ROPE, false, false>(a, p, stream);
+    case EPI_RESIDUAL_F32: return launch_dt<256, EPI_RESIDUAL_F32, false, false>(a, p, stream);
+    case EPI_GELU: return launch_dt<256, EPI_GELU, false, false>(a, p, stream);
+    case EPI_DGELU: return launch_dt<256, EPI_DGELU, false, false>(a, p, stream);
+    case EPI_STORE32: return launch_dt<256, EPI_STORE32, false, false>(a, p, stream);
+    default: return fail(-1, "gemm: epilogue %d not instantiated for BN=256", a.epilogue);
+  }
+}
+
+}  // namespace sam3b

@@ -1,0 +1,42 @@
+// Internal GEMM interface (host side). The C ABI wrapper in capi.cpp and the block
+// schedules in engine.cpp both go through gemm_launch().
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sam3b {
+
+enum GemmEpilogue : int {
+  EPI_STORE16 = 0,       // C16 = alpha*acc (+bias)
+  EPI_QKV_ROPE = 1,      // C16 = rope(acc + bias) on columns < rope_cols, plain on the rest
+  EPI_RESIDUAL_F32 = 2,  // C32 = acc + bias + residual[row % res_row_mod]
+  EPI_GELU = 3,          // C16 = h = acc + bias ; C2_16 = gelu_erf(h)
+  EPI_DGELU = 4,         // C16 = acc * gelu_erf'(aux16)
+  EPI_ATOMIC_F32 = 5,    // C32 (+)= alpha*acc with red.global.add (split-K), optional transpose
+  EPI_STORE32 = 6,       // C32 = alpha*acc (+bias)
+  EPI_COUNT
+};
+
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const void* A = nullptr; int64_t lda = 0; int a_mn = 0;  // a_mn=0: A[M][K] ; 1: A stored as [K][M]
+  const void* B = nullptr; int64_t ldb = 0; int b_mn = 0;  // b_mn=0: B[N][K] ; 1: B stored as [K][N]
+  int dtype = 0;                                           // operand format: 0 fp16, 1 bf16
+  int epilogue = EPI_STORE16;
+  void* C = nullptr; int64_t ldc = 0;
+  void* C2 = nullptr; int64_t ldc2 = 0;
+  const float* bias = nullptr;
+  const float* residual = nullptr; int64_t ldres = 0; int res_row_mod = 0;
+  const void* aux = nullptr; int64_t ldaux = 0;
+  const float* rope = nullptr; int rope_period = 1; int rope_cols = 0;  // rope: [period][32] (cos,sin) pairs
+  float alpha = 1.f;
+  int splitk = 1;
+  int c_trans = 0;      // EPI_ATOMIC_F32 only: write C[col*ldc + row]
+  int bn = 0;           // 0 = choose; else 64 or 256
+  int dbg_lbo = 0, dbg_sbo = 0;  // bring-up overrides for the MN-major descriptors (bytes); 0 = default
+  int max_ctas = 0;     // 0 = number of SMs
+};
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace sam3b
