@@ -73,6 +73,59 @@ typedef struct sam3b_gemm_desc {
 
 int sam3b_gemm(const sam3b_gemm_desc* desc, void* stream);
 
+/* ---- LayerNorm (one warp per token row) -------------------------------------------------- */
+/* y16[row][0..D) = LN(x[row]) * gamma + beta ; saves mean/rstd.   nn.LayerNorm(eps=1e-5), vitdet.py:566,584,719,833 */
+int sam3b_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t rows, int32_t D,
+                        void* y16, int64_t ldy, int32_t dtype, float* mean, float* rstd, void* stream);
+/* dx = dres + dLN(dy16) (autograd of the above + the residual skip); dx16 = 16-bit copy of dx (may be NULL) */
+int sam3b_layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const float* mean, const float* rstd,
+                        const float* gamma, const float* dres, int32_t rows, int32_t D, float* dx, void* dx16,
+                        int64_t lddx16, int32_t dtype, void* stream);
+int sam3b_cast_rows_16(const float* x, int32_t rows, int32_t D, void* y16, int64_t ldy, int32_t dtype, void* stream);
+
+/* ---- attention (head_dim 64; tokens in window-major order so a window/image is a row run) --- */
+/* apply_rotary_enc + F.scaled_dot_product_attention, vitdet.py:68-90,485,502 (RoPE itself is the
+ * SAM3B_EPI_QKV_ROPE epilogue of the qkv GEMM). */
+typedef struct sam3b_attn_desc {
+  const void* qkv; int64_t ldqkv;   /* [tokens][>=3D] 16-bit: q | k | v, head h at columns h*64 of each block */
+  int32_t tokens, seg_len, D, heads, head_dim, dtype;
+  void* O; int64_t ldo;             /* fwd out / bwd in: [tokens][>=D] 16-bit */
+  float* lse2;                      /* [tokens][heads], log2-domain log-sum-exp (fwd out / bwd in) */
+  /* backward only */
+  const void* dO; int64_t lddo;
+  float* delta;                     /* [tokens][heads] scratch: rowsum(dO*O), written by the call */
+  void* dqkv; int64_t lddqkv;       /* [tokens][>=3D] 16-bit out: gradients w.r.t. the un-rotated q | k | v */
+  const float* rope; int32_t rope_period;
+} sam3b_attn_desc;
+int sam3b_attention_fwd(const sam3b_attn_desc* d, void* stream);
+int sam3b_attention_bwd(const sam3b_attn_desc* d, void* stream);
+
+/* ---- patch embed gather + layout ----------------------------------------------------------- */
+/* PatchEmbed conv k=s=P as a GEMM (vitdet.py:323-336): gathers 16-bit rows [token][Kpad], k=(c*P+u)*P+v,
+ * tokens in window-major order (window_partition, vitdet.py:93-115, folded into the layout). */
+int sam3b_patch_gather(const float* img, int32_t B, int32_t C, int32_t Himg, int32_t Wimg, int32_t P, int32_t ws,
+                       void* out16, int64_t ldo, int32_t Kpad, int32_t dtype, void* stream);
+/* ViT output permute to NCHW (vitdet.py:847-857) and its gradient. */
+int sam3b_tokens_to_nchw(const float* x, int32_t B, int32_t G, int32_t ws, int32_t D, float* out, void* stream);
+int sam3b_nchw_to_tokens(const float* g, int32_t B, int32_t G, int32_t ws, int32_t D, float* dx, void* dx16,
+                         int64_t ld16, int32_t dtype, void* stream);
+
+/* ---- LoRA operand packing (lora_layers.py:39-47 parameter layout: A [in][r], B [r][out]) ----- */
+typedef struct sam3b_lora_site {
+  int32_t in, out_total, n, r, rpad;
+  int32_t out_off[3], out_len[3];
+  const float* A[3];
+  const float* B[3];
+} sam3b_lora_site;
+int sam3b_lora_pack(const sam3b_lora_site* site, void* down_T, void* w_ext, int64_t ldw, void* up_pack, void* wt_ext,
+                    int64_t ldwt, int32_t dtype, void* stream);
+int sam3b_lora_unpack_grads(const sam3b_lora_site* site, const float* dA_pack, const float* dB_pack, float* const* dA,
+                            float* const* dB, void* stream);
+
+/* torch.optim.AdamW step on a flat fp32 buffer (train_sam3_lora_native.py:736-740); g is scaled by grad_scale first */
+int sam3b_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,428 @@
+// FlashAttention-style backward for the SAM3 ViT attention (head_dim 64) on tcgen05 + TMA.
+//
+// Reference semantics: autograd of sam3/model/vitdet.py:485-502 (apply_rotary_enc on q,k then
+// F.scaled_dot_product_attention).  Given dO, the forward's q,k (rotated), v, the log2-domain
+// LSE and delta = rowsum(dO*O):
+//     P  = exp2(S*c - lse2)            S = q k^T, c = head_dim^-0.5 * log2(e)
+//     dV = P^T dO        dP = dO V^T   dS = P * (dP - delta)
+//     dQ = scale * dS K  dK = scale * dS^T Q        then the inverse rotation R^T on dQ, dK
+// so that dqkv is the gradient w.r.t. the *un-rotated* qkv projection output.
+//
+// Two deterministic kernels, no atomics (recompute S/dP in both, 7 matmuls instead of 5):
+//   attn_bwd_dkdv : one CTA per (128-key tile, head, segment), loops over 64-query blocks.
+//                   S^T = K Q^T and dP^T = V dO^T in TMEM (thread = key row), P^T / dS^T written
+//                   16-bit to swizzled smem as A operands, dV += P^T dO, dK += dS^T Q with the
+//                   same Q/dO tiles re-used as MN-major B operands.
+//   attn_bwd_dq   : one CTA per (128-query tile, head, segment), loops over 64-key blocks.
+//                   S = Q K^T, dP = dO V^T (thread = query row), dQ += dS K (K tile as MN-major B).
+// Both: warps 0-3 compute, warp 4 TMA, warp 5 MMA issue + TMEM alloc; 256 TMEM columns and
+// <= 100 KB smem so two CTAs share an SM.
+#include "attn.cuh"
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace sam3b {
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int BT = 128;  // rows owned by a CTA (keys in dkdv, queries in dq)
+constexpr int BI = 64;   // inner block (queries in dkdv, keys in dq)
+constexpr int T_BYTES = BT * HD * 2;   // 16 KB
+constexpr int I_BYTES = BI * HD * 2;   // 8 KB
+constexpr int A_BYTES = BT * BI * 2;   // 16 KB: [128][64] 16-bit A operand written by the compute warps
+constexpr int TCOLS = 256;
+
+struct BwdParams {
+  int L, tiles, D, H;
+  const float* lse2;
+  const float* delta;
+  void* dqkv; int64_t lddqkv;
+  const float2* rope; int rope_period;
+  float scale_log2, scale;
+  int total_rows;
+};
+
+template <int DT>
+__device__ __forceinline__ void store_row_chunk16(uint8_t* row_base, int sw, int ch0, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack2<DT>(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack2<DT>(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack2<DT>(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack2<DT>(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(row_base + (((ch0 + q) ^ sw) << 4)) = u;
+  }
+}
+
+// out[row][col0 + 0..63] = (optionally inverse-rotated) acc * mul, 16-bit
+template <int DT, bool ROPE>
+__device__ __forceinline__ void store_grad_row(const BwdParams& p, uint32_t taddr, int row, int col0, float mul, bool valid) {
+#pragma unroll
+  for (int cc = 0; cc < HD; cc += 32) {
+    uint32_t t[32];
+    tmem_ld_x32(taddr + cc, t);
+    tmem_ld_wait();
+    if (valid) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]) * mul;
+      if constexpr (ROPE) {
+        const float4* t4 = reinterpret_cast<const float4*>(p.rope + (int64_t)(row % p.rope_period) * 32 + (cc >> 1));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 cs = __ldg(t4 + q);
+          float a0 = v[q * 4], b0 = v[q * 4 + 1], a1 = v[q * 4 + 2], b1 = v[q * 4 + 3];
+          v[q * 4] = a0 * cs.x + b0 * cs.y;
+          v[q * 4 + 1] = -a0 * cs.y + b0 * cs.x;
+          v[q * 4 + 2] = a1 * cs.z + b1 * cs.w;
+          v[q * 4 + 3] = -a1 * cs.w + b1 * cs.z;
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dqkv) + (int64_t)row * p.lddqkv + col0 + cc);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack2<DT>(v[q * 8 + 0], v[q * 8 + 1]);
+        u.y = pack2<DT>(v[q * 8 + 2], v[q * 8 + 3]);
+        u.z = pack2<DT>(v[q * 8 + 4], v[q * 8 + 5]);
+        u.w = pack2<DT>(v[q * 8 + 6], v[q * 8 + 7]);
+        dst[q] = u;
+      }
+    }
+  }
+}
+
+// =========================================================================================
+// dK / dV
+// =========================================================================================
+constexpr int DKDV_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + 2 * A_BYTES + 2 * 2 * BI * 4 + 128;
+
+template <int DT>
+__global__ void __launch_bounds__(192, 2)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][64]
+                     const __grid_constant__ CUtensorMap tmI,   // qkv, box [64][64]
+                     const __grid_constant__ CUtensorMap tmdO,  // dO,  box [64][64]
+                     const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  uint8_t* sK = smem_raw;
+  uint8_t* sV = sK + T_BYTES;
+  uint8_t* sQ = sV + T_BYTES;            // 2 stages x 8 KB
+  uint8_t* sdO = sQ + 2 * I_BYTES;       // 2 stages x 8 KB
+  uint8_t* sP = sdO + 2 * I_BYTES;       // P^T  [128 keys][64 q]
+  uint8_t* sdS = sP + A_BYTES;           // dS^T [128 keys][64 q]
+  float* sStat = reinterpret_cast<float*>(sdS + A_BYTES);  // [2 stages][2][64]: lse2 | delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * BI);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* in_full = bars + 1;   // [2]
+  uint64_t* in_free = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* acc_done = bars + 7;  // dV/dK MMAs of block j complete (also frees sP/sdS)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x % p.tiles;
+  const int seg = blockIdx.x / p.tiles;
+  const int head = blockIdx.y;
+  const int seg_row0 = seg * p.L;
+  const int t_row0 = seg_row0 + tile * BT;
+  const int n_blocks = p.L / BI;
+
+  if (warp == 4 && elect_one()) {
+    tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 64, tm_dV = tmem_base + 128, tm_dK = tmem_base + 192;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(kv_full, 2 * T_BYTES);
+      tma_load_2d(sK, &tmT, kv_full, p.D + head * HD, t_row0);
+      tma_load_2d(sV, &tmT, kv_full, 2 * p.D + head * HD, t_row0);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        if (j >= 2) mbar_wait(&in_free[st], ((j >> 1) - 1) & 1, 10 + st);
+        mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES);
+        tma_load_2d(sQ + st * I_BYTES, &tmI, &in_full[st], head * HD, seg_row0 + j * BI);
+        tma_load_2d(sdO + st * I_BYTES, &tmdO, &in_full[st], head * HD, seg_row0 + j * BI);
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);  // A K-major, B K-major, N=64
+      constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1); // A K-major, B MN-major, N=64
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
+      mbar_wait(kv_full, 0, 20);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        const uint32_t q_addr = smem_u32(sQ + st * I_BYTES), do_addr = smem_u32(sdO + st * I_BYTES);
+        mbar_wait(&in_full[st], (j >> 1) & 1, 21);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S^T = K . Q^T
+          umma_f16_ss(tm_S, make_desc_kmajor(k_addr + k * 32), make_desc_kmajor(q_addr + k * 32), idesc_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP^T = V . dO^T
+          umma_f16_ss(tm_dP, make_desc_kmajor(v_addr + k * 32), make_desc_kmajor(do_addr + k * 32), idesc_kk, k > 0);
+        umma_commit(sdp_full);
+        mbar_wait(pds_full, j & 1, 22);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dV += P^T . dO   (K = 64 queries)
+          umma_f16_ss(tm_dV, make_desc_kmajor(p_addr + k * 32), make_desc_mnmajor(do_addr + k * 2048, 8192), idesc_kmn,
+                      (j > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dK += dS^T . Q
+          umma_f16_ss(tm_dK, make_desc_kmajor(ds_addr + k * 32), make_desc_mnmajor(q_addr + k * 2048, 8192), idesc_kmn,
+                      (j > 0 || k > 0));
+        umma_commit(&in_free[st]);
+        umma_commit(acc_done);
+      }
+    }
+  } else {
+    const int r = threadIdx.x;  // key row inside the tile
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float c = p.scale_log2;
+    uint8_t* p_row = sP + r * 128;
+    uint8_t* ds_row = sdS + r * 128;
+    const int sw = r & 7;
+    for (int j = 0; j < n_blocks; ++j) {
+      // stage this block's per-query statistics (threads 0-63: lse2, 64-127: delta)
+      float* stat = sStat + (j & 1) * (2 * BI);
+      {
+        const int q = seg_row0 + j * BI + (r & 63);
+        const float* src = (r < 64) ? p.lse2 : p.delta;
+        stat[r] = __ldg(src + (int64_t)q * p.H + head);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sdp_full, j & 1, 30);
+      tc_fence_after();
+      if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);  // previous dV/dK MMAs finished reading sP/sdS
+#pragma unroll
+      for (int cc = 0; cc < BI; cc += 32) {
+        uint32_t s[32], d[32];
+        tmem_ld_x32(tm_S + lane_off + cc, s);
+        tmem_ld_x32(tm_dP + lane_off + cc, d);
+        tmem_ld_wait();
+        float pv[32], dsv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float pe = exp2f(__uint_as_float(s[i]) * c - stat[cc + i]);
+          pv[i] = pe;
+          dsv[i] = pe * (__uint_as_float(d[i]) - stat[BI + cc + i]);
+        }
+        store_row_chunk16<DT>(p_row, sw, cc >> 3, pv);
+        store_row_chunk16<DT>(ds_row, sw, cc >> 3, dsv);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(pds_full);
+    }
+    mbar_wait(acc_done, (n_blocks - 1) & 1, 32);
+    tc_fence_after();
+    const int row = t_row0 + r;
+    const bool valid = (tile * BT + r) < p.L && row < p.total_rows;
+    store_grad_row<DT, false>(p, tm_dV + lane_off, row, 2 * p.D + head * HD, 1.f, valid);
+    store_grad_row<DT, true>(p, tm_dK + lane_off, row, p.D + head * HD, p.scale, valid);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, TCOLS);
+}
+
+// =========================================================================================
+// dQ
+// =========================================================================================
+constexpr int DQ_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + A_BYTES + 128;
+
+template <int DT>
+__global__ void __launch_bounds__(192, 2)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][64]
+                   const __grid_constant__ CUtensorMap tmI,   // qkv, box [64][64]
+                   const __grid_constant__ CUtensorMap tmdO,  // dO,  box [128][64]
+                   const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem_raw;
+  uint8_t* sdO = sQ + T_BYTES;
+  uint8_t* sK = sdO + T_BYTES;           // 2 stages x 8 KB
+  uint8_t* sV = sK + 2 * I_BYTES;        // 2 stages x 8 KB
+  uint8_t* sdS = sV + 2 * I_BYTES;       // dS [128 q][64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + A_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* in_full = bars + 1;   // [2]
+  uint64_t* in_free = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_full = bars + 6;
+  uint64_t* acc_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x % p.tiles;
+  const int seg = blockIdx.x / p.tiles;
+  const int head = blockIdx.y;
+  const int seg_row0 = seg * p.L;
+  const int t_row0 = seg_row0 + tile * BT;
+  const int n_blocks = p.L / BI;
+
+  if (warp == 4 && elect_one()) {
+    tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
+    mbar_init(sdp_full, 1); mbar_init(ds_full, 128); mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 64, tm_dQ = tmem_base + 128;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, 2 * T_BYTES);
+      tma_load_2d(sQ, &tmT, q_full, head * HD, t_row0);
+      tma_load_2d(sdO, &tmdO, q_full, head * HD, t_row0);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        if (j >= 2) mbar_wait(&in_free[st], ((j >> 1) - 1) & 1, 10 + st);
+        mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES);
+        tma_load_2d(sK + st * I_BYTES, &tmI, &in_full[st], p.D + head * HD, seg_row0 + j * BI);
+        tma_load_2d(sV + st * I_BYTES, &tmI, &in_full[st], 2 * p.D + head * HD, seg_row0 + j * BI);
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);
+      constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
+      mbar_wait(q_full, 0, 20);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        const uint32_t k_addr = smem_u32(sK + st * I_BYTES), v_addr = smem_u32(sV + st * I_BYTES);
+        mbar_wait(&in_full[st], (j >> 1) & 1, 21);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // S = Q . K^T
+          umma_f16_ss(tm_S, make_desc_kmajor(q_addr + k * 32), make_desc_kmajor(k_addr + k * 32), idesc_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dP = dO . V^T
+          umma_f16_ss(tm_dP, make_desc_kmajor(do_addr + k * 32), make_desc_kmajor(v_addr + k * 32), idesc_kk, k > 0);
+        umma_commit(sdp_full);
+        mbar_wait(ds_full, j & 1, 22);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dQ += dS . K   (K = 64 keys, K tile as MN-major B)
+          umma_f16_ss(tm_dQ, make_desc_kmajor(ds_addr + k * 32), make_desc_mnmajor(k_addr + k * 2048, 8192), idesc_kmn,
+                      (j > 0 || k > 0));
+        umma_commit(&in_free[st]);
+        umma_commit(acc_done);
+      }
+    }
+  } else {
+    const int r = threadIdx.x;  // query row inside the tile
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float c = p.scale_log2;
+    const int row = t_row0 + r;
+    const int row_c = min(row, p.total_rows - 1);
+    const float lse = __ldg(p.lse2 + (int64_t)row_c * p.H + head);
+    const float dlt = __ldg(p.delta + (int64_t)row_c * p.H + head);
+    uint8_t* ds_row = sdS + r * 128;
+    const int sw = r & 7;
+    for (int j = 0; j < n_blocks; ++j) {
+      mbar_wait(sdp_full, j & 1, 30);
+      tc_fence_after();
+      if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);
+#pragma unroll
+      for (int cc = 0; cc < BI; cc += 32) {
+        uint32_t s[32], d[32];
+        tmem_ld_x32(tm_S + lane_off + cc, s);
+        tmem_ld_x32(tm_dP + lane_off + cc, d);
+        tmem_ld_wait();
+        float dsv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float pe = exp2f(__uint_as_float(s[i]) * c - lse);
+          dsv[i] = pe * (__uint_as_float(d[i]) - dlt);
+        }
+        store_row_chunk16<DT>(ds_row, sw, cc >> 3, dsv);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(ds_full);
+    }
+    mbar_wait(acc_done, (n_blocks - 1) & 1, 32);
+    tc_fence_after();
+    const bool valid = (tile * BT + r) < p.L && row < p.total_rows;
+    store_grad_row<DT, true>(p, tm_dQ + lane_off, row, head * HD, p.scale, valid);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, TCOLS);
+}
+
+template <typename K>
+static int set_smem_once(K kern, int bytes, bool& done) {
+  if (!done) {
+    SAM3B_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done = true;
+  }
+  return 0;
+}
+
+template <int DT>
+static int launch_bwd(const AttnBwdArgs& a, const BwdParams& p, const CUtensorMap& tmT, const CUtensorMap& tmI,
+                      const CUtensorMap& tmdO64, const CUtensorMap& tmdO128, cudaStream_t stream) {
+  static bool s1 = false, s2 = false;
+  int rc = set_smem_once(attn_bwd_dkdv_kernel<DT>, DKDV_SMEM, s1);
+  if (rc) return rc;
+  rc = set_smem_once(attn_bwd_dq_kernel<DT>, DQ_SMEM, s2);
+  if (rc) return rc;
+  const int nseg = a.tokens / a.seg_len;
+  dim3 grid(p.tiles * nseg, a.heads);
+  attn_bwd_dkdv_kernel<DT><<<grid, 192, DKDV_SMEM, stream>>>(tmT, tmI, tmdO64, p);
+  SAM3B_CHECK_CUDA(cudaGetLastError());
+  attn_bwd_dq_kernel<DT><<<grid, 192, DQ_SMEM, stream>>>(tmT, tmI, tmdO128, p);
+  SAM3B_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int attn_bwd_launch(const AttnBwdArgs& a, cudaStream_t stream) {
+  SAM3B_REQUIRE(a.head_dim == 64, "attention bwd: head_dim %d not supported (64 only)", a.head_dim);
+  SAM3B_REQUIRE(a.tokens % a.seg_len == 0, "attention bwd: tokens %% seg_len != 0");
+  SAM3B_REQUIRE(a.seg_len % BI == 0, "attention bwd: seg_len %d must be a multiple of 64", a.seg_len);
+  SAM3B_REQUIRE(a.heads * 64 == a.D, "attention bwd: heads*64 != D");
+  SAM3B_REQUIRE(a.lddqkv % 8 == 0 && a.ldqkv % 8 == 0 && a.lddo % 8 == 0, "attention bwd: leading dimensions must be multiples of 8");
+  SAM3B_REQUIRE(a.rope != nullptr, "attention bwd: rope table required");
+  CUtensorMap tmT, tmI, tmdO64, tmdO128;
+  int rc;
+  if ((rc = make_tmap_2d(&tmT, a.qkv, a.tokens, 3 * a.D, a.ldqkv, BT, HD))) return rc;
+  if ((rc = make_tmap_2d(&tmI, a.qkv, a.tokens, 3 * a.D, a.ldqkv, BI, HD))) return rc;
+  if ((rc = make_tmap_2d(&tmdO64, a.dO, a.tokens, a.D, a.lddo, BI, HD))) return rc;
+  if ((rc = make_tmap_2d(&tmdO128, a.dO, a.tokens, a.D, a.lddo, BT, HD))) return rc;
+  BwdParams p{};
+  p.L = a.seg_len; p.tiles = (a.seg_len + BT - 1) / BT; p.D = a.D; p.H = a.heads;
+  p.lse2 = a.lse2; p.delta = a.delta; p.dqkv = a.dqkv; p.lddqkv = a.lddqkv;
+  p.rope = reinterpret_cast<const float2*>(a.rope); p.rope_period = a.rope_period > 0 ? a.rope_period : 1;
+  p.scale = 0.125f; p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.total_rows = a.tokens;
+  return a.dtype == 0 ? launch_bwd<0>(a, p, tmT, tmI, tmdO64, tmdO128, stream)
+                      : launch_bwd<1>(a, p, tmT, tmI, tmdO64, tmdO128, stream);
+}
+
+}  // namespace sam3b

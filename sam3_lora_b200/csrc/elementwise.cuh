@@ -1,0 +1,63 @@
+// HBM-bound helper kernels of the ViT trunk (host-side launch interface).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sam3b {
+
+// y16[row][0..D) = LayerNorm(x[row]) * gamma + beta   (nn.LayerNorm eps, vitdet.py:566,584,719)
+// Saves mean / rstd per row for the backward.  x: fp32 [rows][D] contiguous.
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int rows, int D,
+                  void* y16, int64_t ldy, int dtype, float* mean, float* rstd, cudaStream_t s);
+
+// dx = dres + dLN(dy16; x, mean, rstd, gamma); also a 16-bit copy of dx for the next GEMM.
+// dres may alias dx (in-place accumulate).  dx16 may be null.
+int layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const float* mean, const float* rstd,
+                  const float* gamma, const float* dres, int rows, int D, float* dx, void* dx16, int64_t lddx16,
+                  int dtype, cudaStream_t s);
+
+// y16[row][0..D) = (16-bit) x[row][0..D)
+int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s);
+
+// delta[row][h] = sum_c dO[row][h*64+c] * O[row][h*64+c]
+int attn_delta(const void* dO, int64_t lddo, const void* O, int64_t ldo, int rows, int heads, int dtype, float* delta,
+               cudaStream_t s);
+
+// Patch gather for the k=s=P patch-embed conv (vitdet.py:323-336): image fp32 NCHW ->
+// 16-bit rows [token][Kpad] with k = (c*P + u)*P + v, tokens in window-major order:
+// token = ((b*nwin + wy*nwx + wx)*ws + i)*ws + j  for patch (wy*ws+i, wx*ws+j).
+int patch_gather(const float* img, int B, int C, int Himg, int Wimg, int P, int ws, void* out16, int64_t ldo, int Kpad,
+                 int dtype, cudaStream_t s);
+
+// Window-major token stream [B][T][D] fp32 <-> NCHW feature map [B][D][G][G] (vitdet.py:847-857).
+int tokens_to_nchw(const float* x, int B, int G, int ws, int D, float* out, cudaStream_t s);
+// and back (gradient path): also emits the 16-bit copy used as the first dgrad operand.
+int nchw_to_tokens(const float* g, int B, int G, int ws, int D, float* dx, void* dx16, int64_t ld16, int dtype,
+                   cudaStream_t s);
+
+// ---- LoRA packing -------------------------------------------------------------------------
+// One adapted Linear (in -> out_total) with n adapters of rank r that each own the output
+// slice [out_off[a], out_off[a]+out_len[a]) (q/k/v slices of the fused qkv; one slice otherwise).
+struct LoraSite {
+  int in = 0, out_total = 0, n = 0, r = 0, rpad = 64;
+  int out_off[3] = {0, 0, 0};
+  int out_len[3] = {0, 0, 0};
+  const float* A[3] = {nullptr, nullptr, nullptr};  // [in][r]   (lora_layers.py:40)
+  const float* B[3] = {nullptr, nullptr, nullptr};  // [r][out_len] (lora_layers.py:41)
+};
+// Fills the four 16-bit operand blocks the fused GEMMs read:
+//   down_T  [rpad][in]            row a*r+j = A_a[:, j]                 (B operand of T = x.A)
+//   w_ext   [out_total][ldw]      cols in + a*r+j = B_a[j][n-off_a]     (K-extension of W)
+//   up_pack [rpad][out_total]     row a*r+j, col n = B_a[j][n-off_a]    (B operand of dT = dy.B^T)
+//   wt_ext  [in][ldwt]            cols out_total + a*r+j = A_a[k][j]    (K-extension of W^T)
+int lora_pack(const LoraSite& site, void* down_T, void* w_ext, int64_t ldw, void* up_pack, void* wt_ext,
+              int64_t ldwt, int dtype, cudaStream_t s);
+// dA_a[k][j] = dA_pack[k][a*r+j] ; dB_a[j][n] = dB_pack[a*r+j][off_a+n]   (fp32)
+int lora_unpack_grads(const LoraSite& site, const float* dA_pack, const float* dB_pack, float* const dA[3],
+                      float* const dB[3], cudaStream_t s);
+
+// Fused AdamW over a flat fp32 buffer (torch.optim.AdamW semantics, train_sam3_lora_native.py:736-740).
+int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, int step, float grad_scale, cudaStream_t s);
+
+}  // namespace sam3b

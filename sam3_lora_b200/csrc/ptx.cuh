@@ -75,7 +75,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef SAM3B_WAIT_TIMEOUT_NS
 #define SAM3B_WAIT_TIMEOUT_NS 4000000000ull
 #endif
-__device__ __noinline__ void mbar_timeout_report(int tag, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout_report(int tag, uint32_t parity) {
   printf("[sam3b] mbarrier timeout: tag=%d parity=%u block=(%d,%d,%d) thread=%d\n", tag, parity,
          (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);
   __trap();
