@@ -1,14 +1,50 @@
 """argtypes/restype declarations for the libsam3b.so entry points beyond sam3b_gemm.
 
 Kept next to include/sam3b.h on purpose: tests/test_abi.py checks that every function the
-header declares is exported by the library and declared here.
+header declares is exported by the library and declared here (or in _lib.py).
 """
 from __future__ import annotations
 
 import ctypes as C
 
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("qkv", vp), ("ldqkv", i64),
+        ("tokens", i32), ("seg_len", i32), ("D", i32), ("heads", i32), ("head_dim", i32), ("dtype", i32),
+        ("O", vp), ("ldo", i64),
+        ("lse2", vp),
+        ("dO", vp), ("lddo", i64),
+        ("delta", vp),
+        ("dqkv", vp), ("lddqkv", i64),
+        ("rope", vp), ("rope_period", i32),
+    ]
+
+
+class LoraSite(C.Structure):
+    _fields_ = [
+        ("in_", i32), ("out_total", i32), ("n", i32), ("r", i32), ("rpad", i32),
+        ("out_off", i32 * 3), ("out_len", i32 * 3),
+        ("A", vp * 3), ("B", vp * 3),
+    ]
+
+
 # name -> (restype, argtypes)
-SIGNATURES: dict[str, tuple] = {}
+SIGNATURES: dict[str, tuple] = {
+    "sam3b_layernorm_fwd": (C.c_int, [vp, vp, vp, f32, i32, i32, vp, i64, i32, vp, vp, vp]),
+    "sam3b_layernorm_bwd": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, i32, i32, vp, vp, i64, i32, vp]),
+    "sam3b_cast_rows_16": (C.c_int, [vp, i32, i32, vp, i64, i32, vp]),
+    "sam3b_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), vp]),
+    "sam3b_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), vp]),
+    "sam3b_patch_gather": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, i64, i32, i32, vp]),
+    "sam3b_tokens_to_nchw": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
+    "sam3b_nchw_to_tokens": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, i64, i32, vp]),
+    "sam3b_lora_pack": (C.c_int, [C.POINTER(LoraSite), vp, vp, i64, vp, vp, i64, i32, vp]),
+    "sam3b_lora_unpack_grads": (C.c_int, [C.POINTER(LoraSite), vp, vp, C.POINTER(vp), C.POINTER(vp), vp]),
+    "sam3b_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]),
+}
 
 
 def declare(lib: C.CDLL) -> None:

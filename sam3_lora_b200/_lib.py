@@ -131,3 +131,98 @@ def gemm(A, B, C_out, *, epilogue=EPI_STORE16, a_mn=False, b_mn=False, M=None, N
     d.dbg_lbo, d.dbg_sbo, d.max_ctas = dbg_lbo, dbg_sbo, max_ctas
     check(lib.sam3b_gemm(C.byref(d), current_stream()))
     return C_out
+
+
+# ----------------------------------------------------------------------------------------------
+# thin wrappers over the remaining entry points (tensors in, tensors out)
+# ----------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, y16, mean, rstd):
+    """x: fp32 [rows, D] contiguous; y16: 16-bit [rows, >=D] (may be a slice of a wider buffer)."""
+    rows, D = x.shape
+    check(load().sam3b_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), eps, rows, D, ptr(y16), y16.stride(0),
+                                     torch_dtype_code(y16.dtype), ptr(mean), ptr(rstd), current_stream()))
+
+
+def layernorm_bwd(dy16, x, mean, rstd, gamma, dres, dx, dx16=None):
+    rows, D = x.shape
+    check(load().sam3b_layernorm_bwd(ptr(dy16), dy16.stride(0), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres),
+                                     rows, D, ptr(dx), ptr(dx16), 0 if dx16 is None else dx16.stride(0),
+                                     torch_dtype_code(dy16.dtype), current_stream()))
+
+
+def cast_rows_16(x, y16):
+    rows, D = x.shape
+    check(load().sam3b_cast_rows_16(ptr(x), rows, D, ptr(y16), y16.stride(0), torch_dtype_code(y16.dtype),
+                                    current_stream()))
+
+
+def _attn_desc(qkv, seg_len, D, heads, O, lse2):
+    from ._abi import AttnDesc  # noqa: PLC0415
+
+    d = AttnDesc()
+    d.qkv, d.ldqkv = ptr(qkv), qkv.stride(0)
+    d.tokens, d.seg_len, d.D, d.heads, d.head_dim = qkv.shape[0], seg_len, D, heads, D // heads
+    d.dtype = torch_dtype_code(qkv.dtype)
+    d.O, d.ldo = ptr(O), O.stride(0)
+    d.lse2 = ptr(lse2)
+    return d
+
+
+def attention_fwd(qkv, seg_len, D, heads, O, lse2):
+    d = _attn_desc(qkv, seg_len, D, heads, O, lse2)
+    check(load().sam3b_attention_fwd(C.byref(d), current_stream()))
+
+
+def attention_bwd(qkv, seg_len, D, heads, O, lse2, dO, delta, dqkv, rope, rope_period):
+    d = _attn_desc(qkv, seg_len, D, heads, O, lse2)
+    d.dO, d.lddo = ptr(dO), dO.stride(0)
+    d.delta = ptr(delta)
+    d.dqkv, d.lddqkv = ptr(dqkv), dqkv.stride(0)
+    d.rope, d.rope_period = ptr(rope), rope_period
+    check(load().sam3b_attention_bwd(C.byref(d), current_stream()))
+
+
+def patch_gather(img, P, ws, out16, Kpad):
+    B, Cc, H, W = img.shape
+    check(load().sam3b_patch_gather(ptr(img), B, Cc, H, W, P, ws, ptr(out16), out16.stride(0), Kpad,
+                                    torch_dtype_code(out16.dtype), current_stream()))
+
+
+def tokens_to_nchw(x, B, G, ws, D, out):
+    check(load().sam3b_tokens_to_nchw(ptr(x), B, G, ws, D, ptr(out), current_stream()))
+
+
+def nchw_to_tokens(g, B, G, ws, D, dx, dx16):
+    check(load().sam3b_nchw_to_tokens(ptr(g), B, G, ws, D, ptr(dx), ptr(dx16), 0 if dx16 is None else dx16.stride(0),
+                                      0 if dx16 is None else torch_dtype_code(dx16.dtype), current_stream()))
+
+
+def make_lora_site(in_features, out_total, r, rpad, adapters):
+    """adapters: list of (out_off, out_len, A_tensor[in,r], B_tensor[r,out_len]) (1..3 entries)."""
+    from ._abi import LoraSite  # noqa: PLC0415
+
+    s = LoraSite()
+    s.in_, s.out_total, s.n, s.r, s.rpad = in_features, out_total, len(adapters), r, rpad
+    for i, (off, ln, A, B) in enumerate(adapters):
+        s.out_off[i], s.out_len[i] = off, ln
+        s.A[i] = ptr(A)
+        s.B[i] = ptr(B)
+    return s
+
+
+def lora_pack(site, down_T, w_ext, up_pack, wt_ext, dtype):
+    check(load().sam3b_lora_pack(C.byref(site), ptr(down_T), ptr(w_ext), 0 if w_ext is None else w_ext.stride(0),
+                                 ptr(up_pack), ptr(wt_ext), 0 if wt_ext is None else wt_ext.stride(0),
+                                 torch_dtype_code(dtype), current_stream()))
+
+
+def lora_unpack_grads(site, dA_pack, dB_pack, dA_list, dB_list):
+    n = site.n
+    arrA = (C.c_void_p * 3)(*([ptr(t) for t in dA_list] + [None] * (3 - n)))
+    arrB = (C.c_void_p * 3)(*([ptr(t) for t in dB_list] + [None] * (3 - n)))
+    check(load().sam3b_lora_unpack_grads(C.byref(site), ptr(dA_pack), ptr(dB_pack), arrA, arrB, current_stream()))
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(load().sam3b_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                  grad_scale, current_stream()))
