@@ -126,6 +126,53 @@ int sam3b_lora_unpack_grads(const sam3b_lora_site* site, const float* dA_pack, c
 int sam3b_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                      float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
+/* ---- ViT trunk engine (ViT.forward / Block.forward / Attention.forward + autograd backward) --- */
+/* sam3/model/vitdet.py:813-859, 597-613, 466-515; only the LoRA adapters receive gradients
+ * (apply_lora_to_model freezes the rest, lora_layers.py:171-172). */
+#define SAM3B_LORA_Q 1
+#define SAM3B_LORA_K 2
+#define SAM3B_LORA_V 4
+#define SAM3B_LORA_O 8
+#define SAM3B_LORA_FC1 16
+#define SAM3B_LORA_FC2 32
+
+typedef struct sam3b_vit_config {
+  int32_t img_size, patch_size, in_chans, embed_dim, depth, num_heads, mlp_hidden, window_size;
+  int32_t n_global; int32_t global_blocks[16];
+  int32_t pos_side;              /* pos_embed is [1][1 + pos_side^2][D] (cls slot first), tiled over the grid */
+  float ln_eps, rope_theta;
+  int32_t lora_rank; float lora_scaling; int32_t lora_targets; /* SAM3B_LORA_* bitmask */
+  int32_t dtype;                 /* SAM3B_F16 | SAM3B_BF16 tensor-core operands; residual stream is fp32 */
+  int32_t max_batch;
+} sam3b_vit_config;
+
+typedef struct sam3b_lora_entry {
+  int32_t block, target, in, out, rank;
+  int64_t a_off, b_off;          /* element offsets into the flat fp32 LoRA buffers: A [in][rank], B [rank][out] */
+} sam3b_lora_entry;
+
+typedef struct sam3b_vit sam3b_vit; /* opaque host object; owns no device memory */
+
+int sam3b_vit_create(const sam3b_vit_config* cfg, sam3b_vit** out);
+void sam3b_vit_destroy(sam3b_vit* v);
+int64_t sam3b_vit_weight_bytes(const sam3b_vit* v);
+int64_t sam3b_vit_workspace_bytes(sam3b_vit* v, int32_t batch, int32_t training);
+int64_t sam3b_vit_lora_numel(const sam3b_vit* v);
+int32_t sam3b_vit_lora_count(const sam3b_vit* v);
+int sam3b_vit_lora_entry(const sam3b_vit* v, int32_t index, sam3b_lora_entry* out);
+/* caller-owned, 1024-byte aligned device buffers */
+int sam3b_vit_bind(sam3b_vit* v, void* weight_buf, int64_t weight_bytes, void* work_buf, int64_t work_bytes,
+                   int32_t batch, int32_t training);
+/* fp32 device tensors in reference state-dict order: patch_embed.proj.weight, pos_embed, ln_pre.weight,
+ * ln_pre.bias, then per block norm1.{weight,bias}, attn.qkv.{weight,bias}, attn.proj.{weight,bias},
+ * norm2.{weight,bias}, mlp.fc1.{weight,bias}, mlp.fc2.{weight,bias}  (4 + 12*depth pointers, host array) */
+int sam3b_vit_load_base(sam3b_vit* v, const float* const* tensors, int32_t n_tensors, void* stream);
+/* img: fp32 NCHW [batch][C][S][S]; lora_flat: flat fp32 adapters; out: fp32 NCHW [batch][D][G][G] */
+int sam3b_vit_forward(sam3b_vit* v, const float* img, int32_t batch, const float* lora_flat, float* out_nchw,
+                      int32_t save_for_backward, void* stream);
+/* gout: dLoss/dout fp32 NCHW; lora_grad_flat: flat fp32 gradients (overwritten, same layout as lora_flat) */
+int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

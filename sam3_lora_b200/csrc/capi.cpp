@@ -4,6 +4,7 @@
 #include "common.h"
 #include "attn.cuh"
 #include "elementwise.cuh"
+#include "engine.h"
 #include "gemm.cuh"
 
 using namespace sam3b;
@@ -99,6 +100,64 @@ int sam3b_lora_unpack_grads(const sam3b_lora_site* site, const float* dA_pack, c
 int sam3b_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                      float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
   return adamw_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
+struct sam3b_vit { VitEngine* eng; };
+
+int sam3b_vit_create(const sam3b_vit_config* c, sam3b_vit** out) {
+  if (!c || !out) return fail(-1, "sam3b_vit_create: null argument");
+  if (c->n_global < 0 || c->n_global > 16) return fail(-1, "sam3b_vit_create: n_global %d", c->n_global);
+  if (c->embed_dim != c->num_heads * 64) return fail(-1, "sam3b_vit_create: head_dim must be 64");
+  if (c->img_size % c->patch_size != 0 || (c->img_size / c->patch_size) % c->window_size != 0)
+    return fail(-1, "sam3b_vit_create: img/patch/window sizes do not tile");
+  if (c->lora_rank < 0 || c->lora_rank > 64) return fail(-1, "sam3b_vit_create: lora_rank %d outside [0,64]", c->lora_rank);
+  if ((c->window_size * c->window_size) % 64 != 0) return fail(-1, "sam3b_vit_create: window tokens must be a multiple of 64");
+  if (c->mlp_hidden % 8 != 0) return fail(-1, "sam3b_vit_create: mlp_hidden %% 8 != 0");
+  VitConfig v;
+  v.img_size = c->img_size; v.patch_size = c->patch_size; v.in_chans = c->in_chans; v.embed_dim = c->embed_dim;
+  v.depth = c->depth; v.num_heads = c->num_heads; v.mlp_hidden = c->mlp_hidden; v.window_size = c->window_size;
+  v.global_blocks.assign(c->global_blocks, c->global_blocks + c->n_global);
+  v.pos_side = c->pos_side; v.ln_eps = c->ln_eps; v.rope_theta = c->rope_theta;
+  v.lora_rank = c->lora_rank; v.lora_scaling = c->lora_scaling; v.lora_targets = c->lora_targets;
+  v.dtype = c->dtype; v.max_batch = c->max_batch;
+  *out = new sam3b_vit{new VitEngine(v)};
+  return 0;
+}
+void sam3b_vit_destroy(sam3b_vit* v) {
+  if (v) { delete v->eng; delete v; }
+}
+int64_t sam3b_vit_weight_bytes(const sam3b_vit* v) { return v ? v->eng->weight_bytes() : -1; }
+int64_t sam3b_vit_workspace_bytes(sam3b_vit* v, int32_t batch, int32_t training) {
+  return v ? v->eng->workspace_bytes(batch, training != 0) : -1;
+}
+int64_t sam3b_vit_lora_numel(const sam3b_vit* v) { return v ? v->eng->lora_numel() : -1; }
+int32_t sam3b_vit_lora_count(const sam3b_vit* v) { return v ? (int32_t)v->eng->lora_entries().size() : -1; }
+int sam3b_vit_lora_entry(const sam3b_vit* v, int32_t index, sam3b_lora_entry* out) {
+  if (!v || !out) return fail(-1, "sam3b_vit_lora_entry: null argument");
+  const auto& es = v->eng->lora_entries();
+  if (index < 0 || index >= (int32_t)es.size()) return fail(-1, "sam3b_vit_lora_entry: index %d out of range", index);
+  const LoraEntry& e = es[index];
+  out->block = e.block; out->target = e.target; out->in = e.in; out->out = e.out; out->rank = e.rank;
+  out->a_off = e.a_off; out->b_off = e.b_off;
+  return 0;
+}
+int sam3b_vit_bind(sam3b_vit* v, void* weight_buf, int64_t weight_bytes, void* work_buf, int64_t work_bytes,
+                   int32_t batch, int32_t training) {
+  if (!v) return fail(-1, "sam3b_vit_bind: null handle");
+  return v->eng->bind(weight_buf, weight_bytes, work_buf, work_bytes, batch, training != 0);
+}
+int sam3b_vit_load_base(sam3b_vit* v, const float* const* tensors, int32_t n_tensors, void* stream) {
+  if (!v || !tensors) return fail(-1, "sam3b_vit_load_base: null argument");
+  return v->eng->load_base(tensors, n_tensors, static_cast<cudaStream_t>(stream));
+}
+int sam3b_vit_forward(sam3b_vit* v, const float* img, int32_t batch, const float* lora_flat, float* out_nchw,
+                      int32_t save_for_backward, void* stream) {
+  if (!v || !img) return fail(-1, "sam3b_vit_forward: null argument");
+  return v->eng->forward(img, batch, lora_flat, out_nchw, save_for_backward != 0, static_cast<cudaStream_t>(stream));
+}
+int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, void* stream) {
+  if (!v) return fail(-1, "sam3b_vit_backward: null handle");
+  return v->eng->backward(gout_nchw, lora_grad_flat, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -21,6 +21,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 template <int DT>
+__device__ __forceinline__ uint16_t to16(float v) {
+  if constexpr (DT == 0) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  else { __nv_bfloat16 h = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+}
+
+template <int DT>
 __device__ __forceinline__ uint2 pack4(float a, float b, float c, float d) {
   uint2 u;
   u.x = pack2<DT>(a, b);
@@ -241,11 +247,6 @@ struct PackArgs {
   uint16_t* down_T; uint16_t* w_ext; int64_t ldw; uint16_t* up_pack; uint16_t* wt_ext; int64_t ldwt;
 };
 template <int DT>
-__device__ __forceinline__ uint16_t to16(float v) {
-  if constexpr (DT == 0) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
-  else { __nv_bfloat16 h = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
-}
-template <int DT>
 __global__ void __launch_bounds__(256) lora_pack_kernel(const PackArgs a) {
   const LoraSite& s = a.s;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -309,6 +310,76 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+
+template <int VPT>
+__global__ void __launch_bounds__(256) ln_fwd_f32_kernel(const float* x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, int rows, float* y) {
+  constexpr int D = 128 * VPT;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * D);
+  float4 v[VPT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    v[i] = xr[lane + i * 32];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mu = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rs = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float4* yr = reinterpret_cast<float4*>(y + (int64_t)row * D);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const float4 g = __ldg(g4 + lane + i * 32), b = __ldg(b4 + lane + i * 32);
+    yr[lane + i * 32] = make_float4((v[i].x - mu) * rs * g.x + b.x, (v[i].y - mu) * rs * g.y + b.y,
+                                    (v[i].z - mu) * rs * g.z + b.z, (v[i].w - mu) * rs * g.w + b.w);
+  }
+}
+
+// frozen weight cast (+ transpose through a 32x33 smem tile)
+template <int DT>
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ W, int N, int K, uint16_t* dst,
+                                                          int64_t ld, int transpose) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + tx;
+    tile[i][tx] = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.f;
+  }
+  __syncthreads();
+  if (!transpose) {
+    for (int i = ty; i < 32; i += 8) {
+      const int n = n0 + i, k = k0 + tx;
+      if (n < N && k < K) dst[(int64_t)n * ld + k] = to16<DT>(tile[i][tx]);
+    }
+  } else {
+    for (int i = ty; i < 32; i += 8) {
+      const int k = k0 + i, n = n0 + tx;
+      if (n < N && k < K) dst[(int64_t)k * ld + n] = to16<DT>(tile[tx][i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) build_pos_table_kernel(const float* __restrict__ pos, int side, int G, int ws,
+                                                              int D, float* __restrict__ out) {
+  const int t = blockIdx.x;
+  const int nwx = G / ws;
+  const int win = t / (ws * ws), in = t % (ws * ws);
+  const int pi = (win / nwx) * ws + in / ws, pj = (win % nwx) * ws + in % ws;
+  const float* src = pos + (int64_t)(1 + (pi % side) * side + (pj % side)) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) out[(int64_t)t * D + d] = src[d];
+}
+
 template <typename F>
 int dispatch_vpt(int D, F&& f) {
   switch (D) {
@@ -350,6 +421,32 @@ int layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const float* m
     SAM3B_CHECK_CUDA(cudaGetLastError());
     return 0;
   });
+}
+
+
+int layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, float eps, int rows, int D, float* y32,
+                      cudaStream_t s) {
+  const int blocks = (rows + 7) / 8;
+  return dispatch_vpt(D, [&](auto vpt) -> int {
+    constexpr int V = decltype(vpt)::value;
+    ln_fwd_f32_kernel<V><<<blocks, 256, 0, s>>>(x, gamma, beta, eps, rows, y32);
+    SAM3B_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  });
+}
+
+int pack_weight(const float* W, int N, int K, void* dst16, int64_t ld, int transpose, int dtype, cudaStream_t s) {
+  dim3 grid((K + 31) / 32, (N + 31) / 32);
+  if (dtype == 0) pack_weight_kernel<0><<<grid, 256, 0, s>>>(W, N, K, (uint16_t*)dst16, ld, transpose);
+  else pack_weight_kernel<1><<<grid, 256, 0, s>>>(W, N, K, (uint16_t*)dst16, ld, transpose);
+  SAM3B_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int build_pos_table(const float* pos_embed, int side, int G, int ws, int D, float* out, cudaStream_t s) {
+  build_pos_table_kernel<<<G * G, 256, 0, s>>>(pos_embed, side, G, ws, D, out);
+  SAM3B_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s) {

@@ -16,6 +16,18 @@ int layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const float* m
                   const float* gamma, const float* dres, int rows, int D, float* dx, void* dx16, int64_t lddx16,
                   int dtype, cudaStream_t s);
 
+// y32[row][0..D) = LayerNorm(x[row]) * gamma + beta in fp32 (ln_pre feeding the fp32 residual stream,
+// vitdet.py:833).  In-place (y32 == x) is allowed.
+int layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, float eps, int rows, int D, float* y32,
+                      cudaStream_t s);
+
+// Frozen-weight packing: W fp32 [N][K] -> 16-bit dst[n][k] (ld) or, transposed, dst[k][n] (ld).
+int pack_weight(const float* W, int N, int K, void* dst16, int64_t ld, int transpose, int dtype, cudaStream_t s);
+
+// Tiled absolute position table in window-major token order (get_abs_pos tiling, vitdet.py:199-222):
+// out[t][:] = pos_embed[1 + (pi % side)*side + (pj % side)][:] for token t at patch (pi, pj).
+int build_pos_table(const float* pos_embed, int side, int G, int ws, int D, float* out, cudaStream_t s);
+
 // y16[row][0..D) = (16-bit) x[row][0..D)
 int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s);
 
