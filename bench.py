@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — SAM3 ViT trunk + rank-16 LoRA training throughput (images/sec) on B200.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # this repo (native sm_100a path)
+    python bench.py --impl reference --steps 2 --warmup 1         # reference arithmetic on the host CPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W    # one rank per GPU, weak scaling
+
+A "step" is one pass of the hot path over one batch: trunk forward + backward to the LoRA
+adapters (q,k,v,out,fc1,fc2, r=16, alpha=32) + [N>1: one all-reduce of the flat LoRA gradient] +
+AdamW, batch 8 x 3x1008x1008 per GPU (BASELINE.json configs[1]; "1024 px" is the source size, the
+model computes at 1008).  `value` is timed with the batch resident in HBM;
+`e2e` goes through the public API (vit.ViT + lora_layers + autograd) with the batch copied from
+pinned host memory and the loss read back every step.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "SAM3 ViT-L r=16 LoRA train images/sec @1024px"
+# algorithmic GFLOP per image: 2*M*N*K per GEMM, no recompute, frozen base (no wgrad)
+GF_ATTN_GEMM_TRAIN = 5522.8 + 130.5     # qkv/proj fwd+dgrad + 3.5x SDPA + r=16 q,k,v,o adapters
+GF_TRUNK_TRAIN = 11965.0 + 130.5 + 183.5  # whole trunk train step + adapters on q,k,v,o,fc1,fc2
+
+
+def read_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"burst": d.get("bf16_tflops"), "sustained": d.get("bf16_tflops_sustained"), "hbm": d.get("hbm_gbs"),
+                "source": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, power) if p > 300] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference arithmetic (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_unit_seconds(reps: int, warm: int):
+    """Times one image through the trunk's repeating 4-block unit (3 window blocks + 1 global block,
+    full width, r=16 adapters on q,k,v,out,fc1,fc2), forward + backward to the adapters, PyTorch CPU fp32,
+    all host threads.  The 32-block trunk is 8 such units (+ patch embed, < 0.2 % of the FLOPs)."""
+    import torch
+
+    from oracle import vit_oracle as O
+
+    cfg = O.ViTConfig(depth=4, global_att_blocks=(3,))
+    spec = O.LoRASpec(rank=16, alpha=32.0)
+    params = O.make_params(cfg, spec, seed=0)
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(1, 3, 1008, 1008, generator=g)
+    gout = torch.randn(1, 1024, 72, 72, generator=g) * 0.01
+    times = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        O.train_step_reference(img, params, cfg, spec, gout)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def cpu_line(times, cores, steps, warmup, kind="port"):
+    t = statistics.mean(times)
+    ips = 1.0 / (8.0 * t)
+    return ips, {"value": ips, "unit": "images/sec", "cores": cores, "kind": kind,
+                 "sample": f"1 image x 4-block unit (3 window + 1 global, D=1024, r=16 q/k/v/o/fc1/fc2 adapters) fwd+bwd, "
+                           f"{len(times)} timed passes of {t:.2f} s; images/sec = 1 / (8 units x pass time)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, cores = cpu_unit_seconds(max(1, args.steps), max(0, min(args.warmup, 1)))
+    ips, cb = cpu_line(times, cores, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cpu=True),
+        "cpu_baseline": cb,
+        "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cpu=False):
+    return {"workload": "SAM3 ViT trunk (32 blocks, D=1024, 16 heads, 24x24 windows + 4 global blocks, 1008x1008 compute "
+                        "resolution) forward+backward with rank-16 LoRA (alpha 32, dropout 0) on q,k,v,out,fc1,fc2, AdamW on the "
+                        "adapters; full_lora_config.yaml shape at r=16",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * (1 if cpu else args.gpus), "image": "3x1008x1008",
+            "parallelism": f"dp{args.gpus}", "l2_policy": "per-step working set (>50 GB of activations) exceeds the 126 MB L2",
+            "depth": args.depth}
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from sam3_lora_b200 import _lib as L
+    from sam3_lora_b200.lora_layers import LoRAConfig, apply_lora_to_model, count_parameters, get_lora_parameters
+    from sam3_lora_b200.vit import ViT
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the native path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    dt = torch.float16 if args.dtype == "float16" else torch.bfloat16
+    B = args.batch
+
+    torch.manual_seed(0)
+    globals_ = tuple(i for i in (7, 15, 23, 31) if i < args.depth) or (args.depth - 1,)
+    model = ViT(depth=args.depth, global_att_blocks=globals_, operand_dtype=dt, max_batch=B)
+    apply_lora_to_model(model, LoRAConfig(rank=args.rank, alpha=2 * args.rank, dropout=0.0,
+                                          target_modules=["q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2"]))
+    for p in get_lora_parameters(model):  # non-zero B so every gradient is exercised
+        if p.shape[0] == args.rank:
+            torch.nn.init.normal_(p, std=0.02)
+    model = model.to(dev)
+    model.train()
+    counts = count_parameters(model)
+
+    # synthetic COCO-shaped batch: uint8 RGB noise, normalised like the reference loader (mean .5, std .5)
+    rng = np.random.default_rng(rank)
+    host = torch.from_numpy(((rng.integers(0, 256, size=(B, 3, 1008, 1008), dtype=np.uint8).astype(np.float32) / 255.0) - 0.5)
+                            / 0.5).pin_memory()
+    gout = torch.randn(B, 1024, 72, 72, device=dev) * 1e-3
+    images = host.to(dev, non_blocking=True)
+
+    # -------- device-resident step (value) --------
+    feats = model(images)[0]            # builds engine, packs weights
+    flat = model.flat_lora()
+    gflat = torch.zeros_like(flat)
+    m_buf, v_buf = torch.zeros_like(flat), torch.zeros_like(flat)
+    eng = model._engine
+    step_no = [0]
+
+    def native_step():
+        out = torch.empty(B, 1024, 72, 72, device=dev)
+        eng.forward(images, flat, out, save_for_backward=True)
+        eng.backward(gout, gflat)
+        if world > 1:
+            dist.all_reduce(gflat)
+        step_no[0] += 1
+        L.adamw_step(flat, gflat, m_buf, v_buf, args.lr, 0.9, 0.999, 1e-8, 0.01, step_no[0], 1.0 / world)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        native_step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        native_step()
+    e1.record()
+    sync_all()
+    launches = (L.launch_count() - n0) // args.steps
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item()
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world / (ms_step / 1000.0)
+
+    # -------- end-to-end step through the public API (e2e) --------
+    params = model.lora_parameters()
+    if world > 1:
+        model.grad_hook = lambda g: dist.all_reduce(g)
+    opt = torch.optim.AdamW(params, lr=args.lr, weight_decay=0.01, fused=True)
+    dev_img = torch.empty_like(images)
+
+    def e2e_step():
+        dev_img.copy_(host, non_blocking=True)         # H2D from pinned memory, every step
+        f = model(dev_img)[0]
+        loss = (f * gout).sum()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            for p in params:
+                p.grad.mul_(1.0 / world)
+        opt.step()
+        return loss.item()                              # D2H read of the step's loss
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    sync_all()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    t1.record()
+    sync_all()
+    ms2 = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = B * world / (ms2.item() / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # -------- roofline of the dominant kernel: the tcgen05 GEMM (fc1 forward shape, GELU epilogue) --------
+    peaks = read_peaks()
+    M, N, K = B * 5184, 4736, 1024 + 64
+    A = (torch.randn(M, K, device=dev) * 0.5).to(dt)
+    W = (torch.randn(N, K, device=dev) * 0.02).to(dt)
+    H = torch.empty(M, N, device=dev, dtype=dt)
+    G = torch.empty(M, N + 64, device=dev, dtype=dt)
+    bias = torch.zeros(N, device=dev)
+    for _ in range(3):
+        L.gemm(A, W, H, epilogue=L.EPI_GELU, bias=bias, C2=G)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 20
+    k0.record()
+    for _ in range(iters):
+        L.gemm(A, W, H, epilogue=L.EPI_GELU, bias=bias, C2=G)
+    k1.record()
+    torch.cuda.synchronize()
+    kms = k0.elapsed_time(k1) / iters
+    achieved = 2.0 * M * N * K / kms / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "gemm_traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN=256, EPI_GELU> M=%d N=%d K=%d" % (M, N, K),
+                "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s", "frac": achieved / peaks["burst"],
+                "peak_source": peaks["source"] + " cuBLAS bf16 burst", "traffic": traffic,
+                "algorithmic_bytes": M * K * 2 + N * K * 2 + M * N * 2 * 2,
+                "step_trunk_tflops": value * GF_TRUNK_TRAIN / 1e3,
+                "step_trunk_frac_of_sustained": value * GF_TRUNK_TRAIN / 1e3 / peaks["sustained"],
+                "attn_gemm_roofline_frac": value / world * GF_ATTN_GEMM_TRAIN / 1e3 / peaks["sustained"]}
+
+    # -------- CPU baseline beside it (rank 0, N=1 only) --------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        times, cores = cpu_unit_seconds(2, 1)
+        _, cpu_baseline = cpu_line(times, cores, args.steps, args.warmup)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16" if dt == torch.float16 else "bf16", "data": "synthetic",
+        "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": host.numel() * 4 * 1, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms2.item()},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "trainable_parameters": counts["trainable_parameters"],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU")
+    ap.add_argument("--depth", type=int, default=32, help="trunk depth (32 = SAM3; smaller only for debugging)")
+    ap.add_argument("--rank", type=int, default=16)
+    ap.add_argument("--dtype", default="float16", choices=["float16", "bfloat16"],
+                    help="tensor-core operand format (fp32 accumulate, fp32 residual stream)")
+    ap.add_argument("--lr", type=float, default=5e-5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,8 @@ extern "C" {
 
 const char* sam3b_last_error(void);
 int sam3b_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (all of them are ours) */
+int64_t sam3b_launch_count(void);
 
 /* C[M][N] = epilogue(alpha * A[M][K] . B[N][K]^T), 16-bit operands, fp32 accumulation in TMEM. */
 typedef struct sam3b_gemm_desc {

@@ -55,6 +55,7 @@ def load() -> C.CDLL:
     lib = C.CDLL(str(path))
     lib.sam3b_last_error.restype = C.c_char_p
     lib.sam3b_abi_version.restype = C.c_int
+    lib.sam3b_launch_count.restype = C.c_int64
     lib.sam3b_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.sam3b_gemm.restype = C.c_int
     _declare_optional(lib)
@@ -67,6 +68,10 @@ def _declare_optional(lib: C.CDLL) -> None:
     from . import _abi  # noqa: PLC0415  (keeps this file small)
 
     _abi.declare(lib)
+
+
+def launch_count() -> int:
+    return int(load().sam3b_launch_count())
 
 
 def check(rc: int) -> None:

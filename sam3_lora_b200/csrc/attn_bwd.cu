@@ -394,9 +394,9 @@ static int launch_bwd(const AttnBwdArgs& a, const BwdParams& p, const CUtensorMa
   const int nseg = a.tokens / a.seg_len;
   dim3 grid(p.tiles * nseg, a.heads);
   attn_bwd_dkdv_kernel<DT><<<grid, 192, DKDV_SMEM, stream>>>(tmT, tmI, tmdO64, p);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   attn_bwd_dq_kernel<DT><<<grid, 192, DQ_SMEM, stream>>>(tmT, tmI, tmdO128, p);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 

@@ -273,7 +273,7 @@ int attn_fwd_launch(const AttnFwdArgs& a, cudaStream_t stream) {
       attr_set = true;
     }
     kern<<<grid, 192, FWD_SMEM, stream>>>(tmQ, tmKV, p);
-    SAM3B_CHECK_CUDA(cudaGetLastError());
+    SAM3B_LAUNCHED();
     return 0;
   };
   return a.dtype == 0 ? launch(attn_fwd_kernel<0>) : launch(attn_fwd_kernel<1>);

@@ -13,6 +13,7 @@ extern "C" {
 
 const char* sam3b_last_error(void) { return last_error_message(); }
 int sam3b_abi_version(void) { return SAM3B_ABI_VERSION; }
+int64_t sam3b_launch_count(void) { return launch_count(); }
 
 int sam3b_gemm(const sam3b_gemm_desc* d, void* stream) {
   if (!d) return fail(-1, "sam3b_gemm: null descriptor");

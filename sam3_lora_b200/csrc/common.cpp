@@ -1,6 +1,7 @@
 #include "common.h"
 
 #include <cstdarg>
+#include <atomic>
 #include <cstdio>
 #include <cudaTypedefs.h>
 
@@ -52,6 +53,10 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
   return 0;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int n = [] {

@@ -20,6 +20,13 @@ const char* last_error_message();
                            __LINE__);                                                              \
   } while (0)
 
+// after every kernel launch: check the launch and count it (sam3b_launch_count(), used by bench.py's gpu_launches)
+#define SAM3B_LAUNCHED()                                   \
+  do {                                                     \
+    SAM3B_CHECK_CUDA(cudaGetLastError());                  \
+    ::sam3b::count_launch();                               \
+  } while (0)
+
 #define SAM3B_REQUIRE(cond, ...)                                  \
   do {                                                            \
     if (!(cond)) return ::sam3b::fail(-1, __VA_ARGS__);           \
@@ -32,5 +39,7 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
                  uint32_t box_rows, uint32_t box_cols, int elem_bytes = 2);
 
 int num_sms();
+void count_launch();
+long long launch_count();
 
 }  // namespace sam3b

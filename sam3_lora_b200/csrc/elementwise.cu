@@ -402,7 +402,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
     constexpr int V = decltype(vpt)::value;
     if (dtype == 0) ln_fwd_kernel<V, 0><<<blocks, 256, 0, s>>>(x, gamma, beta, eps, rows, (uint16_t*)y16, ldy, mean, rstd);
     else ln_fwd_kernel<V, 1><<<blocks, 256, 0, s>>>(x, gamma, beta, eps, rows, (uint16_t*)y16, ldy, mean, rstd);
-    SAM3B_CHECK_CUDA(cudaGetLastError());
+    SAM3B_LAUNCHED();
     return 0;
   });
 }
@@ -418,7 +418,7 @@ int layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const float* m
       ln_bwd_kernel<V, 0><<<blocks, 256, 0, s>>>((const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16);
     else
       ln_bwd_kernel<V, 1><<<blocks, 256, 0, s>>>((const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16);
-    SAM3B_CHECK_CUDA(cudaGetLastError());
+    SAM3B_LAUNCHED();
     return 0;
   });
 }
@@ -430,7 +430,7 @@ int layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, flo
   return dispatch_vpt(D, [&](auto vpt) -> int {
     constexpr int V = decltype(vpt)::value;
     ln_fwd_f32_kernel<V><<<blocks, 256, 0, s>>>(x, gamma, beta, eps, rows, y32);
-    SAM3B_CHECK_CUDA(cudaGetLastError());
+    SAM3B_LAUNCHED();
     return 0;
   });
 }
@@ -439,13 +439,13 @@ int pack_weight(const float* W, int N, int K, void* dst16, int64_t ld, int trans
   dim3 grid((K + 31) / 32, (N + 31) / 32);
   if (dtype == 0) pack_weight_kernel<0><<<grid, 256, 0, s>>>(W, N, K, (uint16_t*)dst16, ld, transpose);
   else pack_weight_kernel<1><<<grid, 256, 0, s>>>(W, N, K, (uint16_t*)dst16, ld, transpose);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
 int build_pos_table(const float* pos_embed, int side, int G, int ws, int D, float* out, cudaStream_t s) {
   build_pos_table_kernel<<<G * G, 256, 0, s>>>(pos_embed, side, G, ws, D, out);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
@@ -455,7 +455,7 @@ int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dt
   const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == 0) cast_rows_kernel<0><<<blocks, 256, 0, s>>>(x, rows, D, (uint16_t*)y16, ldy);
   else cast_rows_kernel<1><<<blocks, 256, 0, s>>>(x, rows, D, (uint16_t*)y16, ldy);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
@@ -466,7 +466,7 @@ int attn_delta(const void* dO, int64_t lddo, const void* O, int64_t ldo, int row
   const int blocks = (int)((threads + 255) / 256);
   if (dtype == 0) attn_delta_kernel<0><<<blocks, 256, 0, s>>>((const uint16_t*)dO, lddo, (const uint16_t*)O, ldo, rows, heads, delta);
   else attn_delta_kernel<1><<<blocks, 256, 0, s>>>((const uint16_t*)dO, lddo, (const uint16_t*)O, ldo, rows, heads, delta);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
@@ -479,7 +479,7 @@ int patch_gather(const float* img, int B, int C, int Himg, int Wimg, int P, int 
   const int tokens = B * G * G;
   if (dtype == 0) patch_gather_kernel<0><<<tokens, 128, 0, s>>>(img, C, Himg, Wimg, P, ws, G, (uint16_t*)out16, ldo, Kpad);
   else patch_gather_kernel<1><<<tokens, 128, 0, s>>>(img, C, Himg, Wimg, P, ws, G, (uint16_t*)out16, ldo, Kpad);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
@@ -487,7 +487,7 @@ int tokens_to_nchw(const float* x, int B, int G, int ws, int D, float* out, cuda
   SAM3B_REQUIRE(D % 32 == 0 && G % ws == 0, "tokens_to_nchw: D %% 32, G %% ws");
   dim3 grid((G * G + 31) / 32, D / 32, B);
   tokens_to_nchw_kernel<<<grid, 256, 0, s>>>(x, G, ws, D, out);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
@@ -497,7 +497,7 @@ int nchw_to_tokens(const float* g, int B, int G, int ws, int D, float* dx, void*
   dim3 grid((G * G + 31) / 32, D / 32, B);
   if (dtype == 0) nchw_to_tokens_kernel<0><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16);
   else nchw_to_tokens_kernel<1><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
@@ -509,7 +509,7 @@ int lora_pack(const LoraSite& site, void* down_T, void* w_ext, int64_t ldw, void
   const int blocks = (int)std::min<int64_t>((work + 255) / 256, 1024);
   if (dtype == 0) lora_pack_kernel<0><<<blocks, 256, 0, s>>>(a);
   else lora_pack_kernel<1><<<blocks, 256, 0, s>>>(a);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
@@ -521,7 +521,7 @@ int lora_unpack_grads(const LoraSite& site, const float* dA_pack, const float* d
   const int64_t work = (int64_t)site.r * std::max(site.in, site.out_total);
   const int blocks = (int)std::min<int64_t>((work + 255) / 256, 512);
   lora_unpack_kernel<<<blocks, 256, 0, s>>>(a);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
@@ -532,7 +532,7 @@ int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8);
   adamw_kernel<<<blocks, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 

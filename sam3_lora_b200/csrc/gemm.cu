@@ -326,7 +326,7 @@ static int launch_one(const GemmArgs& a, const GemmParams& p, cudaStream_t strea
   int ctas = a.max_ctas > 0 ? a.max_ctas : num_sms();
   if (ctas > total) ctas = total;
   kern<<<ctas, 256, Cfg::SMEM, stream>>>(tmA, tmB, p);
-  SAM3B_CHECK_CUDA(cudaGetLastError());
+  SAM3B_LAUNCHED();
   return 0;
 }
 
@@ -339,7 +339,8 @@ static int launch_dt(const GemmArgs& a, const GemmParams& p, cudaStream_t stream
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   SAM3B_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
   SAM3B_REQUIRE(a.N % 8 == 0, "gemm: N=%d must be a multiple of 8", a.N);
-  SAM3B_REQUIRE(a.K % 16 == 0, "gemm: K=%d must be a multiple of 16", a.K);
+  // K needs no alignment: TMA zero-fills out-of-bounds columns/rows and the last k-block issues
+  // ceil(K_rem/16) MMAs over them.
   SAM3B_REQUIRE(a.dtype == 0 || a.dtype == 1, "gemm: dtype %d (0 fp16, 1 bf16)", a.dtype);
   SAM3B_REQUIRE(a.A && a.B && a.C, "gemm: null operand");
   SAM3B_REQUIRE(a.a_mn == a.b_mn, "gemm: mixed operand majors are not instantiated");
