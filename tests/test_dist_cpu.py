@@ -1,0 +1,61 @@
+"""N>1 host logic on CPU: gloo, world_size 2 (rendezvous on 127.0.0.1)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sam3_lora_b200.dist import LoRAGradAllReducer, shard_indices
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from sam3_lora_b200.dist import init_from_env
+
+    r, _, w = init_from_env("gloo")
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    red = LoRAGradAllReducer()
+    red(flat)
+    expect = torch.arange(1000, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    ok = torch.allclose(flat, expect)
+    # summed (not averaged) variant + one collective per call
+    flat2 = torch.ones(10) * (rank + 1)
+    LoRAGradAllReducer(average=False)(flat2)
+    ok = ok and torch.allclose(flat2, torch.ones(10) * sum(range(1, world + 1))) and red.calls == 1 and red.bytes == 4000
+    idx = shard_indices(10, r, w, epoch=3)
+    gathered = [None] * w
+    dist.all_gather_object(gathered, idx)
+    q.put((rank, bool(ok), gathered))
+    dist.destroy_process_group()
+
+
+def test_lora_grad_allreduce_and_sharding_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, gathered in res:
+        assert ok, rank
+        a, b = gathered
+        assert len(a) == len(b) == 5 and sorted(a + b) == list(range(10))   # disjoint cover of the dataset
+
+
+def test_shard_indices_padding_and_determinism():
+    parts = [shard_indices(7, r, 4, epoch=1) for r in range(4)]
+    assert all(len(p) == 2 for p in parts)
+    assert set(sum(parts, [])) == set(range(7))
+    assert shard_indices(7, 1, 4, epoch=1) == parts[1]
+    assert shard_indices(7, 1, 4, epoch=2) != parts[1]
+    assert shard_indices(6, 0, 2, shuffle=False) == [0, 2, 4]
+
+
+def test_allreducer_is_noop_without_process_group():
+    t = torch.ones(4)
+    assert LoRAGradAllReducer()(t) is t and torch.equal(t, torch.ones(4))
