@@ -181,11 +181,14 @@ def run_native(args):
     dt = torch.float16 if args.dtype == "float16" else torch.bfloat16
     B = args.batch
 
+    import contextlib
+
     torch.manual_seed(0)
     globals_ = tuple(i for i in (7, 15, 23, 31) if i < args.depth) or (args.depth - 1,)
     model = ViT(depth=args.depth, global_att_blocks=globals_, operand_dtype=dt, max_batch=B)
-    apply_lora_to_model(model, LoRAConfig(rank=args.rank, alpha=2 * args.rank, dropout=0.0,
-                                          target_modules=["q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2"]))
+    with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly one JSON line
+        apply_lora_to_model(model, LoRAConfig(rank=args.rank, alpha=2 * args.rank, dropout=0.0,
+                                              target_modules=["q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2"]))
     for p in get_lora_parameters(model):  # non-zero B so every gradient is exercised
         if p.shape[0] == args.rank:
             torch.nn.init.normal_(p, std=0.02)

@@ -246,6 +246,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 5) tmem_dealloc(tmem_base, TCOLS);
 }
 
+// one instantiation (and one cached smem attribute) per operand format
+template <int DT>
+static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const FwdParams& p, dim3 grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAM3B_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr_set = true;
+  }
+  attn_fwd_kernel<DT><<<grid, 192, FWD_SMEM, stream>>>(tmQ, tmKV, p);
+  SAM3B_LAUNCHED();
+  return 0;
+}
+
 }  // namespace
 
 int attn_fwd_launch(const AttnFwdArgs& a, cudaStream_t stream) {
@@ -266,17 +279,7 @@ int attn_fwd_launch(const AttnFwdArgs& a, cudaStream_t stream) {
   p.total_rows = a.tokens;
   const int nseg = a.tokens / a.seg_len;
   dim3 grid(p.q_tiles * nseg, a.heads);
-  auto launch = [&](auto kern) -> int {
-    static bool attr_set = false;
-    if (!attr_set) {
-      SAM3B_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-      attr_set = true;
-    }
-    kern<<<grid, 192, FWD_SMEM, stream>>>(tmQ, tmKV, p);
-    SAM3B_LAUNCHED();
-    return 0;
-  };
-  return a.dtype == 0 ? launch(attn_fwd_kernel<0>) : launch(attn_fwd_kernel<1>);
+  return a.dtype == 0 ? launch_fwd<0>(tmQ, tmKV, p, grid, stream) : launch_fwd<1>(tmQ, tmKV, p, grid, stream);
 }
 
 }  // namespace sam3b
