@@ -15,8 +15,9 @@
 //                   same Q/dO tiles re-used as MN-major B operands.
 //   attn_bwd_dq   : one CTA per (128-query tile, head, segment), loops over 64-key blocks.
 //                   S = Q K^T, dP = dO V^T (thread = query row), dQ += dS K (K tile as MN-major B).
-// Both: warps 0-3 compute, warp 4 TMA, warp 5 MMA issue + TMEM alloc; 256 TMEM columns and
-// <= 100 KB smem so two CTAs share an SM.
+// Both: warps 0-7 compute (two warps per TMEM lane quarter, each owning 32 of the 64 inner columns, so
+// 16 compute warps per SM hide the tcgen05.ld / MUFU latencies), warp 8 TMA, warp 9 MMA issue + TMEM
+// alloc; 256 TMEM columns and <= 100 KB smem so two CTAs share an SM.
 #include "attn.cuh"
 
 #include "common.h"
@@ -57,41 +58,38 @@ __device__ __forceinline__ void store_row_chunk16(uint8_t* row_base, int sw, int
   }
 }
 
-// out[row][col0 + 0..63] = (optionally inverse-rotated) acc * mul, 16-bit
+// out[row][col0 + cc .. col0 + cc + 32) = (optionally inverse-rotated) acc * mul, 16-bit
 template <int DT, bool ROPE>
-__device__ __forceinline__ void store_grad_row(const BwdParams& p, uint32_t taddr, int row, int col0, float mul, bool valid) {
+__device__ __forceinline__ void store_grad_chunk(const BwdParams& p, uint32_t taddr, int row, int col0, int cc, float mul,
+                                                 bool valid) {
+  uint32_t t[32];
+  tmem_ld_x32(taddr + cc, t);
+  tmem_ld_wait();
+  if (!valid) return;
+  float v[32];
 #pragma unroll
-  for (int cc = 0; cc < HD; cc += 32) {
-    uint32_t t[32];
-    tmem_ld_x32(taddr + cc, t);
-    tmem_ld_wait();
-    if (valid) {
-      float v[32];
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]) * mul;
+  if constexpr (ROPE) {
+    const float4* t4 = reinterpret_cast<const float4*>(p.rope + (int64_t)(row % p.rope_period) * 32 + (cc >> 1));
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]) * mul;
-      if constexpr (ROPE) {
-        const float4* t4 = reinterpret_cast<const float4*>(p.rope + (int64_t)(row % p.rope_period) * 32 + (cc >> 1));
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 cs = __ldg(t4 + q);
-          float a0 = v[q * 4], b0 = v[q * 4 + 1], a1 = v[q * 4 + 2], b1 = v[q * 4 + 3];
-          v[q * 4] = a0 * cs.x + b0 * cs.y;
-          v[q * 4 + 1] = -a0 * cs.y + b0 * cs.x;
-          v[q * 4 + 2] = a1 * cs.z + b1 * cs.w;
-          v[q * 4 + 3] = -a1 * cs.w + b1 * cs.z;
-        }
-      }
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dqkv) + (int64_t)row * p.lddqkv + col0 + cc);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack2<DT>(v[q * 8 + 0], v[q * 8 + 1]);
-        u.y = pack2<DT>(v[q * 8 + 2], v[q * 8 + 3]);
-        u.z = pack2<DT>(v[q * 8 + 4], v[q * 8 + 5]);
-        u.w = pack2<DT>(v[q * 8 + 6], v[q * 8 + 7]);
-        dst[q] = u;
-      }
+    for (int q = 0; q < 8; ++q) {
+      float4 cs = __ldg(t4 + q);
+      float a0 = v[q * 4], b0 = v[q * 4 + 1], a1 = v[q * 4 + 2], b1 = v[q * 4 + 3];
+      v[q * 4] = a0 * cs.x + b0 * cs.y;
+      v[q * 4 + 1] = -a0 * cs.y + b0 * cs.x;
+      v[q * 4 + 2] = a1 * cs.z + b1 * cs.w;
+      v[q * 4 + 3] = -a1 * cs.w + b1 * cs.z;
     }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dqkv) + (int64_t)row * p.lddqkv + col0 + cc);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack2<DT>(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack2<DT>(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack2<DT>(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack2<DT>(v[q * 8 + 6], v[q * 8 + 7]);
+    dst[q] = u;
   }
 }
 
@@ -101,7 +99,7 @@ __device__ __forceinline__ void store_grad_row(const BwdParams& p, uint32_t tadd
 constexpr int DKDV_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + 2 * A_BYTES + 2 * 2 * BI * 4 + 128;
 
 template <int DT>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(320, 2)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][64]
                      const __grid_constant__ CUtensorMap tmI,   // qkv, box [64][64]
                      const __grid_constant__ CUtensorMap tmdO,  // dO,  box [64][64]
@@ -132,21 +130,21 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
   const int t_row0 = seg_row0 + tile * BT;
   const int n_blocks = p.L / BI;
 
-  if (warp == 4 && elect_one()) {
+  if (warp == 8 && elect_one()) {
     tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(acc_done, 1);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
+  if (warp == 9) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 64, tm_dV = tmem_base + 128, tm_dK = tmem_base + 192;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       mbar_arrive_expect_tx(kv_full, 2 * T_BYTES);
       tma_load_2d(sK, &tmT, kv_full, p.D + head * HD, t_row0);
@@ -159,7 +157,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
         tma_load_2d(sdO + st * I_BYTES, &tmdO, &in_full[st], head * HD, seg_row0 + j * BI);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);  // A K-major, B K-major, N=64
       constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1); // A K-major, B MN-major, N=64
@@ -192,8 +190,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
       }
     }
   } else {
-    const int r = threadIdx.x;  // key row inside the tile
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int r = threadIdx.x & 127;   // key row inside the tile == TMEM lane
+    const int cc = (warp >> 2) * 32;   // this warp's half of the 64 inner (query) columns
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c = p.scale_log2;
     uint8_t* p_row = sP + r * 128;
     uint8_t* ds_row = sdS + r * 128;
@@ -201,17 +200,16 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
     for (int j = 0; j < n_blocks; ++j) {
       // stage this block's per-query statistics (threads 0-63: lse2, 64-127: delta)
       float* stat = sStat + (j & 1) * (2 * BI);
-      {
-        const int q = seg_row0 + j * BI + (r & 63);
-        const float* src = (r < 64) ? p.lse2 : p.delta;
-        stat[r] = __ldg(src + (int64_t)q * p.H + head);
+      if (threadIdx.x < 128) {
+        const int q = seg_row0 + j * BI + (threadIdx.x & 63);
+        const float* src = (threadIdx.x < 64) ? p.lse2 : p.delta;
+        stat[threadIdx.x] = __ldg(src + (int64_t)q * p.H + head);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sdp_full, j & 1, 30);
       tc_fence_after();
       if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);  // previous dV/dK MMAs finished reading sP/sdS
-#pragma unroll
-      for (int cc = 0; cc < BI; cc += 32) {
+      {
         uint32_t s[32], d[32];
         tmem_ld_x32(tm_S + lane_off + cc, s);
         tmem_ld_x32(tm_dP + lane_off + cc, d);
@@ -234,12 +232,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
     tc_fence_after();
     const int row = t_row0 + r;
     const bool valid = (tile * BT + r) < p.L && row < p.total_rows;
-    store_grad_row<DT, false>(p, tm_dV + lane_off, row, 2 * p.D + head * HD, 1.f, valid);
-    store_grad_row<DT, true>(p, tm_dK + lane_off, row, p.D + head * HD, p.scale, valid);
+    store_grad_chunk<DT, false>(p, tm_dV + lane_off, row, 2 * p.D + head * HD, cc, 1.f, valid);
+    store_grad_chunk<DT, true>(p, tm_dK + lane_off, row, p.D + head * HD, cc, p.scale, valid);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, TCOLS);
+  if (warp == 9) tmem_dealloc(tmem_base, TCOLS);
 }
 
 // =========================================================================================
@@ -248,7 +246,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
 constexpr int DQ_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + A_BYTES + 128;
 
 template <int DT>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(320, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][64]
                    const __grid_constant__ CUtensorMap tmI,   // qkv, box [64][64]
                    const __grid_constant__ CUtensorMap tmdO,  // dO,  box [128][64]
@@ -277,21 +275,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
   const int t_row0 = seg_row0 + tile * BT;
   const int n_blocks = p.L / BI;
 
-  if (warp == 4 && elect_one()) {
+  if (warp == 8 && elect_one()) {
     tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(ds_full, 128); mbar_init(acc_done, 1);
+    mbar_init(sdp_full, 1); mbar_init(ds_full, 256); mbar_init(acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
+  if (warp == 9) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 64, tm_dQ = tmem_base + 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * T_BYTES);
       tma_load_2d(sQ, &tmT, q_full, head * HD, t_row0);
@@ -304,7 +302,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
         tma_load_2d(sV + st * I_BYTES, &tmI, &in_full[st], 2 * p.D + head * HD, seg_row0 + j * BI);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);
       constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1);
@@ -333,8 +331,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
       }
     }
   } else {
-    const int r = threadIdx.x;  // query row inside the tile
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int r = threadIdx.x & 127;   // query row inside the tile == TMEM lane
+    const int cc = (warp >> 2) * 32;   // this warp's half of the 64 inner (key) columns
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c = p.scale_log2;
     const int row = t_row0 + r;
     const int row_c = min(row, p.total_rows - 1);
@@ -346,8 +345,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
       mbar_wait(sdp_full, j & 1, 30);
       tc_fence_after();
       if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);
-#pragma unroll
-      for (int cc = 0; cc < BI; cc += 32) {
+      {
         uint32_t s[32], d[32];
         tmem_ld_x32(tm_S + lane_off + cc, s);
         tmem_ld_x32(tm_dP + lane_off + cc, d);
@@ -367,11 +365,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
     mbar_wait(acc_done, (n_blocks - 1) & 1, 32);
     tc_fence_after();
     const bool valid = (tile * BT + r) < p.L && row < p.total_rows;
-    store_grad_row<DT, true>(p, tm_dQ + lane_off, row, head * HD, p.scale, valid);
+    store_grad_chunk<DT, true>(p, tm_dQ + lane_off, row, head * HD, cc, p.scale, valid);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, TCOLS);
+  if (warp == 9) tmem_dealloc(tmem_base, TCOLS);
 }
 
 template <typename K>
@@ -393,9 +391,9 @@ static int launch_bwd(const AttnBwdArgs& a, const BwdParams& p, const CUtensorMa
   if (rc) return rc;
   const int nseg = a.tokens / a.seg_len;
   dim3 grid(p.tiles * nseg, a.heads);
-  attn_bwd_dkdv_kernel<DT><<<grid, 192, DKDV_SMEM, stream>>>(tmT, tmI, tmdO64, p);
+  attn_bwd_dkdv_kernel<DT><<<grid, 320, DKDV_SMEM, stream>>>(tmT, tmI, tmdO64, p);
   SAM3B_LAUNCHED();
-  attn_bwd_dq_kernel<DT><<<grid, 192, DQ_SMEM, stream>>>(tmT, tmI, tmdO128, p);
+  attn_bwd_dq_kernel<DT><<<grid, 320, DQ_SMEM, stream>>>(tmT, tmI, tmdO128, p);
   SAM3B_LAUNCHED();
   return 0;
 }

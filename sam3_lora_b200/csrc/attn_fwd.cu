@@ -7,14 +7,18 @@
 // is kept in window-major order, so a window is a contiguous run of L rows ("segment").
 //
 // Layout: qkv [tokens][ld] 16-bit with q at column h*64, k at D + h*64, v at 2D + h*64.
-// One CTA = one (128-query tile, head, segment); 2 CTAs are co-resident per SM (<= 113 KB smem,
-// 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// One CTA = one (128-query tile, head, segment); 2 CTAs co-resident per SM (80 KB smem, 256 TMEM
+// columns each).  Everything that crosses a role boundary is double-buffered so the tensor core
+// works on block j+1 while the softmax warps work on block j:
 //   warps 0-3 : softmax + output (thread t owns query row t == TMEM lane t)
-//   warp  4   : TMA producer (Q once, then K_j / V_j, single-buffered)
-//   warp  5   : MMA issuer + TMEM allocator
-// Per 192-key block j:  S = Q K_j^T (tcgen05, fp32 in TMEM) -> online softmax in registers ->
-// P (16-bit) to 128B-swizzled smem -> PV_j = P V_j (V as MN-major B operand) -> accumulated into
-// the fp32 register copy of O with the running rescale.  Output: O 16-bit, LSE in log2 units.
+//   warp  4   : TMA producer (Q once, then K_j / V_j into 2-stage rings)
+//   warp  5   : MMA issuer + TMEM allocator; issue order S_0, S_1, PV_0, S_2, PV_1, ...
+// Per 64-key block j:  S_j = Q K_j^T (fp32, TMEM buffer j&1) -> one pass over the 64 scores in
+// registers: row max, p = exp2(s*c - m*c), row sum -> P_j (16-bit) into swizzled smem buffer j&1 ->
+// O += P_j V_j accumulated IN TMEM (V tile as MN-major B operand).  The running max only moves when
+// the block max exceeds it by more than 2^8 in the exp2 domain ("lazy rescale"): then the softmax
+// warps rescale the O accumulator in TMEM (tcgen05.ld / st) before publishing P_j.  Output: O
+// 16-bit, LSE in log2 units.
 #include "attn.cuh"
 
 #include "common.h"
@@ -25,16 +29,16 @@ namespace sam3b {
 namespace {
 
 constexpr int HD = 64;
-constexpr int BQ = 128;   // queries per CTA
-constexpr int BKV = 192;  // keys per block: divides 576 and 5184
-constexpr int Q_BYTES = BQ * HD * 2;    // 16 KB
-constexpr int K_BYTES = BKV * HD * 2;   // 24 KB
-constexpr int V_BYTES = BKV * HD * 2;   // 24 KB
-constexpr int P_BYTES = BQ * BKV * 2;   // 48 KB = 3 swizzle atoms of [128][64]
-// 2 CTAs/SM: 2 x (dynamic + 1 KB reserved) must fit the SM's 228 KB, so no alignment slack: the
-// dynamic window is declared 1024-byte aligned and checked at run time.
-constexpr int FWD_SMEM = Q_BYTES + K_BYTES + V_BYTES + P_BYTES + 128 /*barriers*/;
-constexpr int TCOLS = 256;  // S: [0,192)  PV: [192,256)
+constexpr int BQ = 128;  // queries per CTA
+constexpr int BKV = 64;  // keys per block: divides 576 and 5184
+constexpr int Q_BYTES = BQ * HD * 2;   // 16 KB
+constexpr int KV_BYTES = BKV * HD * 2; // 8 KB
+constexpr int P_BYTES = BQ * BKV * 2;  // 16 KB = one swizzle atom [128][64]
+// 2 CTAs/SM: 2 x (dynamic + 1 KB reserved) must fit the SM's 228 KB: no alignment slack, the dynamic
+// window is declared 1024-byte aligned and checked at run time.
+constexpr int FWD_SMEM = Q_BYTES + 4 * KV_BYTES + 2 * P_BYTES + 256 /*barriers*/;
+constexpr int TCOLS = 256;  // S0: [0,64)  S1: [64,128)  O: [128,192)
+constexpr float RESCALE_LOG2 = 8.f;  // p <= 2^8 between rescales: safe in fp16/bf16 and fp32 sums
 
 struct FwdParams {
   int L;          // tokens per segment
@@ -53,19 +57,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // swizzle-128B operands need 1024-byte alignment
   uint8_t* sQ = smem_raw;
-  uint8_t* sK = sQ + Q_BYTES;
-  uint8_t* sV = sK + K_BYTES;
-  uint8_t* sP = sV + V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint8_t* sK = sQ + Q_BYTES;          // 2 stages
+  uint8_t* sV = sK + 2 * KV_BYTES;     // 2 stages
+  uint8_t* sP = sV + 2 * KV_BYTES;     // 2 buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_free = bars + 2;
-  uint64_t* v_full = bars + 3;
-  uint64_t* v_free = bars + 4;
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_free = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_free = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;   // [2]
+  uint64_t* p_full = bars + 11;  // [2]
+  uint64_t* pv_done = bars + 13; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int q_tile = blockIdx.x % p.q_tiles;
@@ -78,8 +82,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 4 && elect_one()) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_free, 1); mbar_init(v_full, 1); mbar_init(v_free, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_free[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_free[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -90,128 +97,135 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_PV = tmem_base + BKV;
+  const uint32_t tmem_O = tmem_base + 2 * BKV;
 
   if (warp == 4) {
+    // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, Q_BYTES);
       tma_load_2d(sQ, &tmQ, q_full, head * HD, q_row0);
       for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
         const int kv_row0 = seg_row0 + j * BKV;
-        if (j > 0) mbar_wait(k_free, (j - 1) & 1, 10);
-        mbar_arrive_expect_tx(k_full, K_BYTES);
-        tma_load_2d(sK, &tmKV, k_full, p.D + head * HD, kv_row0);
-        if (j > 0) mbar_wait(v_free, (j - 1) & 1, 11);
-        mbar_arrive_expect_tx(v_full, V_BYTES);
-        tma_load_2d(sV, &tmKV, v_full, 2 * p.D + head * HD, kv_row0);
+        if (j >= 2) mbar_wait(&k_free[st], ((j - 2) >> 1) & 1, 10);
+        mbar_arrive_expect_tx(&k_full[st], KV_BYTES);
+        tma_load_2d(sK + st * KV_BYTES, &tmKV, &k_full[st], p.D + head * HD, kv_row0);
+        if (j >= 2) mbar_wait(&v_free[st], ((j - 2) >> 1) & 1, 11);
+        mbar_arrive_expect_tx(&v_full[st], KV_BYTES);
+        tma_load_2d(sV + st * KV_BYTES, &tmKV, &v_full[st], 2 * p.D + head * HD, kv_row0);
       }
     }
   } else if (warp == 5) {
+    // ------------------------------ MMA issuer ------------------------------
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, DT, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(BQ, HD, DT, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
-      mbar_wait(q_full, 0, 20);
-      for (int j = 0; j < n_blocks; ++j) {
-        mbar_wait(k_full, j & 1, 21);
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1, 21);
         tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * KV_BYTES);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_f16_ss(tmem_S, make_desc_kmajor(q_addr + k * 32), make_desc_kmajor(k_addr + k * 32), idesc_s, k > 0);
-        umma_commit(s_full);
-        umma_commit(k_free);
-        mbar_wait(p_full, j & 1, 22);
-        mbar_wait(v_full, j & 1, 23);
+          umma_f16_ss(tmem_base + st * BKV, make_desc_kmajor(q_addr + k * 32), make_desc_kmajor(k_addr + k * 32), idesc_s, k > 0);
+        umma_commit(&s_full[st]);
+        umma_commit(&k_free[st]);
+      };
+      mbar_wait(q_full, 0, 20);
+      issue_s(0);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        // S_{j+1} goes out before we block on the softmax of block j (its buffer was consumed when
+        // p_full(j-1) completed, which the previous iteration waited for).
+        if (j + 1 < n_blocks) issue_s(j + 1);
+        mbar_wait(&p_full[st], (j >> 1) & 1, 22);
+        mbar_wait(&v_full[st], (j >> 1) & 1, 23);
         tc_fence_after();
+        const uint32_t p_addr = smem_u32(sP + st * P_BYTES), v_addr = smem_u32(sV + st * KV_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
-          umma_f16_ss(tmem_PV, make_desc_kmajor(p_addr + (k >> 2) * (BQ * 128) + (k & 3) * 32),
-                      make_desc_mnmajor(v_addr + k * 2048, 8192), idesc_pv, k > 0);
-        umma_commit(o_full);
-        umma_commit(v_free);
+          umma_f16_ss(tmem_O, make_desc_kmajor(p_addr + k * 32), make_desc_mnmajor(v_addr + k * 2048, 8192), idesc_pv,
+                      (j > 0 || k > 0));
+        umma_commit(&pv_done[st]);
+        umma_commit(&v_free[st]);
       }
     }
   } else {
     // ------------------------------ softmax / output ------------------------------
     const int r = threadIdx.x;  // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    float o_acc[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
     const float c = p.scale_log2;
-    uint8_t* p_row = sP + r * 128;
+    const float tau = RESCALE_LOG2 / c;  // in raw-score units
+    float m_used = -INFINITY, l_run = 0.f;
     const int sw = r & 7;
 
     for (int j = 0; j < n_blocks; ++j) {
+      const int st = j & 1;
       const int kv_valid = min(BKV, p.L - j * BKV);
-      mbar_wait(s_full, j & 1, 30);
+      mbar_wait(&s_full[st], (j >> 1) & 1, 30);
       tc_fence_after();
-      // pass 1: row max over the valid keys of this block
+      uint32_t s[BKV];
+      {
+        uint32_t a[32], b[32];
+        tmem_ld_x32(tmem_base + lane_off + st * BKV, a);
+        tmem_ld_x32(tmem_base + lane_off + st * BKV + 32, b);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { s[i] = a[i]; s[32 + i] = b[i]; }
+      }
       float m_blk = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < BKV; cc += 32) {
-        uint32_t s[32];
-        tmem_ld_x32(tmem_S + lane_off + cc, s);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (cc + i < kv_valid) m_blk = fmaxf(m_blk, __uint_as_float(s[i]));
-      }
-      const float m_new = fmaxf(m_run, m_blk);
-      const float alpha = exp2f((m_run - m_new) * c);  // exp2(-inf) = 0 on the first block
-      // fold in the previous block's P.V, then rescale
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1, 31);
-        tc_fence_after();
+      for (int i = 0; i < BKV; ++i)
+        if (i < kv_valid) m_blk = fmaxf(m_blk, __uint_as_float(s[i]));
+      const bool need = m_blk > m_used + tau;  // always true on the first block (m_used = -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? m_blk : m_used;
+        const float alpha = exp2f((m_used - m_new) * c);  // 0 on the first block, 1 for rows that keep their max
+        if (j > 0) {
+          // every earlier P.V has landed in the accumulator (MMAs complete in issue order)
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1, 31);
+          tc_fence_after();
 #pragma unroll
-        for (int cc = 0; cc < HD; cc += 32) {
-          uint32_t t[32];
-          tmem_ld_x32(tmem_PV + lane_off + cc, t);
-          tmem_ld_wait();
+          for (int cc = 0; cc < HD; cc += 32) {
+            uint32_t t[32];
+            tmem_ld_x32(tmem_O + lane_off + cc, t);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[cc + i] = (o_acc[cc + i] + __uint_as_float(t[i])) * alpha;
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st_x32(tmem_O + lane_off + cc, t);
+          }
+          tmem_st_wait();
         }
+        l_run *= alpha;
+        m_used = m_new;
       }
-      l_run *= alpha;
-      m_run = m_new;
-      // pass 2: p = exp2(s*c - m*c), write 16-bit P into the swizzled A-operand tile
-      const float mc = m_new * c;
+      // P buffer `st` was last read by P.V of block j-2
+      if (j >= 2) mbar_wait(&pv_done[st], ((j - 2) >> 1) & 1, 32);
+      const float mc = m_used * c;
+      uint8_t* p_row = sP + st * P_BYTES + r * 128;
       float l_blk = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < BKV; cc += 32) {
-        uint32_t s[32];
-        tmem_ld_x32(tmem_S + lane_off + cc, s);
-        tmem_ld_wait();
-        float pv[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = exp2f(__uint_as_float(s[i]) * c - mc);
-          pv[i] = (cc + i < kv_valid) ? e : 0.f;
-        }
-        uint8_t* atom = p_row + (cc >> 6) * (BQ * 128);
-        const int ch0 = (cc & 63) >> 3;  // first 16-byte chunk of this 32-column group inside the atom row
+      for (int q = 0; q < 8; ++q) {
+        float e[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack2<DT>(pv[q * 8 + 0], pv[q * 8 + 1]);
-          u.y = pack2<DT>(pv[q * 8 + 2], pv[q * 8 + 3]);
-          u.z = pack2<DT>(pv[q * 8 + 4], pv[q * 8 + 5]);
-          u.w = pack2<DT>(pv[q * 8 + 6], pv[q * 8 + 7]);
-          // the row sum uses the rounded probabilities that the P.V MMA will actually see
-          float2 f0 = unpack2<DT>(u.x), f1 = unpack2<DT>(u.y), f2 = unpack2<DT>(u.z), f3 = unpack2<DT>(u.w);
-          l_blk += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-          *reinterpret_cast<uint4*>(atom + (((ch0 + q) ^ sw) << 4)) = u;
+        for (int i = 0; i < 8; ++i) {
+          const float v = exp2f(__uint_as_float(s[q * 8 + i]) * c - mc);
+          e[i] = (q * 8 + i < kv_valid) ? v : 0.f;
         }
+        uint4 u;
+        u.x = pack2<DT>(e[0], e[1]); u.y = pack2<DT>(e[2], e[3]); u.z = pack2<DT>(e[4], e[5]); u.w = pack2<DT>(e[6], e[7]);
+        // the row sum uses the rounded probabilities that the P.V MMA will actually see
+        const float2 f0 = unpack2<DT>(u.x), f1 = unpack2<DT>(u.y), f2 = unpack2<DT>(u.z), f3 = unpack2<DT>(u.w);
+        l_blk += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
+        *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) = u;
       }
       l_run += l_blk;
-      tc_fence_before();       // our tcgen05.ld of S complete before the MMA warp overwrites S
+      tc_fence_before();         // our tcgen05.ld/st are ordered before the MMA warp's next tcgen05 ops
       fence_proxy_async_smem();  // st.shared of P visible to the tensor core (async proxy)
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[st]);
     }
-    // last block's P.V
-    mbar_wait(o_full, (n_blocks - 1) & 1, 32);
+    mbar_wait(&pv_done[(n_blocks - 1) & 1], ((n_blocks - 1) >> 1) & 1, 33);
     tc_fence_after();
     const float inv_l = 1.f / l_run;
     const int row = q_row0 + r;
@@ -219,26 +233,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int cc = 0; cc < HD; cc += 32) {
       uint32_t t[32];
-      tmem_ld_x32(tmem_PV + lane_off + cc, t);
+      tmem_ld_x32(tmem_O + lane_off + cc, t);
       tmem_ld_wait();
       if (valid) {
         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + (int64_t)row * p.ldo + head * HD + cc);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 u;
-          u.x = pack2<DT>((o_acc[cc + q * 8 + 0] + __uint_as_float(t[q * 8 + 0])) * inv_l,
-                          (o_acc[cc + q * 8 + 1] + __uint_as_float(t[q * 8 + 1])) * inv_l);
-          u.y = pack2<DT>((o_acc[cc + q * 8 + 2] + __uint_as_float(t[q * 8 + 2])) * inv_l,
-                          (o_acc[cc + q * 8 + 3] + __uint_as_float(t[q * 8 + 3])) * inv_l);
-          u.z = pack2<DT>((o_acc[cc + q * 8 + 4] + __uint_as_float(t[q * 8 + 4])) * inv_l,
-                          (o_acc[cc + q * 8 + 5] + __uint_as_float(t[q * 8 + 5])) * inv_l);
-          u.w = pack2<DT>((o_acc[cc + q * 8 + 6] + __uint_as_float(t[q * 8 + 6])) * inv_l,
-                          (o_acc[cc + q * 8 + 7] + __uint_as_float(t[q * 8 + 7])) * inv_l);
+          u.x = pack2<DT>(__uint_as_float(t[q * 8 + 0]) * inv_l, __uint_as_float(t[q * 8 + 1]) * inv_l);
+          u.y = pack2<DT>(__uint_as_float(t[q * 8 + 2]) * inv_l, __uint_as_float(t[q * 8 + 3]) * inv_l);
+          u.z = pack2<DT>(__uint_as_float(t[q * 8 + 4]) * inv_l, __uint_as_float(t[q * 8 + 5]) * inv_l);
+          u.w = pack2<DT>(__uint_as_float(t[q * 8 + 6]) * inv_l, __uint_as_float(t[q * 8 + 7]) * inv_l);
           dst[q] = u;
         }
       }
     }
-    if (valid) p.lse2[(int64_t)row * p.H + head] = m_run * c + log2f(l_run);
+    if (valid) p.lse2[(int64_t)row * p.H + head] = m_used * c + log2f(l_run);
   }
 
   tc_fence_before();

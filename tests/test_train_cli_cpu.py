@@ -1,0 +1,61 @@
+"""Host logic of the train_sam3_lora_native surface: YAML schema, COCO dataset (polygon + RLE), shapes."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_shipped_configs_have_the_keys_the_native_cli_reads():
+    for name in ("full_lora_config.yaml", "bench_r16_config.yaml", "minimal_lora_config.yaml"):
+        cfg = yaml.safe_load((ROOT / "configs" / name).read_text())
+        assert {"rank", "alpha", "dropout", "target_modules"} <= set(cfg["lora"])
+        assert {"learning_rate", "weight_decay", "data_dir", "batch_size", "num_epochs"} <= set(cfg["training"])
+        assert "output_dir" in cfg["output"]
+    full = yaml.safe_load((ROOT / "configs" / "full_lora_config.yaml").read_text())
+    assert (full["lora"]["rank"], full["lora"]["alpha"], full["training"]["batch_size"]) == (32, 64, 8)
+
+
+def test_synthetic_coco_and_dataset(tmp_path):
+    out = tmp_path / "coco"
+    subprocess.run([sys.executable, str(ROOT / "tools" / "make_synthetic_coco.py"), str(out), "--n-train", "3", "--n-valid", "1",
+                    "--size", "128"], check=True)
+    from sam3_lora_b200.train_native import COCOSegmentDataset, _ann_to_mask, collate
+
+    ds = COCOSegmentDataset(out, "train")
+    assert len(ds) == 3
+    item = ds[0]
+    assert item["image"].shape == (3, 1008, 1008) and item["image"].dtype == torch.float32
+    assert -1.0 <= item["image"].min() and item["image"].max() <= 1.0
+    assert item["mask"].shape == (1, 72, 72) and 0 < item["mask"].sum() < 72 * 72
+    assert isinstance(item["prompt"], str)
+    b = collate([ds[0], ds[1]])
+    assert b["image"].shape == (2, 3, 1008, 1008) and b["mask"].shape == (2, 1, 72, 72) and len(b["prompt"]) == 2
+    # RLE and polygon of the same box agree
+    coco = json.loads((out / "train" / "_annotations.coco.json").read_text())
+    x, y, w, h = 10, 20, 30, 40
+    counts, pos = [], 0
+    for col in range(x, x + w):
+        start = col * 128 + y
+        counts += [start - pos, h]
+        pos = start + h
+    counts.append(128 * 128 - pos)
+    m_rle = _ann_to_mask({"segmentation": {"size": [128, 128], "counts": counts}}, 128, 128)
+    assert m_rle.sum() == w * h and m_rle[y:y + h, x:x + w].all()
+    with pytest.raises(FileNotFoundError):
+        COCOSegmentDataset(out, "test")
+
+
+def test_trainer_refuses_to_run_without_gpu(tmp_path):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from sam3_lora_b200.train_native import SAM3TrainerNative
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        SAM3TrainerNative(str(ROOT / "configs" / "minimal_lora_config.yaml"))
