@@ -71,6 +71,7 @@ typedef struct sam3b_gemm_desc {
   int32_t bn;                               /* 0 = auto, 64, 256 */
   int32_t dbg_lbo, dbg_sbo;                 /* bring-up only; 0 = default */
   int32_t max_ctas;                         /* 0 = one CTA per SM */
+  int32_t cta_pair;                         /* 0 = default, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles */
 } sam3b_gemm_desc;
 
 int sam3b_gemm(const sam3b_gemm_desc* desc, void* stream);

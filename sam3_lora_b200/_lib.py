@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ("rope", C.c_void_p), ("rope_period", C.c_int32), ("rope_cols", C.c_int32),
         ("alpha", C.c_float),
         ("splitk", C.c_int32), ("c_trans", C.c_int32), ("bn", C.c_int32),
-        ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32), ("max_ctas", C.c_int32),
+        ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32), ("max_ctas", C.c_int32), ("cta_pair", C.c_int32),
     ]
 
 
@@ -103,7 +103,7 @@ def torch_dtype_code(dt) -> int:
 
 def gemm(A, B, C_out, *, epilogue=EPI_STORE16, a_mn=False, b_mn=False, M=None, N=None, K=None,
          bias=None, residual=None, res_row_mod=0, aux=None, rope=None, rope_period=1, rope_cols=0,
-         C2=None, alpha=1.0, splitk=1, c_trans=False, bn=0, dbg_lbo=0, dbg_sbo=0, max_ctas=0):
+         C2=None, alpha=1.0, splitk=1, c_trans=False, bn=0, dbg_lbo=0, dbg_sbo=0, max_ctas=0, cta_pair=0):
     """C = epilogue(alpha * A @ B^T).  A:[M,K] (or [K,M] if a_mn), B:[N,K] (or [K,N] if b_mn).
 
     Tensors may be column-slices of wider buffers: leading dimensions are taken from stride(0).
@@ -133,7 +133,7 @@ def gemm(A, B, C_out, *, epilogue=EPI_STORE16, a_mn=False, b_mn=False, M=None, N
         d.rope, d.rope_period, d.rope_cols = ptr(rope), rope_period, rope_cols
     d.alpha = alpha
     d.splitk, d.c_trans, d.bn = splitk, int(c_trans), bn
-    d.dbg_lbo, d.dbg_sbo, d.max_ctas = dbg_lbo, dbg_sbo, max_ctas
+    d.dbg_lbo, d.dbg_sbo, d.max_ctas, d.cta_pair = dbg_lbo, dbg_sbo, max_ctas, cta_pair
     check(lib.sam3b_gemm(C.byref(d), current_stream()))
     return C_out
 

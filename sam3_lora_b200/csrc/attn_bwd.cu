@@ -217,7 +217,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
         float pv[32], dsv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float pe = exp2f(__uint_as_float(s[i]) * c - stat[cc + i]);
+          const float pe = ex2_approx(__uint_as_float(s[i]) * c - stat[cc + i]);
           pv[i] = pe;
           dsv[i] = pe * (__uint_as_float(d[i]) - stat[BI + cc + i]);
         }
@@ -353,7 +353,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
         float dsv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float pe = exp2f(__uint_as_float(s[i]) * c - lse);
+          const float pe = ex2_approx(__uint_as_float(s[i]) * c - lse);
           dsv[i] = pe * (__uint_as_float(d[i]) - dlt);
         }
         store_row_chunk16<DT>(ds_row, sw, cc >> 3, dsv);

@@ -181,7 +181,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool need = m_blk > m_used + tau;  // always true on the first block (m_used = -inf)
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? m_blk : m_used;
-        const float alpha = exp2f((m_used - m_new) * c);  // 0 on the first block, 1 for rows that keep their max
+        const float alpha = ex2_approx((m_used - m_new) * c);  // 0 on the first block, 1 for rows that keep their max
         if (j > 0) {
           // every earlier P.V has landed in the accumulator (MMAs complete in issue order)
           mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1, 31);
@@ -210,7 +210,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float e[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float v = exp2f(__uint_as_float(s[q * 8 + i]) * c - mc);
+          const float v = ex2_approx(__uint_as_float(s[q * 8 + i]) * c - mc);
           e[i] = (q * 8 + i < kv_valid) ? v : 0.f;
         }
         uint4 u;

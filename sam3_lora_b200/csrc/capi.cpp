@@ -28,7 +28,7 @@ int sam3b_gemm(const sam3b_gemm_desc* d, void* stream) {
   a.aux = d->aux; a.ldaux = d->ldaux;
   a.rope = d->rope; a.rope_period = d->rope_period; a.rope_cols = d->rope_cols;
   a.alpha = d->alpha; a.splitk = d->splitk; a.c_trans = d->c_trans; a.bn = d->bn;
-  a.dbg_lbo = d->dbg_lbo; a.dbg_sbo = d->dbg_sbo; a.max_ctas = d->max_ctas;
+  a.dbg_lbo = d->dbg_lbo; a.dbg_sbo = d->dbg_sbo; a.max_ctas = d->max_ctas; a.cta_pair = d->cta_pair;
   return gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
 

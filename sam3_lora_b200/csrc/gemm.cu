@@ -19,6 +19,8 @@
 // together share the A row-panel in L2).
 #include "gemm.cuh"
 
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -55,14 +57,14 @@ struct GemmCfg {
 // exp(-x^2) with x = h/sqrt(2) is exp(-h^2/2): the Gaussian term of GELU' comes for free.
 __device__ __forceinline__ void erf_gauss(float h, float& erf_v, float& gauss) {
   const float x = fabsf(h) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.f));
-  gauss = exp2f(-1.4426950408889634f * x * x);  // exp(-h^2/2)
+  const float t = rcp_approx(fmaf(0.3275911f, x, 1.f));
+  gauss = ex2_approx(-1.4426950408889634f * x * x);  // exp(-h^2/2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   const float e = fmaf(-poly * t, gauss, 1.f);
-  erf_v = copysignf(e, h);
+  erf_v = __uint_as_float(__float_as_uint(e) | (__float_as_uint(h) & 0x80000000u));  // e >= 0
 }
 __device__ __forceinline__ float gelu_erf(float h) {
   float e, g;
@@ -323,6 +325,168 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TCOLS);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs owns one 256 x 256 output tile.  Each CTA
+// loads its own 128 rows of A and its own 128-row half of the B tile (32 KB per 64-deep k-block
+// instead of 48 KB), the leader issues M=256 MMAs that read both CTAs' shared memory, and each
+// CTA drains its own 128 accumulator rows.  Per FLOP this moves 2/3 of the L2->SM bytes of the
+// single-CTA 128x256 tile, which is what bounded the single-CTA kernel (~13 TB/s of L2 reads at
+// 1.1 PFLOP/s).  K-major operands, BN = 256 only.
+// ---------------------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int BM = 128, BN = 256, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;        // 16 KB (this CTA's rows)
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB (this CTA's half of the N tile)
+  static constexpr int STAGES = 6;
+  static constexpr int TCOLS = 512;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+};
+
+template <int EPI, int DT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint64_t* full = bars;                 // used in the leader CTA only
+  uint64_t* empty = bars + STAGES;       // in both CTAs (multicast commit)
+  uint64_t* tfull = bars + 2 * STAGES;   // in both CTAs (multicast commit)
+  uint64_t* tempty = tfull + 2;          // used in the leader CTA only, 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int m_pairs = (p.M + 255) / 256;
+  const int kb_total = (p.K + 63) / 64;
+  const int total_work = m_pairs * n_tiles;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, Cfg::TCOLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = cluster_id; w < total_work; w += n_clusters) {
+        const int n_blk = w % n_tiles, m_pair = w / n_tiles;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
+          const uint32_t full_leader = mapa_u32(&full[stage], 0);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+          tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, full_leader, kb * 64, m_pair * 256 + (int)rank * 128);
+          tma_load_2d_pair(sB + stage * Cfg::B_BYTES, &tmB, full_leader, kb * 64, n_blk * BN + (int)rank * 128);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(256, BN, DT, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = cluster_id; w < total_work; w += n_clusters) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+          const int ksteps = min(4, (p.K - kb * 64 + 15) / 16);
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_ss_pair(d_tmem, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32), idesc,
+                             (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty[stage], 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
+    const int ew = warp - 4;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = cluster_id; w < total_work; w += n_clusters) {
+      const int n_blk = w % n_tiles, m_pair = w / n_tiles;
+      mbar_wait(&tfull[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+      const int row = m_pair * 256 + (int)rank * 128 + ew * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c, r);
+        tmem_ld_wait();
+        epilogue_chunk<EPI, DT>(p, row, n_blk * BN + c, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TCOLS);
+}
+
+template <int EPI, int DT>
+static int launch_pair(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d(&tmA, a.A, a.M, a.K, a.lda, 128, 64))) return rc;
+  if ((rc = make_tmap_2d(&tmB, a.B, a.N, a.K, a.ldb, 128, 64))) return rc;
+  auto kern = gemm2_kernel<EPI, DT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAM3B_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  const int total = ((a.M + 255) / 256) * ((a.N + 255) / 256);
+  int clusters = (a.max_ctas > 0 ? a.max_ctas : num_sms()) / 2;
+  if (clusters > total) clusters = total;
+  if (clusters < 1) clusters = 1;
+  kern<<<2 * clusters, 256, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  SAM3B_LAUNCHED();
+  return 0;
+}
+template <int EPI>
+static int launch_pair_dt(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
+  return a.dtype == 0 ? launch_pair<EPI, 0>(a, p, stream) : launch_pair<EPI, 1>(a, p, stream);
+}
+
 // ---------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------
@@ -356,6 +520,15 @@ template <int BN, int EPI, bool A_MN, bool B_MN>
 static int launch_dt(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
   if (a.dtype == 0) return launch_one<BN, EPI, 0, A_MN, B_MN>(a, p, stream);
   return launch_one<BN, EPI, 1, A_MN, B_MN>(a, p, stream);
+}
+
+// CTA-pair tiles are opt-in until validated on hardware: SAM3B_GEMM_PAIR=1 (or GemmArgs::cta_pair = 2)
+static bool pair_default() {
+  static const bool on = [] {
+    const char* e = getenv("SAM3B_GEMM_PAIR");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
 }
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
@@ -414,6 +587,18 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     }
   }
   SAM3B_REQUIRE(bn == 256, "gemm: bn must be 64 or 256 (got %d)", bn);
+  const bool pair = a.cta_pair == 2 || (a.cta_pair == 0 && pair_default() && a.M >= 512 && a.N >= 256);
+  if (pair) {
+    switch (a.epilogue) {
+      case EPI_STORE16: return launch_pair_dt<EPI_STORE16>(a, p, stream);
+      case EPI_QKV_ROPE: return launch_pair_dt<EPI_QKV_ROPE>(a, p, stream);
+      case EPI_RESIDUAL_F32: return launch_pair_dt<EPI_RESIDUAL_F32>(a, p, stream);
+      case EPI_GELU: return launch_pair_dt<EPI_GELU>(a, p, stream);
+      case EPI_DGELU: return launch_pair_dt<EPI_DGELU>(a, p, stream);
+      case EPI_STORE32: return launch_pair_dt<EPI_STORE32>(a, p, stream);
+      default: break;
+    }
+  }
   switch (a.epilogue) {
     case EPI_STORE16: return launch_dt<256, EPI_STORE16, false, false>(a, p, stream);
     case EPI_QKV_ROPE: return launch_dt<256, EPI_QKV_ROPE, false, false>(a, p, stream);

@@ -35,6 +35,7 @@ struct GemmArgs {
   int bn = 0;           // 0 = choose; else 64 or 256
   int dbg_lbo = 0, dbg_sbo = 0;  // bring-up overrides for the MN-major descriptors (bytes); 0 = default
   int max_ctas = 0;     // 0 = number of SMs
+  int cta_pair = 0;     // 0 = default policy, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) 256x256 tiles
 };
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);

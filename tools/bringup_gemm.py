@@ -69,13 +69,17 @@ def run_case(name: str) -> dict:
         A, B = mk(M, K, dt), mk(N, K, dt)
         out_dt = torch.float32 if epi in (L.EPI_STORE32,) else dt
         Cb = torch.zeros(M, N, device=dev, dtype=out_dt)
-        L.gemm(A, B, Cb, epilogue=epi, bn=bn, **kw)
+        L.gemm(A, B, Cb, epilogue=epi, bn=bn, cta_pair=pair, **kw)
         torch.cuda.synchronize()
         ref = A.float() @ B.float().T
         return rel_err(Cb, ref)
 
+    pair = 0
+    if name.startswith("p_") or name.startswith("perfp_"):   # same cases on the CTA-pair (cta_group::2) kernel
+        pair = 2
+        name = ("k_" + name[2:]) if name.startswith("p_") else ("perf_" + name[6:])
     if name == "k_tile1":
-        res["err"] = basic(128, 256, 64)
+        res["err"] = basic(256 if pair else 128, 256, 64)
     elif name == "k_tile1_bn64":
         res["err"] = basic(128, 64, 64, bn=64)
     elif name == "k_multi":
@@ -159,18 +163,37 @@ def run_case(name: str) -> dict:
             "perf_fc2": (41472, 1024, 4800, L.EPI_STORE16),
             "perf_proj": (41472, 1024, 1088, L.EPI_STORE16),
             "perf_skinny": (41472, 64, 1024, L.EPI_STORE16),
+            "perf_gelu": (41472, 4736, 1088, L.EPI_GELU),
+            "perf_dgelu": (41472, 4736, 1088, L.EPI_DGELU),
         }
         M, N, K, epi = shapes[name]
         A, B = mk(M, K, torch.float16), mk(N, K, torch.float16)
         Cb = torch.zeros(M, N, device=dev, dtype=torch.float16)
+        if epi in (L.EPI_GELU, L.EPI_DGELU):   # epilogue cost only: time the GELU / GELU' variants of the same shape
+            G2 = torch.zeros(M, N, device=dev, dtype=torch.float16)
+            Hh = (torch.randn(M, N, device=dev)).to(torch.float16)
+            kw2 = dict(C2=G2) if epi == L.EPI_GELU else dict(aux=Hh)
+            for _ in range(3):
+                L.gemm(A, B, Cb, epilogue=epi, cta_pair=pair, **kw2)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                L.gemm(A, B, Cb, epilogue=epi, cta_pair=pair, **kw2)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            res["ms"] = ms
+            res["tflops"] = 2.0 * M * N * K / ms / 1e9
+            return res
         for _ in range(3):
-            L.gemm(A, B, Cb, epilogue=epi)
+            L.gemm(A, B, Cb, epilogue=epi, cta_pair=pair)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         iters = 10
         e0.record()
         for _ in range(iters):
-            L.gemm(A, B, Cb, epilogue=epi)
+            L.gemm(A, B, Cb, epilogue=epi, cta_pair=pair)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
@@ -198,7 +221,9 @@ CASES = [
     "k_tile1", "k_tile1_bn64", "k_multi", "k_ragged", "k_store16", "k_skinny", "k_persist", "k_big_f16", "k_big_bf16",
     "epi_residual", "epi_gelu", "epi_dgelu", "epi_rope",
     "mn_8192_1024", "mn_1024_8192", "mn_16_1024", "mn_8192_128",
-    "perf_qkv", "perf_fc1", "perf_fc2", "perf_proj", "perf_skinny",
+    "perf_qkv", "perf_fc1", "perf_fc2", "perf_proj", "perf_skinny", "perf_gelu", "perf_dgelu",
+    "p_tile1", "p_multi", "p_ragged", "p_store16", "p_persist", "p_big_f16", "p_big_bf16",
+    "perfp_qkv", "perfp_fc1", "perfp_fc2", "perfp_proj", "perfp_gelu", "perfp_dgelu",
 ]
 
 
