@@ -72,6 +72,7 @@ typedef struct sam3b_gemm_desc {
   int32_t dbg_lbo, dbg_sbo;                 /* bring-up only; 0 = default */
   int32_t max_ctas;                         /* 0 = one CTA per SM */
   int32_t cta_pair;                         /* 0 = default, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles */
+  const float* row_scale; int32_t rows_per_scale; /* RESIDUAL_F32: out = res + row_scale[row/rows_per_scale]*(acc+bias) */
 } sam3b_gemm_desc;
 
 int sam3b_gemm(const sam3b_gemm_desc* desc, void* stream);
@@ -173,6 +174,9 @@ int sam3b_vit_load_base(sam3b_vit* v, const float* const* tensors, int32_t n_ten
 /* img: fp32 NCHW [batch][C][S][S]; lora_flat: flat fp32 adapters; out: fp32 NCHW [batch][D][G][G] */
 int sam3b_vit_forward(sam3b_vit* v, const float* img, int32_t batch, const float* lora_flat, float* out_nchw,
                       int32_t save_for_backward, void* stream);
+/* DropPath (vitdet.py:610-611, rates linspace(0, 0.1, depth), model_builder.py:80): device array [depth][2][batch]
+ * of per-image branch scales (0 or 1/keep; [i][0] attention, [i][1] MLP) for the next forward + backward; NULL = off */
+int sam3b_vit_set_drop_path(sam3b_vit* v, const float* scales);
 /* gout: dLoss/dout fp32 NCHW; lora_grad_flat: flat fp32 gradients (overwritten, same layout as lora_flat) */
 int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, void* stream);
 

@@ -149,8 +149,9 @@ def window_unpartition(w: Tensor, ws: int, G: int) -> Tensor:
 
 
 def block(x: Tensor, params: Dict[str, Tensor], i: int, cfg: ViTConfig, scaling: float,
-          prefix: str = "") -> Tensor:
-    """Pre-norm residual block (vitdet.py:597-613); drop_path / dropout are identity (parity mode)."""
+          prefix: str = "", drop: Optional[Tensor] = None) -> Tensor:
+    """Pre-norm residual block (vitdet.py:597-613).  `drop` [2, B]: per-sample DropPath scales (0 or 1/keep)
+    of the attention and MLP branches (timm DropPath, scale_by_keep); None = identity (eval / parity mode)."""
     p = f"{prefix}blocks.{i}"
     D = cfg.embed_dim
     G = cfg.grid
@@ -165,6 +166,8 @@ def block(x: Tensor, params: Dict[str, Tensor], i: int, cfg: ViTConfig, scaling:
         w = window_partition(h, ws)
         a = attention(w.reshape(w.shape[0], ws * ws, D), params, f"{p}.attn", cfg, ang, scaling)
         a = window_unpartition(a.reshape(-1, ws, ws, D), ws, G)
+    if drop is not None:
+        a = a * drop[0].to(a.dtype).view(-1, 1, 1, 1)
     x = shortcut + a
     h = F.layer_norm(x, (D,), params[f"{p}.norm2.weight"], params[f"{p}.norm2.bias"], cfg.ln_eps)
     h1 = h @ params[f"{p}.mlp.fc1.weight"].T + params[f"{p}.mlp.fc1.bias"]
@@ -176,6 +179,8 @@ def block(x: Tensor, params: Dict[str, Tensor], i: int, cfg: ViTConfig, scaling:
     ab = _lora(params, f"{p}.mlp", "fc2")
     if ab is not None:
         h2 = h2 + lora_delta(g, ab[0], ab[1], scaling)
+    if drop is not None:
+        h2 = h2 * drop[1].to(h2.dtype).view(-1, 1, 1, 1)
     return x + h2
 
 
@@ -195,13 +200,13 @@ def patch_embed(img: Tensor, params: Dict[str, Tensor], cfg: ViTConfig, prefix: 
 
 
 def vit_forward(img: Tensor, params: Dict[str, Tensor], cfg: ViTConfig, scaling: float = 1.0,
-                prefix: str = "", return_blocks: bool = False):
+                prefix: str = "", return_blocks: bool = False, drop_scales: Optional[Tensor] = None):
     """ViT.forward (vitdet.py:813-859): returns the NCHW feature map [B, D, G, G] after the last block
     (ln_post is Identity in SAM3, model_builder.py:92)."""
     x = patch_embed(img, params, cfg, prefix)
     outs = [x]
     for i in range(cfg.depth):
-        x = block(x, params, i, cfg, scaling, prefix)
+        x = block(x, params, i, cfg, scaling, prefix, None if drop_scales is None else drop_scales[i])
         if return_blocks:
             outs.append(x)
     y = x.permute(0, 3, 1, 2)
@@ -272,13 +277,13 @@ def lora_keys(params: Dict[str, Tensor]) -> List[str]:
 
 
 def train_step_reference(img: Tensor, params: Dict[str, Tensor], cfg: ViTConfig, spec: LoRASpec,
-                         gout: Tensor) -> Tuple[Tensor, Dict[str, Tensor]]:
+                         gout: Tensor, drop_scales: Optional[Tensor] = None) -> Tuple[Tensor, Dict[str, Tensor]]:
     """Forward + backward of the trunk with only the adapters trainable (apply_lora_to_model freezes
     everything else, lora_layers.py:171-172).  Loss = sum(out * gout).  Returns (out, {lora key: grad})."""
     keys = lora_keys(params)
     leaf = {k: params[k].detach().clone().requires_grad_(True) for k in keys}
     p = dict(params)
     p.update(leaf)
-    out = vit_forward(img, p, cfg, spec.scaling)
+    out = vit_forward(img, p, cfg, spec.scaling, drop_scales=drop_scales)
     (out * gout).sum().backward()
     return out.detach(), {k: leaf[k].grad for k in keys}

@@ -36,6 +36,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float),
         ("splitk", C.c_int32), ("c_trans", C.c_int32), ("bn", C.c_int32),
         ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32), ("max_ctas", C.c_int32), ("cta_pair", C.c_int32),
+        ("row_scale", C.c_void_p), ("rows_per_scale", C.c_int32),
     ]
 
 
@@ -103,7 +104,7 @@ def torch_dtype_code(dt) -> int:
 
 def gemm(A, B, C_out, *, epilogue=EPI_STORE16, a_mn=False, b_mn=False, M=None, N=None, K=None,
          bias=None, residual=None, res_row_mod=0, aux=None, rope=None, rope_period=1, rope_cols=0,
-         C2=None, alpha=1.0, splitk=1, c_trans=False, bn=0, dbg_lbo=0, dbg_sbo=0, max_ctas=0, cta_pair=0):
+         C2=None, alpha=1.0, splitk=1, c_trans=False, bn=0, dbg_lbo=0, dbg_sbo=0, max_ctas=0, cta_pair=0, row_scale=None, rows_per_scale=1):
     """C = epilogue(alpha * A @ B^T).  A:[M,K] (or [K,M] if a_mn), B:[N,K] (or [K,N] if b_mn).
 
     Tensors may be column-slices of wider buffers: leading dimensions are taken from stride(0).
@@ -134,6 +135,7 @@ def gemm(A, B, C_out, *, epilogue=EPI_STORE16, a_mn=False, b_mn=False, M=None, N
     d.alpha = alpha
     d.splitk, d.c_trans, d.bn = splitk, int(c_trans), bn
     d.dbg_lbo, d.dbg_sbo, d.max_ctas, d.cta_pair = dbg_lbo, dbg_sbo, max_ctas, cta_pair
+    d.row_scale, d.rows_per_scale = ptr(row_scale), rows_per_scale
     check(lib.sam3b_gemm(C.byref(d), current_stream()))
     return C_out
 

@@ -25,6 +25,7 @@ int sam3b_gemm(const sam3b_gemm_desc* d, void* stream) {
   a.C = d->C; a.ldc = d->ldc; a.C2 = d->C2; a.ldc2 = d->ldc2;
   a.bias = d->bias;
   a.residual = d->residual; a.ldres = d->ldres; a.res_row_mod = d->res_row_mod;
+  a.row_scale = d->row_scale; a.rows_per_scale = d->rows_per_scale;
   a.aux = d->aux; a.ldaux = d->ldaux;
   a.rope = d->rope; a.rope_period = d->rope_period; a.rope_cols = d->rope_cols;
   a.alpha = d->alpha; a.splitk = d->splitk; a.c_trans = d->c_trans; a.bn = d->bn;
@@ -155,6 +156,11 @@ int sam3b_vit_forward(sam3b_vit* v, const float* img, int32_t batch, const float
                       int32_t save_for_backward, void* stream) {
   if (!v || !img) return fail(-1, "sam3b_vit_forward: null argument");
   return v->eng->forward(img, batch, lora_flat, out_nchw, save_for_backward != 0, static_cast<cudaStream_t>(stream));
+}
+int sam3b_vit_set_drop_path(sam3b_vit* v, const float* scales) {
+  if (!v) return fail(-1, "sam3b_vit_set_drop_path: null handle");
+  v->eng->set_drop_path(scales);
+  return 0;
 }
 int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, void* stream) {
   if (!v) return fail(-1, "sam3b_vit_backward: null handle");

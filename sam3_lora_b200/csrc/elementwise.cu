@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
                                                      const float* __restrict__ x, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                      const float* dres, int rows, float* dx, uint16_t* dx16,
-                                                     int64_t lddx16) {
+                                                     int64_t lddx16, const float* __restrict__ row_scale,
+                                                     int rows_per_scale) {
   constexpr int D = 128 * VPT;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
   const float m1 = warp_sum(s1) * (1.f / D), m2 = warp_sum(s2) * (1.f / D);
   const float4* rr = reinterpret_cast<const float4*>(dres + (int64_t)row * D);
   float4* dxr = reinterpret_cast<float4*>(dx + (int64_t)row * D);
+  const float sc = row_scale != nullptr ? __ldg(row_scale + row / rows_per_scale) : 1.f;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const float4 r = rr[lane + i * 32];
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
     o.w = r.w + rs * (g[i].w - m1 - xh[i].w * m2);
     dxr[lane + i * 32] = o;
     if (dx16 != nullptr)
-      reinterpret_cast<uint2*>(dx16 + (int64_t)row * lddx16)[lane + i * 32] = pack4<DT>(o.x, o.y, o.z, o.w);
+      reinterpret_cast<uint2*>(dx16 + (int64_t)row * lddx16)[lane + i * 32] = pack4<DT>(o.x * sc, o.y * sc, o.z * sc, o.w * sc);
   }
 }
 
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const float* __rest
 template <int DT>
 __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __restrict__ g, int G, int ws, int D,
                                                              float* __restrict__ dx, uint16_t* __restrict__ dx16,
-                                                             int64_t ld16) {
+                                                             int64_t ld16, const float* __restrict__ img_scale) {
   __shared__ float tile[32][33];
   const int T = G * G, nwx = G / ws;
   const int b = blockIdx.z;
@@ -232,8 +234,9 @@ __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __rest
       const int64_t r = (int64_t)b * T + tok;
       dx[r * D + d0 + tx] = v;
       if (dx16 != nullptr) {
-        if constexpr (DT == 0) reinterpret_cast<__half*>(dx16)[r * ld16 + d0 + tx] = __float2half_rn(v);
-        else reinterpret_cast<__nv_bfloat16*>(dx16)[r * ld16 + d0 + tx] = __float2bfloat16_rn(v);
+        const float vs = img_scale != nullptr ? v * __ldg(img_scale + b) : v;
+        if constexpr (DT == 0) reinterpret_cast<__half*>(dx16)[r * ld16 + d0 + tx] = __float2half_rn(vs);
+        else reinterpret_cast<__nv_bfloat16*>(dx16)[r * ld16 + d0 + tx] = __float2bfloat16_rn(vs);
       }
     }
   }
@@ -409,15 +412,15 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
 
 int layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const float* mean, const float* rstd,
                   const float* gamma, const float* dres, int rows, int D, float* dx, void* dx16, int64_t lddx16,
-                  int dtype, cudaStream_t s) {
+                  int dtype, cudaStream_t s, const float* row_scale, int rows_per_scale) {
   SAM3B_REQUIRE(lddy % 4 == 0 && (dx16 == nullptr || lddx16 % 4 == 0), "layernorm bwd: ld %% 4 != 0");
   const int blocks = (rows + 7) / 8;
   return dispatch_vpt(D, [&](auto vpt) -> int {
     constexpr int V = decltype(vpt)::value;
     if (dtype == 0)
-      ln_bwd_kernel<V, 0><<<blocks, 256, 0, s>>>((const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16);
+      ln_bwd_kernel<V, 0><<<blocks, 256, 0, s>>>((const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16, row_scale, rows_per_scale);
     else
-      ln_bwd_kernel<V, 1><<<blocks, 256, 0, s>>>((const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16);
+      ln_bwd_kernel<V, 1><<<blocks, 256, 0, s>>>((const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16, row_scale, rows_per_scale);
     SAM3B_LAUNCHED();
     return 0;
   });
@@ -492,11 +495,11 @@ int tokens_to_nchw(const float* x, int B, int G, int ws, int D, float* out, cuda
 }
 
 int nchw_to_tokens(const float* g, int B, int G, int ws, int D, float* dx, void* dx16, int64_t ld16, int dtype,
-                   cudaStream_t s) {
+                   cudaStream_t s, const float* img_scale) {
   SAM3B_REQUIRE(D % 32 == 0 && G % ws == 0, "nchw_to_tokens: D %% 32, G %% ws");
   dim3 grid((G * G + 31) / 32, D / 32, B);
-  if (dtype == 0) nchw_to_tokens_kernel<0><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16);
-  else nchw_to_tokens_kernel<1><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16);
+  if (dtype == 0) nchw_to_tokens_kernel<0><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16, img_scale);
+  else nchw_to_tokens_kernel<1><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16, img_scale);
   SAM3B_LAUNCHED();
   return 0;
 }

@@ -12,9 +12,10 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
 
 // dx = dres + dLN(dy16; x, mean, rstd, gamma); also a 16-bit copy of dx for the next GEMM.
 // dres may alias dx (in-place accumulate).  dx16 may be null.
+// dx16 = row_scale[row / rows_per_scale] * dx when row_scale != null (DropPath scaling of the branch gradient).
 int layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const float* mean, const float* rstd,
                   const float* gamma, const float* dres, int rows, int D, float* dx, void* dx16, int64_t lddx16,
-                  int dtype, cudaStream_t s);
+                  int dtype, cudaStream_t s, const float* row_scale = nullptr, int rows_per_scale = 1);
 
 // y32[row][0..D) = LayerNorm(x[row]) * gamma + beta in fp32 (ln_pre feeding the fp32 residual stream,
 // vitdet.py:833).  In-place (y32 == x) is allowed.
@@ -45,7 +46,7 @@ int patch_gather(const float* img, int B, int C, int Himg, int Wimg, int P, int 
 int tokens_to_nchw(const float* x, int B, int G, int ws, int D, float* out, cudaStream_t s);
 // and back (gradient path): also emits the 16-bit copy used as the first dgrad operand.
 int nchw_to_tokens(const float* g, int B, int G, int ws, int D, float* dx, void* dx16, int64_t ld16, int dtype,
-                   cudaStream_t s);
+                   cudaStream_t s, const float* img_scale = nullptr);
 
 // ---- LoRA packing -------------------------------------------------------------------------
 // One adapted Linear (in -> out_total) with n adapters of rank r that each own the output

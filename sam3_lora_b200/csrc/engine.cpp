@@ -394,6 +394,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
       g.A = a.O; g.lda = ld_O; g.B = w.proj.w_ext; g.ldb = w.proj.ldw;
       g.dtype = dt; g.epilogue = EPI_RESIDUAL_F32; g.bias = w.proj.bias;
       g.residual = x_[i]; g.ldres = D_;
+      if (drop_scales_) { g.row_scale = drop_scales_ + (int64_t)(2 * i) * batch; g.rows_per_scale = T_; }
       g.C = a.x_mid; g.ldc = D_;
       if ((rc = gemm_launch(g, s))) return rc;
     }
@@ -415,6 +416,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
       g.A = a.g; g.lda = ld_g; g.B = w.fc2.w_ext; g.ldb = w.fc2.ldw;
       g.dtype = dt; g.epilogue = EPI_RESIDUAL_F32; g.bias = w.fc2.bias;
       g.residual = a.x_mid; g.ldres = D_;
+      if (drop_scales_) { g.row_scale = drop_scales_ + (int64_t)(2 * i + 1) * batch; g.rows_per_scale = T_; }
       g.C = x_[i + 1]; g.ldc = D_;
       if ((rc = gemm_launch(g, s))) return rc;
     }
@@ -423,6 +425,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
     if ((rc = tokens_to_nchw(x_[cfg_.depth], batch, G_, cfg_.window_size, D_, out_nchw, s))) return rc;
   last_batch_ = batch;
   last_saved_ = save;
+  fwd_drop_scales_ = drop_scales_;
   return 0;
 }
 
@@ -437,7 +440,10 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
   float* dx = dxa_;      // gradient w.r.t. the current block's output (fp32)
   float* dx_alt = dxb_;
   int64_t ld_dx16 = D_ + Rmax_;
-  if ((rc = nchw_to_tokens(gout_nchw, last_batch_, G_, cfg_.window_size, D_, dx, dx16_, ld_dx16, dt, s))) return rc;
+  const float* ds = fwd_drop_scales_;
+  const int Bn = last_batch_;
+  auto drop = [&](int blk, int branch) -> const float* { return ds ? ds + (int64_t)(2 * blk + branch) * Bn : nullptr; };
+  if ((rc = nchw_to_tokens(gout_nchw, last_batch_, G_, cfg_.window_size, D_, dx, dx16_, ld_dx16, dt, s, drop(cfg_.depth - 1, 1)))) return rc;
 
   // dst16[:, out .. out+R) = s * dy[:, :out] . B^T      (skinny GEMM; B operand = up_pack [R][out])
   auto site_up_grad = [&](const Site& st, uint16_t* dy, int64_t ld) -> int {
@@ -472,7 +478,7 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
     if ((rc = site_wgrad(w.fc1, a.xn2, ld_xn2, dh16_, ld_dh, M, grad_flat, s))) return rc;
     if ((rc = site_dgrad(w.fc1, dh16_, ld_dh, EPI_STORE16, dxn16_, D_, nullptr, 0))) return rc;
     // dx_mid = dx + dLN2(dxn2)
-    if ((rc = layernorm_bwd(dxn16_, D_, a.x_mid, a.mean2, a.rstd2, w.g2, dx, M, D_, dx_alt, dx16_, ld_dx16, dt, s))) return rc;
+    if ((rc = layernorm_bwd(dxn16_, D_, a.x_mid, a.mean2, a.rstd2, w.g2, dx, M, D_, dx_alt, dx16_, ld_dx16, dt, s, drop(i, 0), T_))) return rc;
     std::swap(dx, dx_alt);
     // ---- attention half.  dx16_ holds dy for proj.
     if ((rc = site_up_grad(w.proj, dx16_, ld_dx16))) return rc;
@@ -491,7 +497,7 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
     if ((rc = site_wgrad(w.qkv, a.xn1, ld_xn1, dqkv16_, ld_dqkv, M, grad_flat, s))) return rc;
     if (i == 0) break;  // nothing upstream of block 0 is trainable (patch embed / pos / ln_pre are frozen)
     if ((rc = site_dgrad(w.qkv, dqkv16_, ld_dqkv, EPI_STORE16, dxn16_, D_, nullptr, 0))) return rc;
-    if ((rc = layernorm_bwd(dxn16_, D_, x_[i], a.mean1, a.rstd1, w.g1, dx, M, D_, dx_alt, dx16_, ld_dx16, dt, s))) return rc;
+    if ((rc = layernorm_bwd(dxn16_, D_, x_[i], a.mean1, a.rstd1, w.g1, dx, M, D_, dx_alt, dx16_, ld_dx16, dt, s, drop(i - 1, 1), T_))) return rc;
     std::swap(dx, dx_alt);
   }
   last_saved_ = false;

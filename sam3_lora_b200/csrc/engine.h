@@ -51,6 +51,10 @@ class VitEngine {
   int load_base(const float* const* tensors, int n, cudaStream_t s);
   int forward(const float* img, int batch, const float* lora_flat, float* out_nchw, bool save, cudaStream_t s);
   int backward(const float* gout_nchw, float* lora_grad_flat, cudaStream_t s);
+  // Stochastic depth (DropPath, vitdet.py:610-611): device array [depth][2][batch] of per-image branch scales
+  // (0 or 1/keep; [i][0] attention branch, [i][1] MLP branch) used by the next forward AND its backward.
+  // nullptr disables it (eval mode / drop_path 0).
+  void set_drop_path(const float* scales) { drop_scales_ = scales; }
 
  private:
   struct Site {
@@ -101,6 +105,8 @@ class VitEngine {
   float *dxa_ = nullptr, *dxb_ = nullptr, *delta_ = nullptr, *dA_pack_ = nullptr, *dB_pack_ = nullptr;
   uint16_t *dx16_ = nullptr, *dh16_ = nullptr, *dxn16_ = nullptr, *dO16_ = nullptr, *dqkv16_ = nullptr;
   int Rmax_ = 0;
+  const float* drop_scales_ = nullptr;
+  const float* fwd_drop_scales_ = nullptr;  // what the saved forward used
   int last_batch_ = 0;
   bool last_saved_ = false;
   bool base_loaded_ = false;

@@ -32,6 +32,7 @@ struct GemmParams {
   void* C2; int64_t ldc2;
   const float* bias;
   const float* res; int64_t ldres; int res_row_mod;
+  const float* row_scale; int rows_per_scale;
   const void* aux; int64_t ldaux;
   const float2* rope; int rope_period; int rope_cols;
   float alpha;
@@ -147,6 +148,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
     store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
   } else if constexpr (EPI == EPI_RESIDUAL_F32) {
     const int rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
+    if (p.row_scale != nullptr) {  // stochastic depth: per-image 0 or 1/keep on the branch (vitdet.py:610-611)
+      const float sc = __ldg(p.row_scale + row / p.rows_per_scale);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= sc;
+    }
     const float4* r4 = reinterpret_cast<const float4*>(p.res + (int64_t)rr * p.ldres + col);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -557,6 +563,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.C = a.C; p.ldc = a.ldc; p.C2 = a.C2; p.ldc2 = a.ldc2;
   p.bias = a.bias;
   p.res = a.residual; p.ldres = a.ldres; p.res_row_mod = a.res_row_mod;
+  p.row_scale = a.row_scale; p.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
   p.aux = a.aux; p.ldaux = a.ldaux;
   p.rope = reinterpret_cast<const float2*>(a.rope); p.rope_period = a.rope_period > 0 ? a.rope_period : 1;
   p.rope_cols = a.rope_cols;

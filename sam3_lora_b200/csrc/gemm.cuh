@@ -27,6 +27,7 @@ struct GemmArgs {
   void* C2 = nullptr; int64_t ldc2 = 0;
   const float* bias = nullptr;
   const float* residual = nullptr; int64_t ldres = 0; int res_row_mod = 0;
+  const float* row_scale = nullptr; int rows_per_scale = 1;  // EPI_RESIDUAL_F32: out = res + row_scale[row / rows_per_scale] * (acc + bias)  (DropPath)
   const void* aux = nullptr; int64_t ldaux = 0;
   const float* rope = nullptr; int rope_period = 1; int rope_cols = 0;  // rope: [period][32] (cos,sin) pairs
   float alpha = 1.f;

@@ -90,6 +90,8 @@ def _declare(lib):
     lib.sam3b_vit_load_base.restype = C.c_int
     lib.sam3b_vit_forward.argtypes = [C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p, i32, C.c_void_p]
     lib.sam3b_vit_forward.restype = C.c_int
+    lib.sam3b_vit_set_drop_path.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sam3b_vit_set_drop_path.restype = C.c_int
     lib.sam3b_vit_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sam3b_vit_backward.restype = C.c_int
     lib._vit_declared = True
@@ -206,6 +208,11 @@ class VitEngine:
     def forward(self, img, lora_flat, out, save_for_backward: bool):
         _lib.check(self.lib.sam3b_vit_forward(self._h, img.data_ptr(), img.shape[0], _lib.ptr(lora_flat), out.data_ptr(),
                                               int(save_for_backward), _lib.current_stream()))
+
+    def set_drop_path(self, scales):
+        """scales: fp32 CUDA tensor [depth, 2, batch] (0 or 1/keep) or None; the caller keeps it alive until backward."""
+        self._drop_scales = scales
+        _lib.check(self.lib.sam3b_vit_set_drop_path(self._h, _lib.ptr(scales)))
 
     def backward(self, gout, grad_flat):
         _lib.check(self.lib.sam3b_vit_backward(self._h, gout.data_ptr(), _lib.ptr(grad_flat), _lib.current_stream()))

@@ -95,6 +95,8 @@ class _TrunkFn(torch.autograd.Function):
         spec = vit.spec
         out = torch.empty(B, spec.embed_dim, spec.grid, spec.grid, device=images.device, dtype=torch.float32)
         img = images.detach().float().contiguous()
+        ctx.drop = vit._drop_scales_for(B, images.device)   # keeps the tensor alive until backward
+        eng.set_drop_path(ctx.drop)
         eng.forward(img, flat, out, save_for_backward=need_grad)
         ctx.vit = vit
         ctx.n = len(lora_params)
@@ -116,8 +118,12 @@ class ViT(nn.Module):
 
     def __init__(self, img_size=1008, patch_size=14, in_chans=3, embed_dim=1024, depth=32, num_heads=16,
                  mlp_ratio=4.625, window_size=24, global_att_blocks=(7, 15, 23, 31), pretrain_img_size=336,
-                 ln_eps=1e-5, rope_theta=10000.0, operand_dtype=torch.float16, max_batch=8):
+                 ln_eps=1e-5, rope_theta=10000.0, drop_path_rate=0.1, operand_dtype=torch.float16, max_batch=8):
         super().__init__()
+        # stochastic depth decay rule of the reference: linspace(0, rate, depth) (vitdet.py:746), 0.1 in SAM3
+        # (model_builder.py:80); active in train() mode only.
+        self.drop_path_rates = [drop_path_rate * i / (depth - 1) for i in range(depth)] if depth > 1 else [float(drop_path_rate)]
+        self.drop_scales_override: Optional[torch.Tensor] = None  # tests: inject [depth, 2, B] branch scales
         self.spec = VitSpec(img_size=img_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim, depth=depth,
                             num_heads=num_heads, mlp_hidden=int(embed_dim * mlp_ratio), window_size=window_size,
                             global_blocks=tuple(global_att_blocks), pretrain_img_size=pretrain_img_size, ln_eps=ln_eps,
@@ -273,6 +279,17 @@ class ViT(nn.Module):
     def _after_backward(self, gflat: torch.Tensor):
         if self.grad_hook is not None:
             self.grad_hook(gflat)
+
+    def _drop_scales_for(self, batch: int, device) -> Optional[torch.Tensor]:
+        """DropPath (timm semantics, scale_by_keep): one Bernoulli(keep) draw per sample and per residual branch;
+        returns [depth, 2, batch] with entries 0 or 1/keep, or None when inactive."""
+        if self.drop_scales_override is not None:
+            return self.drop_scales_override.to(device=device, dtype=torch.float32).contiguous()
+        if not self.training or max(self.drop_path_rates) <= 0.0:
+            return None
+        keep = 1.0 - torch.tensor(self.drop_path_rates, device=device, dtype=torch.float32).view(-1, 1, 1)
+        mask = (torch.rand(self.spec.depth, 2, batch, device=device) < keep).float()
+        return (mask / keep).contiguous()
 
     # ---- forward ------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:

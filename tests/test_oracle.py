@@ -54,3 +54,26 @@ def test_rope_angles_match_reference_buffer_shape_and_scale():
     assert w.shape == (576, 32) and gl.shape == (5184, 32)
     # global rope is the window rope sampled at 1/3 positions: token (row 3, col 6) == window (1, 2)
     assert torch.allclose(gl[3 * 72 + 6], w[1 * 24 + 2], atol=1e-12)
+
+
+def test_oracle_drop_path_matches_timm_semantics():
+    """x + DropPath(branch): per-sample mask/keep on the branch only (timm DropPath, used at vitdet.py:610-611)."""
+    g = load_small_golden()
+    cfg = g["cfg"]
+    img2 = torch.cat([g["img"], g["img"].flip(-1)], dim=0)
+    full = O.vit_forward(img2, g["params"], cfg, g["spec"].scaling, return_blocks=True)[1]
+    drop = torch.ones(cfg.depth, 2, 2)
+    drop[0, 0, 1] = 0.0          # sample 1 skips block 0's attention branch
+    drop[1, 1, 0] = 1.0 / 0.9    # sample 0 keeps block 1's MLP branch, scaled by 1/keep
+    out, blocks = O.vit_forward(img2, g["params"], cfg, g["spec"].scaling, return_blocks=True, drop_scales=drop)
+    # sample 0, block 0 untouched
+    assert torch.equal(blocks[1][0], full[1][0])
+    # sample 1, block 0: attention branch removed -> x_mid == x_in, then MLP on it
+    x_in = blocks[0][1:2]
+    D = cfg.embed_dim
+    p = g["params"]
+    h = torch.nn.functional.layer_norm(x_in, (D,), p["blocks.0.norm2.weight"], p["blocks.0.norm2.bias"], cfg.ln_eps)
+    h1 = h @ p["blocks.0.mlp.fc1.weight"].T + p["blocks.0.mlp.fc1.bias"] + O.lora_delta(h, p["blocks.0.mlp.fc1.lora.lora_A"], p["blocks.0.mlp.fc1.lora.lora_B"], g["spec"].scaling)
+    gl = torch.nn.functional.gelu(h1)
+    h2 = gl @ p["blocks.0.mlp.fc2.weight"].T + p["blocks.0.mlp.fc2.bias"] + O.lora_delta(gl, p["blocks.0.mlp.fc2.lora.lora_A"], p["blocks.0.mlp.fc2.lora.lora_B"], g["spec"].scaling)
+    assert rel_max(blocks[1][1:2], x_in + h2) < 1e-6

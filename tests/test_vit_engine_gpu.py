@@ -163,3 +163,66 @@ def test_forward_tolerance_budget():
     e = rel_l2(out, g["out"])
     _report("north_star_fwd", {"out_rel_l2": e})
     assert e < 1e-3
+
+
+def test_drop_path_with_injected_scales_matches_oracle():
+    """Stochastic depth (vitdet.py:610-611): per-sample branch scales, forward and LoRA gradients."""
+    from sam3_lora_b200.engine import VitEngine
+
+    g = load_small_golden()
+    cfg, spec, params = g["cfg"], g["spec"], g["params"]
+    img2 = torch.cat([g["img"], g["img"].flip(-1)], dim=0)
+    gout2 = torch.cat([g["gout"], g["gout"].flip(-2)], dim=0)
+    drop = torch.tensor([[[1.0, 0.0], [1.25, 1.25]], [[0.0, 1.0 / 0.9], [1.0 / 0.9, 0.0]]])  # [depth=2][branch][sample]
+    eng = _engine_for(cfg, spec, params)
+    dev = "cuda"
+    eng.bind(dev, 2, training=True)
+    eng.load_base({k: v.to(dev) for k, v in params.items() if ".lora." not in k})
+    flat = _flat_lora(eng, params, dev)
+    out = torch.empty(2, cfg.embed_dim, cfg.grid, cfg.grid, device=dev)
+    dscales = drop.to(dev).contiguous()
+    eng.set_drop_path(dscales)
+    eng.forward(img2.to(dev), flat, out, save_for_backward=True)
+    gflat = torch.zeros_like(flat)
+    eng.backward(gout2.to(dev).contiguous(), gflat)
+    torch.cuda.synchronize()
+    eng.set_drop_path(None)
+    ref_out, ref_grads = O.train_step_reference(img2, params, cfg, spec, gout2, drop_scales=drop)
+    assert rel_l2(out.cpu(), ref_out) < FWD_TOL
+    grads = _unflat_grads(eng, gflat)
+    for k, ref in ref_grads.items():
+        assert rel_l2(grads[k], ref) < GRAD_TOL, k
+
+
+def test_vit_module_public_api_train_eval_and_droppath_statistics():
+    """vit.ViT + lora_layers through autograd: eval() is deterministic and matches the golden; train() applies DropPath."""
+    from sam3_lora_b200.lora_layers import LoRAConfig, apply_lora_to_model
+    from sam3_lora_b200.vit import ViT
+
+    g = load_small_golden()
+    model = ViT(img_size=224, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4.75, window_size=8, global_att_blocks=(1,),
+                pretrain_img_size=112, drop_path_rate=0.5, max_batch=2)
+    apply_lora_to_model(model, LoRAConfig(rank=4, alpha=8, target_modules=["q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2"]))
+    sd = {}
+    for k, v in g["params"].items():
+        for fc in ("fc1", "fc2"):
+            k = k.replace(f"mlp.{fc}.weight", f"mlp.{fc}.original_layer.weight").replace(f"mlp.{fc}.bias", f"mlp.{fc}.original_layer.bias")
+        sd[k] = v
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(m.endswith("freqs_cis") for m in missing)
+    model = model.cuda().eval()
+    img = g["img"].cuda()
+    with torch.no_grad():
+        o1 = model(img)[0]
+        o2 = model(img)[0]
+    assert torch.equal(o1, o2) and rel_l2(o1.cpu(), g["out"]) < FWD_TOL
+    model.train()
+    outs = [model(img)[0].detach() for _ in range(6)]
+    assert any(not torch.equal(outs[0], o) for o in outs[1:])       # block 1 is dropped with p=0.5 per branch
+    model.eval()
+    out = model(img)[0]
+    (out * g["gout"].cuda()).sum().backward()
+    named = dict(model.named_parameters())
+    for k, ref in g["grads"].items():
+        assert rel_l2(named[k].grad.cpu(), ref) < GRAD_TOL, k
+    assert named["blocks.0.attn.qkv.weight"].grad is None
