@@ -46,6 +46,7 @@ extern "C" {
 #define SAM3B_EPI_DGELU 4        /* C16 = acc * gelu_erf'(aux16) */
 #define SAM3B_EPI_ATOMIC_F32 5   /* C32 += alpha*acc (split-K, red.global.add) */
 #define SAM3B_EPI_STORE32 6      /* C32 = alpha*acc (+bias) */
+#define SAM3B_EPI_ADDMASK16 7    /* C16 += dropout_mask/(1-p) * alpha*acc [* gelu_erf'(aux16)] */
 
 const char* sam3b_last_error(void);
 int sam3b_abi_version(void);
@@ -73,6 +74,7 @@ typedef struct sam3b_gemm_desc {
   int32_t max_ctas;                         /* 0 = one CTA per SM */
   int32_t cta_pair;                         /* 0 = default, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles */
   const float* row_scale; int32_t rows_per_scale; /* RESIDUAL_F32: out = res + row_scale[row/rows_per_scale]*(acc+bias) */
+  float drop_p; uint32_t drop_seed;         /* ADDMASK16 */
 } sam3b_gemm_desc;
 
 int sam3b_gemm(const sam3b_gemm_desc* desc, void* stream);
@@ -177,6 +179,12 @@ int sam3b_vit_forward(sam3b_vit* v, const float* img, int32_t batch, const float
 /* DropPath (vitdet.py:610-611, rates linspace(0, 0.1, depth), model_builder.py:80): device array [depth][2][batch]
  * of per-image branch scales (0 or 1/keep; [i][0] attention, [i][1] MLP) for the next forward + backward; NULL = off */
 int sam3b_vit_set_drop_path(sam3b_vit* v, const float* scales);
+/* Adapter dropout (nn.Dropout on the LoRA branch input only, lora_layers.py:43,54) for the next forward + backward.
+ * The mask is a stateless hash of (seed, block, site, row, col) — csrc/rng.cuh — regenerated where needed. p = 0: off */
+int sam3b_vit_set_lora_dropout(sam3b_vit* v, float p, uint32_t seed);
+/* out16 = inverted-dropout(x16) with that mask (exposed for tests of the mask definition) */
+int sam3b_dropout_rows16(const void* x16, int64_t ldx, int32_t rows, int32_t cols, void* out16, int64_t ldo, float p,
+                         uint32_t seed, int32_t dtype, void* stream);
 /* gout: dLoss/dout fp32 NCHW; lora_grad_flat: flat fp32 gradients (overwritten, same layout as lora_flat) */
 int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, void* stream);
 

@@ -93,9 +93,51 @@ def rope_angles_for_block(cfg: ViTConfig, is_global: bool) -> Tensor:
 # --------------------------------------------------------------------------------------------
 # LoRA (lora_layers.py:49-55, 87-91)
 # --------------------------------------------------------------------------------------------
-def lora_delta(x: Tensor, A: Tensor, B: Tensor, scaling: float) -> Tensor:
-    """(x @ A @ B) * alpha/r with A:[in,r], B:[r,out]; dropout is identity here (parity runs use p=0)."""
+def lora_delta(x: Tensor, A: Tensor, B: Tensor, scaling: float, mask: Optional[Tensor] = None) -> Tensor:
+    """(dropout(x) @ A @ B) * alpha/r with A:[in,r], B:[r,out]; `mask` = inverted-dropout scale mask on x
+    (adapter branch only, lora_layers.py:54) or None."""
+    if mask is not None:
+        x = x * mask.to(x.dtype)
     return (x @ A @ B) * scaling
+
+
+# adapter dropout: the CUDA path draws its mask from a stateless hash (sam3_lora_b200/csrc/rng.cuh); restated here
+# so that parity runs with p > 0 see the identical mask.  Rows are the engine's window-major token indices.
+def _lowbias32(x):
+    import numpy as np
+
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16); x *= np.uint32(0x7feb352d)
+    x ^= x >> np.uint32(15); x *= np.uint32(0x846ca68b)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def site_seed(seed: int, block_idx: int, site: int) -> int:
+    return (seed + 0x9E3779B9 * (block_idx * 4 + site + 1)) & 0xFFFFFFFF
+
+
+def dropout_scale_mask(rows: Tensor, cols: int, p: float, seed: int) -> Tensor:
+    """[..., cols] float mask: 1/(1-p) where kept, 0 where dropped; `rows` = engine row index of each token."""
+    import numpy as np
+
+    r = rows.reshape(-1, 1).numpy().astype(np.uint32)
+    c = np.arange(cols, dtype=np.uint32).reshape(1, -1)
+    with np.errstate(over="ignore"):
+        h = _lowbias32(np.uint32(seed) ^ _lowbias32(r * np.uint32(cols) + c))
+    thr = min(int(p * 4294967296.0), 0xFFFFFFFF)
+    keep = h >= np.uint32(thr)
+    return torch.from_numpy(keep.astype(np.float32) / (1.0 - p)).reshape(*rows.shape, cols)
+
+
+def engine_row_index(cfg: "ViTConfig", batch: int) -> Tensor:
+    """[B, G, G] window-major row index of every token (the order the CUDA engine stores tokens in)."""
+    G, ws = cfg.grid, cfg.window_size
+    nwx = G // ws
+    pi = torch.arange(G).view(G, 1).expand(G, G)
+    pj = torch.arange(G).view(1, G).expand(G, G)
+    tok = ((pi // ws) * nwx + pj // ws) * (ws * ws) + (pi % ws) * ws + (pj % ws)
+    return torch.arange(batch).view(-1, 1, 1) * (G * G) + tok.unsqueeze(0)
 
 
 def _lora(params: Dict[str, Tensor], prefix: str, name: str) -> Optional[Tuple[Tensor, Tensor]]:
@@ -109,7 +151,7 @@ def _lora(params: Dict[str, Tensor], prefix: str, name: str) -> Optional[Tuple[T
 # Attention / Block / ViT (vitdet.py:466-515, 597-613, 813-859)
 # --------------------------------------------------------------------------------------------
 def attention(x: Tensor, params: Dict[str, Tensor], prefix: str, cfg: ViTConfig, ang: Tensor,
-              scaling: float) -> Tensor:
+              scaling: float, drop=None) -> Tensor:
     """x [Bw, L, D] -> [Bw, L, D].  qkv Linear, per-head split (reshape(B,L,3,H,hd), vitdet.py:480-482),
     RoPE on q,k (:485), softmax(q k^T / sqrt(hd)) v (:502), proj (:513).  Adapters on the virtual
     q_proj/k_proj/v_proj (row slices of qkv) and out_proj (= proj)."""
@@ -117,10 +159,14 @@ def attention(x: Tensor, params: Dict[str, Tensor], prefix: str, cfg: ViTConfig,
     H, hd = cfg.num_heads, cfg.head_dim
     W, b = params[f"{prefix}.qkv.weight"], params[f"{prefix}.qkv.bias"]
     qkv = x @ W.T + b
+    # drop = (rows [Bw, L], p, seed, block index): one mask per site, shared by the q/k/v adapters (they read the
+    # same masked activation in the fused kernel)
+    m_in = dropout_scale_mask(drop[0], D, drop[1], site_seed(drop[2], drop[3], 0)) if drop else None
+    m_o = dropout_scale_mask(drop[0], D, drop[1], site_seed(drop[2], drop[3], 1)) if drop else None
     for i, name in enumerate(("q_proj", "k_proj", "v_proj")):
         ab = _lora(params, prefix, name)
         if ab is not None:
-            qkv = torch.cat([qkv[..., : i * D], qkv[..., i * D:(i + 1) * D] + lora_delta(x, ab[0], ab[1], scaling),
+            qkv = torch.cat([qkv[..., : i * D], qkv[..., i * D:(i + 1) * D] + lora_delta(x, ab[0], ab[1], scaling, m_in),
                              qkv[..., (i + 1) * D:]], dim=-1)
     qkv = qkv.reshape(Bw, L, 3, H, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
@@ -130,7 +176,7 @@ def attention(x: Tensor, params: Dict[str, Tensor], prefix: str, cfg: ViTConfig,
     y = o @ params[f"{prefix}.proj.weight"].T + params[f"{prefix}.proj.bias"]
     ab = _lora(params, prefix, "out_proj")
     if ab is not None:
-        y = y + lora_delta(o, ab[0], ab[1], scaling)
+        y = y + lora_delta(o, ab[0], ab[1], scaling, m_o)
     return y
 
 
@@ -149,7 +195,7 @@ def window_unpartition(w: Tensor, ws: int, G: int) -> Tensor:
 
 
 def block(x: Tensor, params: Dict[str, Tensor], i: int, cfg: ViTConfig, scaling: float,
-          prefix: str = "", drop: Optional[Tensor] = None) -> Tensor:
+          prefix: str = "", drop: Optional[Tensor] = None, lora_dropout=None) -> Tensor:
     """Pre-norm residual block (vitdet.py:597-613).  `drop` [2, B]: per-sample DropPath scales (0 or 1/keep)
     of the attention and MLP branches (timm DropPath, scale_by_keep); None = identity (eval / parity mode)."""
     p = f"{prefix}blocks.{i}"
@@ -158,13 +204,19 @@ def block(x: Tensor, params: Dict[str, Tensor], i: int, cfg: ViTConfig, scaling:
     is_global = i in cfg.global_att_blocks
     ang = rope_angles_for_block(cfg, is_global)
     shortcut = x
+    rows = engine_row_index(cfg, x.shape[0]) if lora_dropout else None     # lora_dropout = (p, seed)
     h = F.layer_norm(x, (D,), params[f"{p}.norm1.weight"], params[f"{p}.norm1.bias"], cfg.ln_eps)
     if is_global:
-        a = attention(h.reshape(h.shape[0], G * G, D), params, f"{p}.attn", cfg, ang, scaling).reshape(h.shape)
+        dr = (rows.reshape(x.shape[0], G * G), lora_dropout[0], lora_dropout[1], i) if lora_dropout else None
+        a = attention(h.reshape(h.shape[0], G * G, D), params, f"{p}.attn", cfg, ang, scaling, dr).reshape(h.shape)
     else:
         ws = cfg.window_size
         w = window_partition(h, ws)
-        a = attention(w.reshape(w.shape[0], ws * ws, D), params, f"{p}.attn", cfg, ang, scaling)
+        dr = None
+        if lora_dropout:
+            rw = window_partition(rows.unsqueeze(-1), ws).reshape(-1, ws * ws)
+            dr = (rw, lora_dropout[0], lora_dropout[1], i)
+        a = attention(w.reshape(w.shape[0], ws * ws, D), params, f"{p}.attn", cfg, ang, scaling, dr)
         a = window_unpartition(a.reshape(-1, ws, ws, D), ws, G)
     if drop is not None:
         a = a * drop[0].to(a.dtype).view(-1, 1, 1, 1)
@@ -173,12 +225,14 @@ def block(x: Tensor, params: Dict[str, Tensor], i: int, cfg: ViTConfig, scaling:
     h1 = h @ params[f"{p}.mlp.fc1.weight"].T + params[f"{p}.mlp.fc1.bias"]
     ab = _lora(params, f"{p}.mlp", "fc1")
     if ab is not None:
-        h1 = h1 + lora_delta(h, ab[0], ab[1], scaling)
+        m1 = dropout_scale_mask(rows, D, lora_dropout[0], site_seed(lora_dropout[1], i, 2)) if lora_dropout else None
+        h1 = h1 + lora_delta(h, ab[0], ab[1], scaling, m1)
     g = F.gelu(h1)  # exact erf GELU (nn.GELU default, timm Mlp)
     h2 = g @ params[f"{p}.mlp.fc2.weight"].T + params[f"{p}.mlp.fc2.bias"]
     ab = _lora(params, f"{p}.mlp", "fc2")
     if ab is not None:
-        h2 = h2 + lora_delta(g, ab[0], ab[1], scaling)
+        m2 = dropout_scale_mask(rows, cfg.mlp_hidden, lora_dropout[0], site_seed(lora_dropout[1], i, 3)) if lora_dropout else None
+        h2 = h2 + lora_delta(g, ab[0], ab[1], scaling, m2)
     if drop is not None:
         h2 = h2 * drop[1].to(h2.dtype).view(-1, 1, 1, 1)
     return x + h2
@@ -200,13 +254,13 @@ def patch_embed(img: Tensor, params: Dict[str, Tensor], cfg: ViTConfig, prefix: 
 
 
 def vit_forward(img: Tensor, params: Dict[str, Tensor], cfg: ViTConfig, scaling: float = 1.0,
-                prefix: str = "", return_blocks: bool = False, drop_scales: Optional[Tensor] = None):
+                prefix: str = "", return_blocks: bool = False, drop_scales: Optional[Tensor] = None, lora_dropout=None):
     """ViT.forward (vitdet.py:813-859): returns the NCHW feature map [B, D, G, G] after the last block
     (ln_post is Identity in SAM3, model_builder.py:92)."""
     x = patch_embed(img, params, cfg, prefix)
     outs = [x]
     for i in range(cfg.depth):
-        x = block(x, params, i, cfg, scaling, prefix, None if drop_scales is None else drop_scales[i])
+        x = block(x, params, i, cfg, scaling, prefix, None if drop_scales is None else drop_scales[i], lora_dropout)
         if return_blocks:
             outs.append(x)
     y = x.permute(0, 3, 1, 2)
@@ -277,13 +331,13 @@ def lora_keys(params: Dict[str, Tensor]) -> List[str]:
 
 
 def train_step_reference(img: Tensor, params: Dict[str, Tensor], cfg: ViTConfig, spec: LoRASpec,
-                         gout: Tensor, drop_scales: Optional[Tensor] = None) -> Tuple[Tensor, Dict[str, Tensor]]:
+                         gout: Tensor, drop_scales: Optional[Tensor] = None, lora_dropout=None) -> Tuple[Tensor, Dict[str, Tensor]]:
     """Forward + backward of the trunk with only the adapters trainable (apply_lora_to_model freezes
     everything else, lora_layers.py:171-172).  Loss = sum(out * gout).  Returns (out, {lora key: grad})."""
     keys = lora_keys(params)
     leaf = {k: params[k].detach().clone().requires_grad_(True) for k in keys}
     p = dict(params)
     p.update(leaf)
-    out = vit_forward(img, p, cfg, spec.scaling, drop_scales=drop_scales)
+    out = vit_forward(img, p, cfg, spec.scaling, drop_scales=drop_scales, lora_dropout=lora_dropout)
     (out * gout).sum().backward()
     return out.detach(), {k: leaf[k].grad for k in keys}

@@ -14,7 +14,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libsam3b.so"
 
 F16, BF16 = 0, 1
-EPI_STORE16, EPI_QKV_ROPE, EPI_RESIDUAL_F32, EPI_GELU, EPI_DGELU, EPI_ATOMIC_F32, EPI_STORE32 = range(7)
+EPI_STORE16, EPI_QKV_ROPE, EPI_RESIDUAL_F32, EPI_GELU, EPI_DGELU, EPI_ATOMIC_F32, EPI_STORE32, EPI_ADDMASK16 = range(8)
 
 
 class Sam3bError(RuntimeError):
@@ -37,6 +37,7 @@ class GemmDesc(C.Structure):
         ("splitk", C.c_int32), ("c_trans", C.c_int32), ("bn", C.c_int32),
         ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32), ("max_ctas", C.c_int32), ("cta_pair", C.c_int32),
         ("row_scale", C.c_void_p), ("rows_per_scale", C.c_int32),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint32),
     ]
 
 
@@ -104,7 +105,7 @@ def torch_dtype_code(dt) -> int:
 
 def gemm(A, B, C_out, *, epilogue=EPI_STORE16, a_mn=False, b_mn=False, M=None, N=None, K=None,
          bias=None, residual=None, res_row_mod=0, aux=None, rope=None, rope_period=1, rope_cols=0,
-         C2=None, alpha=1.0, splitk=1, c_trans=False, bn=0, dbg_lbo=0, dbg_sbo=0, max_ctas=0, cta_pair=0, row_scale=None, rows_per_scale=1):
+         C2=None, alpha=1.0, splitk=1, c_trans=False, bn=0, dbg_lbo=0, dbg_sbo=0, max_ctas=0, cta_pair=0, row_scale=None, rows_per_scale=1, drop_p=0.0, drop_seed=0):
     """C = epilogue(alpha * A @ B^T).  A:[M,K] (or [K,M] if a_mn), B:[N,K] (or [K,N] if b_mn).
 
     Tensors may be column-slices of wider buffers: leading dimensions are taken from stride(0).
@@ -136,6 +137,7 @@ def gemm(A, B, C_out, *, epilogue=EPI_STORE16, a_mn=False, b_mn=False, M=None, N
     d.splitk, d.c_trans, d.bn = splitk, int(c_trans), bn
     d.dbg_lbo, d.dbg_sbo, d.max_ctas, d.cta_pair = dbg_lbo, dbg_sbo, max_ctas, cta_pair
     d.row_scale, d.rows_per_scale = ptr(row_scale), rows_per_scale
+    d.drop_p, d.drop_seed = drop_p, drop_seed
     check(lib.sam3b_gemm(C.byref(d), current_stream()))
     return C_out
 
@@ -233,3 +235,9 @@ def lora_unpack_grads(site, dA_pack, dB_pack, dA_list, dB_list):
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     check(load().sam3b_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
                                   grad_scale, current_stream()))
+
+
+def dropout_rows16(x16, out16, p, seed):
+    rows, cols = x16.shape
+    check(load().sam3b_dropout_rows16(ptr(x16), x16.stride(0), rows, cols, ptr(out16), out16.stride(0), p, seed,
+                                      torch_dtype_code(x16.dtype), current_stream()))

@@ -26,6 +26,7 @@ int sam3b_gemm(const sam3b_gemm_desc* d, void* stream) {
   a.bias = d->bias;
   a.residual = d->residual; a.ldres = d->ldres; a.res_row_mod = d->res_row_mod;
   a.row_scale = d->row_scale; a.rows_per_scale = d->rows_per_scale;
+  a.drop_p = d->drop_p; a.drop_seed = d->drop_seed;
   a.aux = d->aux; a.ldaux = d->ldaux;
   a.rope = d->rope; a.rope_period = d->rope_period; a.rope_cols = d->rope_cols;
   a.alpha = d->alpha; a.splitk = d->splitk; a.c_trans = d->c_trans; a.bn = d->bn;
@@ -161,6 +162,14 @@ int sam3b_vit_set_drop_path(sam3b_vit* v, const float* scales) {
   if (!v) return fail(-1, "sam3b_vit_set_drop_path: null handle");
   v->eng->set_drop_path(scales);
   return 0;
+}
+int sam3b_vit_set_lora_dropout(sam3b_vit* v, float p, uint32_t seed) {
+  if (!v) return fail(-1, "sam3b_vit_set_lora_dropout: null handle");
+  return v->eng->set_lora_dropout(p, seed);
+}
+int sam3b_dropout_rows16(const void* x16, int64_t ldx, int32_t rows, int32_t cols, void* out16, int64_t ldo, float p,
+                         uint32_t seed, int32_t dtype, void* stream) {
+  return dropout_rows16(x16, ldx, rows, cols, out16, ldo, p, seed, dtype, static_cast<cudaStream_t>(stream));
 }
 int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, void* stream) {
   if (!v) return fail(-1, "sam3b_vit_backward: null handle");

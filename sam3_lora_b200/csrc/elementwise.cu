@@ -6,6 +6,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "rng.cuh"
 
 #include <algorithm>
 #include <type_traits>
@@ -383,6 +384,29 @@ __global__ void __launch_bounds__(256) build_pos_table_kernel(const float* __res
   for (int d = threadIdx.x; d < D; d += blockDim.x) out[(int64_t)t * D + d] = src[d];
 }
 
+
+template <int DT>
+__global__ void __launch_bounds__(256) dropout_rows16_kernel(const uint16_t* __restrict__ x, int64_t ldx, int rows, int cols,
+                                                             uint16_t* __restrict__ out, int64_t ldo, float inv_keep,
+                                                             uint32_t seed, uint32_t thr) {
+  const int c8 = cols / 8;
+  const int64_t n = (int64_t)rows * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / c8), c0 = (int)(i % c8) * 8;
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (int64_t)row * ldx + c0);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float2 f = unpack2<DT>(w[q]);
+      f.x = dropout_keep(seed, row, c0 + 2 * q, cols, thr) ? f.x * inv_keep : 0.f;
+      f.y = dropout_keep(seed, row, c0 + 2 * q + 1, cols, thr) ? f.y * inv_keep : 0.f;
+      o[q] = pack2<DT>(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(out + (int64_t)row * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 template <typename F>
 int dispatch_vpt(int D, F&& f) {
   switch (D) {
@@ -448,6 +472,20 @@ int pack_weight(const float* W, int N, int K, void* dst16, int64_t ld, int trans
 
 int build_pos_table(const float* pos_embed, int side, int G, int ws, int D, float* out, cudaStream_t s) {
   build_pos_table_kernel<<<G * G, 256, 0, s>>>(pos_embed, side, G, ws, D, out);
+  SAM3B_LAUNCHED();
+  return 0;
+}
+
+int dropout_rows16(const void* x16, int64_t ldx, int rows, int cols, void* out16, int64_t ldo, float p, uint32_t seed,
+                   int dtype, cudaStream_t s) {
+  SAM3B_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "dropout_rows16: cols / ld must be multiples of 8");
+  SAM3B_REQUIRE(p >= 0.f && p < 1.f, "dropout_rows16: p=%f outside [0,1)", p);
+  const int64_t n = (int64_t)rows * (cols / 8);
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
+  const float inv_keep = 1.f / (1.f - p);
+  const uint32_t thr = dropout_threshold(p);
+  if (dtype == 0) dropout_rows16_kernel<0><<<blocks, 256, 0, s>>>((const uint16_t*)x16, ldx, rows, cols, (uint16_t*)out16, ldo, inv_keep, seed, thr);
+  else dropout_rows16_kernel<1><<<blocks, 256, 0, s>>>((const uint16_t*)x16, ldx, rows, cols, (uint16_t*)out16, ldo, inv_keep, seed, thr);
   SAM3B_LAUNCHED();
   return 0;
 }

@@ -29,6 +29,10 @@ int pack_weight(const float* W, int N, int K, void* dst16, int64_t ld, int trans
 // out[t][:] = pos_embed[1 + (pi % side)*side + (pj % side)][:] for token t at patch (pi, pj).
 int build_pos_table(const float* pos_embed, int side, int G, int ws, int D, float* out, cudaStream_t s);
 
+// out16[row][c] = keep(row,c) ? x16[row][c] / (1-p) : 0  for c < cols (inverted dropout, mask from rng.cuh)
+int dropout_rows16(const void* x16, int64_t ldx, int rows, int cols, void* out16, int64_t ldo, float p, uint32_t seed,
+                   int dtype, cudaStream_t s);
+
 // y16[row][0..D) = (16-bit) x[row][0..D)
 int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s);
 

@@ -21,6 +21,7 @@
 #include "attn.cuh"
 #include "common.h"
 #include "gemm.cuh"
+#include "rng.cuh"
 
 namespace sam3b {
 
@@ -157,6 +158,7 @@ void VitEngine::layout_work(Bump& b, int batch, bool training) {
     dxn16_ = b.take<uint16_t>(M * D_);
     dO16_ = b.take<uint16_t>(M * D_);
     dqkv16_ = b.take<uint16_t>(M * (3 * D_ + Rmax_));
+    xd16_ = b.take<uint16_t>(M * std::max(Dm_, D_));
     const int max_feat = std::max(3 * D_, Dm_);
     dA_pack_ = b.take<float>((int64_t)max_feat * std::max(Rmax_, 1));
     dB_pack_ = b.take<float>((int64_t)max_feat * std::max(Rmax_, 1));
@@ -284,12 +286,29 @@ int VitEngine::pack_site(const Site& st, const float* lora_flat, cudaStream_t s)
   return lora_pack(make_site(st, lora_flat), st.down_T, st.w_ext, st.ldw, st.up_pack, st.wt_ext, st.ldwt, cfg_.dtype, s);
 }
 
-// act[:, in .. in+R) = s * act[:, :in] . A   (skinny GEMM; B operand = down_T [R][in])
-int VitEngine::site_down(const Site& st, uint16_t* act, int64_t ld, int M, cudaStream_t s) const {
+int VitEngine::set_lora_dropout(float p, uint32_t seed) {
+  SAM3B_REQUIRE(p >= 0.f && p < 1.f, "vit set_lora_dropout: p=%f outside [0,1)", p);
+  drop_p_ = p;
+  drop_seed_ = seed;
+  return 0;
+}
+
+// act[:, in .. in+R) = s * drop(act[:, :in]) . A   (skinny GEMM; B operand = down_T [R][in]).  With adapter
+// dropout the A operand is the masked copy xd16_ (the base branch keeps reading the unmasked act).
+int VitEngine::site_down(const Site& st, uint16_t* act, int64_t ld, int M, int block, int site, cudaStream_t s) const {
   if (st.R == 0) return 0;
+  const uint16_t* src = act;
+  int64_t lds = ld;
+  if (drop_p_ > 0.f) {
+    SAM3B_REQUIRE(xd16_ != nullptr, "vit: adapter dropout needs a training workspace");
+    int rc = dropout_rows16(act, ld, M, st.in, xd16_, st.in, drop_p_, site_seed(drop_seed_, block, site), cfg_.dtype, s);
+    if (rc) return rc;
+    src = xd16_;
+    lds = st.in;
+  }
   GemmArgs a;
   a.M = M; a.N = st.R; a.K = st.in;
-  a.A = act; a.lda = ld; a.B = st.down_T; a.ldb = st.in;
+  a.A = src; a.lda = lds; a.B = st.down_T; a.ldb = st.in;
   a.dtype = cfg_.dtype; a.epilogue = EPI_STORE16; a.alpha = cfg_.lora_scaling;
   a.C = act + st.in; a.ldc = ld; a.bn = 64;
   return gemm_launch(a, s);
@@ -299,8 +318,16 @@ int VitEngine::site_down(const Site& st, uint16_t* act, int64_t ld, int M, cudaS
 // dy_act: [M][out | dT''] (dT'' = s*dy.B^T in the extension).
 //   dB_a = T'_a^T . dy[:, slice_a]      dA_a = x^T . dT''_a
 int VitEngine::site_wgrad(const Site& st, const uint16_t* x_act, int64_t ldx, const uint16_t* dy_act, int64_t lddy, int M,
-                          float* grad_flat, cudaStream_t s) {
+                          float* grad_flat, int block, int site, cudaStream_t s) {
   if (st.R == 0) return 0;
+  const uint16_t* xa = x_act;   // operand of dA = drop(x)^T . dT''
+  int64_t ldxa = ldx;
+  if (fwd_drop_p_ > 0.f) {
+    int rcd = dropout_rows16(x_act, ldx, M, st.in, xd16_, st.in, fwd_drop_p_, site_seed(fwd_drop_seed_, block, site), cfg_.dtype, s);
+    if (rcd) return rcd;
+    xa = xd16_;
+    ldxa = st.in;
+  }
   SAM3B_CHECK_CUDA(cudaMemsetAsync(dA_pack_, 0, (size_t)st.in * st.R * 4, s));
   SAM3B_CHECK_CUDA(cudaMemsetAsync(dB_pack_, 0, (size_t)st.R * st.out * 4, s));
   const int kb_total = (M + 63) / 64;
@@ -322,7 +349,7 @@ int VitEngine::site_wgrad(const Site& st, const uint16_t* x_act, int64_t ldx, co
   {  // dA_pack [in][R] = x^T . dT''
     GemmArgs a;
     a.M = st.in; a.N = st.R; a.K = M;
-    a.A = x_act; a.lda = ldx; a.a_mn = 1;
+    a.A = xa; a.lda = ldxa; a.a_mn = 1;
     a.B = dy_act + st.out; a.ldb = lddy; a.b_mn = 1;
     a.dtype = cfg_.dtype; a.epilogue = EPI_ATOMIC_F32;
     a.C = dA_pack_; a.ldc = st.R; a.splitk = splitk_for(st.in);
@@ -344,6 +371,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
   SAM3B_REQUIRE(batch >= 1 && batch <= bound_batch_, "vit forward: batch %d exceeds bound batch %d", batch, bound_batch_);
   SAM3B_REQUIRE(!save || bound_training_, "vit forward: save_for_backward needs a training workspace");
   SAM3B_REQUIRE(lora_numel_ == 0 || lora_flat != nullptr, "vit forward: lora parameters missing");
+  SAM3B_REQUIRE(drop_p_ == 0.f || bound_training_, "vit forward: adapter dropout needs a training workspace");
   const int M = batch * T_;
   const int dt = cfg_.dtype;
   const int ws2 = cfg_.window_size * cfg_.window_size;
@@ -371,7 +399,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
       if ((rc = pack_site(*st, lora_flat, s))) return rc;
     // ---- attention half: x_mid = x + proj(attn(rope(qkv(LN1(x)))))
     if ((rc = layernorm_fwd(x_[i], w.g1, w.b1, cfg_.ln_eps, M, D_, a.xn1, ld_xn1, dt, a.mean1, a.rstd1, s))) return rc;
-    if ((rc = site_down(w.qkv, a.xn1, ld_xn1, M, s))) return rc;
+    if ((rc = site_down(w.qkv, a.xn1, ld_xn1, M, i, 0, s))) return rc;
     {
       GemmArgs g;
       g.M = M; g.N = 3 * D_; g.K = (int)ld_xn1;
@@ -387,7 +415,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
       f.dtype = dt; f.O = a.O; f.ldo = ld_O; f.lse2 = a.lse2;
       if ((rc = attn_fwd_launch(f, s))) return rc;
     }
-    if ((rc = site_down(w.proj, a.O, ld_O, M, s))) return rc;
+    if ((rc = site_down(w.proj, a.O, ld_O, M, i, 1, s))) return rc;
     {
       GemmArgs g;
       g.M = M; g.N = D_; g.K = (int)ld_O;
@@ -400,7 +428,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
     }
     // ---- MLP half: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
     if ((rc = layernorm_fwd(a.x_mid, w.g2, w.b2, cfg_.ln_eps, M, D_, a.xn2, ld_xn2, dt, a.mean2, a.rstd2, s))) return rc;
-    if ((rc = site_down(w.fc1, a.xn2, ld_xn2, M, s))) return rc;
+    if ((rc = site_down(w.fc1, a.xn2, ld_xn2, M, i, 2, s))) return rc;
     {
       GemmArgs g;
       g.M = M; g.N = Dm_; g.K = (int)ld_xn2;
@@ -409,7 +437,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
       g.C = a.h; g.ldc = Dm_; g.C2 = a.g; g.ldc2 = ld_g;
       if ((rc = gemm_launch(g, s))) return rc;
     }
-    if ((rc = site_down(w.fc2, a.g, ld_g, M, s))) return rc;
+    if ((rc = site_down(w.fc2, a.g, ld_g, M, i, 3, s))) return rc;
     {
       GemmArgs g;
       g.M = M; g.N = D_; g.K = (int)ld_g;
@@ -426,6 +454,8 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
   last_batch_ = batch;
   last_saved_ = save;
   fwd_drop_scales_ = drop_scales_;
+  fwd_drop_p_ = drop_p_;
+  fwd_drop_seed_ = drop_seed_;
   return 0;
 }
 
@@ -457,12 +487,22 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
   };
   // dst = [dy | dT''] . [W^T | A]^T  (dgrad through the frozen weight + the adapter in one K loop)
   auto site_dgrad = [&](const Site& st, const uint16_t* dy, int64_t ld, int epi, void* dst, int64_t lddst,
-                        const void* aux, int64_t ldaux) -> int {
+                        const void* aux, int64_t ldaux, int block, int site) -> int {
+    const bool masked = fwd_drop_p_ > 0.f && st.R > 0;
     GemmArgs a;
-    a.M = M; a.N = st.in; a.K = st.out + st.R;
+    a.M = M; a.N = st.in; a.K = masked ? st.out : st.out + st.R;
     a.A = dy; a.lda = ld; a.B = st.wt_ext; a.ldb = st.ldwt;
     a.dtype = dt; a.epilogue = epi; a.C = dst; a.ldc = lddst; a.aux = aux; a.ldaux = ldaux;
-    return gemm_launch(a, s);
+    int r2 = gemm_launch(a, s);
+    if (r2 || !masked) return r2;
+    // adapter part under dropout: dst += mask/(1-p) * (dT'' . A^T) [* gelu'(h)], K = R
+    GemmArgs b;
+    b.M = M; b.N = st.in; b.K = st.R;
+    b.A = dy + st.out; b.lda = ld; b.B = st.wt_ext + st.out; b.ldb = st.ldwt;
+    b.dtype = dt; b.epilogue = EPI_ADDMASK16; b.C = dst; b.ldc = lddst;
+    if (epi == EPI_DGELU) { b.aux = aux; b.ldaux = ldaux; }
+    b.drop_p = fwd_drop_p_; b.drop_seed = site_seed(fwd_drop_seed_, block, site);
+    return gemm_launch(b, s);
   };
 
   for (int i = cfg_.depth - 1; i >= 0; --i) {
@@ -472,18 +512,18 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
     const int64_t ld_dh = Dm_ + Rmax_, ld_dqkv = 3 * D_ + Rmax_;
     // ---- MLP half.  dx16_ holds dy for fc2 (width D [+R]).
     if ((rc = site_up_grad(w.fc2, dx16_, ld_dx16))) return rc;
-    if ((rc = site_wgrad(w.fc2, a.g, ld_g, dx16_, ld_dx16, M, grad_flat, s))) return rc;
-    if ((rc = site_dgrad(w.fc2, dx16_, ld_dx16, EPI_DGELU, dh16_, ld_dh, a.h, Dm_))) return rc;
+    if ((rc = site_wgrad(w.fc2, a.g, ld_g, dx16_, ld_dx16, M, grad_flat, i, 3, s))) return rc;
+    if ((rc = site_dgrad(w.fc2, dx16_, ld_dx16, EPI_DGELU, dh16_, ld_dh, a.h, Dm_, i, 3))) return rc;
     if ((rc = site_up_grad(w.fc1, dh16_, ld_dh))) return rc;
-    if ((rc = site_wgrad(w.fc1, a.xn2, ld_xn2, dh16_, ld_dh, M, grad_flat, s))) return rc;
-    if ((rc = site_dgrad(w.fc1, dh16_, ld_dh, EPI_STORE16, dxn16_, D_, nullptr, 0))) return rc;
+    if ((rc = site_wgrad(w.fc1, a.xn2, ld_xn2, dh16_, ld_dh, M, grad_flat, i, 2, s))) return rc;
+    if ((rc = site_dgrad(w.fc1, dh16_, ld_dh, EPI_STORE16, dxn16_, D_, nullptr, 0, i, 2))) return rc;
     // dx_mid = dx + dLN2(dxn2)
     if ((rc = layernorm_bwd(dxn16_, D_, a.x_mid, a.mean2, a.rstd2, w.g2, dx, M, D_, dx_alt, dx16_, ld_dx16, dt, s, drop(i, 0), T_))) return rc;
     std::swap(dx, dx_alt);
     // ---- attention half.  dx16_ holds dy for proj.
     if ((rc = site_up_grad(w.proj, dx16_, ld_dx16))) return rc;
-    if ((rc = site_wgrad(w.proj, a.O, ld_O, dx16_, ld_dx16, M, grad_flat, s))) return rc;
-    if ((rc = site_dgrad(w.proj, dx16_, ld_dx16, EPI_STORE16, dO16_, D_, nullptr, 0))) return rc;
+    if ((rc = site_wgrad(w.proj, a.O, ld_O, dx16_, ld_dx16, M, grad_flat, i, 1, s))) return rc;
+    if ((rc = site_dgrad(w.proj, dx16_, ld_dx16, EPI_STORE16, dO16_, D_, nullptr, 0, i, 1))) return rc;
     if ((rc = attn_delta(dO16_, D_, a.O, ld_O, M, H_, dt, delta_, s))) return rc;
     {
       AttnBwdArgs b;
@@ -494,9 +534,9 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
       if ((rc = attn_bwd_launch(b, s))) return rc;
     }
     if ((rc = site_up_grad(w.qkv, dqkv16_, ld_dqkv))) return rc;
-    if ((rc = site_wgrad(w.qkv, a.xn1, ld_xn1, dqkv16_, ld_dqkv, M, grad_flat, s))) return rc;
+    if ((rc = site_wgrad(w.qkv, a.xn1, ld_xn1, dqkv16_, ld_dqkv, M, grad_flat, i, 0, s))) return rc;
     if (i == 0) break;  // nothing upstream of block 0 is trainable (patch embed / pos / ln_pre are frozen)
-    if ((rc = site_dgrad(w.qkv, dqkv16_, ld_dqkv, EPI_STORE16, dxn16_, D_, nullptr, 0))) return rc;
+    if ((rc = site_dgrad(w.qkv, dqkv16_, ld_dqkv, EPI_STORE16, dxn16_, D_, nullptr, 0, i, 0))) return rc;
     if ((rc = layernorm_bwd(dxn16_, D_, x_[i], a.mean1, a.rstd1, w.g1, dx, M, D_, dx_alt, dx16_, ld_dx16, dt, s, drop(i - 1, 1), T_))) return rc;
     std::swap(dx, dx_alt);
   }

@@ -55,6 +55,8 @@ class VitEngine {
   // (0 or 1/keep; [i][0] attention branch, [i][1] MLP branch) used by the next forward AND its backward.
   // nullptr disables it (eval mode / drop_path 0).
   void set_drop_path(const float* scales) { drop_scales_ = scales; }
+  // Adapter dropout (lora_layers.py:43,54): probability and seed for the next forward and its backward; p = 0 disables.
+  int set_lora_dropout(float p, uint32_t seed);
 
  private:
   struct Site {
@@ -79,9 +81,9 @@ class VitEngine {
   void layout_work(Bump& b, int batch, bool training);
   int pack_site(const Site& st, const float* lora_flat, cudaStream_t s) const;
   LoraSite make_site(const Site& st, const float* flat) const;
-  int site_down(const Site& st, uint16_t* act, int64_t ld, int M, cudaStream_t s) const;
+  int site_down(const Site& st, uint16_t* act, int64_t ld, int M, int block, int site, cudaStream_t s) const;
   int site_wgrad(const Site& st, const uint16_t* x_act, int64_t ldx, const uint16_t* dy_act, int64_t lddy, int M,
-                 float* grad_flat, cudaStream_t s);
+                 float* grad_flat, int block, int site, cudaStream_t s);
 
   VitConfig cfg_;
   int G_ = 0, T_ = 0, D_ = 0, H_ = 0, Dm_ = 0, Kpe_ = 0, Kpe_pad_ = 0;
@@ -105,6 +107,9 @@ class VitEngine {
   float *dxa_ = nullptr, *dxb_ = nullptr, *delta_ = nullptr, *dA_pack_ = nullptr, *dB_pack_ = nullptr;
   uint16_t *dx16_ = nullptr, *dh16_ = nullptr, *dxn16_ = nullptr, *dO16_ = nullptr, *dqkv16_ = nullptr;
   int Rmax_ = 0;
+  float drop_p_ = 0.f, fwd_drop_p_ = 0.f;
+  uint32_t drop_seed_ = 0, fwd_drop_seed_ = 0;
+  uint16_t* xd16_ = nullptr;  // dropout(x) scratch [M][max in]
   const float* drop_scales_ = nullptr;
   const float* fwd_drop_scales_ = nullptr;  // what the saved forward used
   int last_batch_ = 0;

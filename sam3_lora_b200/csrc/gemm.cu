@@ -23,6 +23,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace sam3b {
 
@@ -33,6 +34,7 @@ struct GemmParams {
   const float* bias;
   const float* res; int64_t ldres; int res_row_mod;
   const float* row_scale; int rows_per_scale;
+  float drop_inv_keep; uint32_t drop_seed, drop_thr;
   const void* aux; int64_t ldaux;
   const float2* rope; int rope_period; int rope_cols;
   float alpha;
@@ -111,7 +113,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
 
-  if constexpr (EPI != EPI_ATOMIC_F32 && EPI != EPI_DGELU) {
+  if constexpr (EPI != EPI_ATOMIC_F32 && EPI != EPI_DGELU && EPI != EPI_ADDMASK16) {
     if (p.bias != nullptr) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
@@ -182,6 +184,30 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
       }
     }
     store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
+  } else if constexpr (EPI == EPI_ADDMASK16) {
+    // data-gradient of the adapter branch under dropout: dx += mask/(1-p) * (dT''.A^T) [* gelu'(h) on the fc2 site]
+    uint4* c4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.C) + (int64_t)row * p.ldc + col);
+    const uint4* h4 = p.aux == nullptr ? nullptr
+                                       : reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row * p.ldaux + col);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q * 8 < nvalid) {
+        uint4 cu = c4[q];
+        uint32_t cw[4] = {cu.x, cu.y, cu.z, cu.w};
+        uint32_t hw[4] = {0, 0, 0, 0};
+        if (h4 != nullptr) { const uint4 hu = h4[q]; hw[0] = hu.x; hw[1] = hu.y; hw[2] = hu.z; hw[3] = hu.w; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 c = unpack2<DT>(cw[e]);
+          float a0 = v[q * 8 + 2 * e] * p.drop_inv_keep, a1 = v[q * 8 + 2 * e + 1] * p.drop_inv_keep;
+          if (h4 != nullptr) { const float2 hh = unpack2<DT>(hw[e]); a0 *= dgelu_erf(hh.x); a1 *= dgelu_erf(hh.y); }
+          if (dropout_keep(p.drop_seed, row, col + q * 8 + 2 * e, p.N, p.drop_thr)) c.x += a0;
+          if (dropout_keep(p.drop_seed, row, col + q * 8 + 2 * e + 1, p.N, p.drop_thr)) c.y += a1;
+          cw[e] = pack2<DT>(c.x, c.y);
+        }
+        c4[q] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+      }
+    }
   } else if constexpr (EPI == EPI_ATOMIC_F32) {
     float* C = reinterpret_cast<float*>(p.C);
 #pragma unroll
@@ -564,6 +590,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.bias = a.bias;
   p.res = a.residual; p.ldres = a.ldres; p.res_row_mod = a.res_row_mod;
   p.row_scale = a.row_scale; p.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
+  p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_seed = a.drop_seed; p.drop_thr = dropout_threshold(a.drop_p);
   p.aux = a.aux; p.ldaux = a.ldaux;
   p.rope = reinterpret_cast<const float2*>(a.rope); p.rope_period = a.rope_period > 0 ? a.rope_period : 1;
   p.rope_cols = a.rope_cols;
@@ -572,7 +599,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.mn_sbo = a.dbg_sbo > 0 ? a.dbg_sbo : 1024;
 
   const bool is16 = (a.epilogue == EPI_STORE16 || a.epilogue == EPI_QKV_ROPE || a.epilogue == EPI_GELU ||
-                     a.epilogue == EPI_DGELU);
+                     a.epilogue == EPI_DGELU || a.epilogue == EPI_ADDMASK16);
   if (a.epilogue != EPI_ATOMIC_F32) {
     SAM3B_REQUIRE(a.ldc % (is16 ? 8 : 4) == 0, "gemm: ldc=%lld breaks 16-byte store alignment", (long long)a.ldc);
     SAM3B_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "gemm: C not 16-byte aligned");
@@ -609,6 +636,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
       case EPI_GELU: return launch_pair_dt<EPI_GELU>(a, p, stream);
       case EPI_DGELU: return launch_pair_dt<EPI_DGELU>(a, p, stream);
       case EPI_STORE32: return launch_pair_dt<EPI_STORE32>(a, p, stream);
+      case EPI_ADDMASK16: return launch_pair_dt<EPI_ADDMASK16>(a, p, stream);
       default: break;
     }
   }
@@ -619,6 +647,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     case EPI_GELU: return launch_dt<256, EPI_GELU, false, false>(a, p, stream);
     case EPI_DGELU: return launch_dt<256, EPI_DGELU, false, false>(a, p, stream);
     case EPI_STORE32: return launch_dt<256, EPI_STORE32, false, false>(a, p, stream);
+    case EPI_ADDMASK16: return launch_dt<256, EPI_ADDMASK16, false, false>(a, p, stream);
     default: return fail(-1, "gemm: epilogue %d not instantiated for BN=256", a.epilogue);
   }
 }

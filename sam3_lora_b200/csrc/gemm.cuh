@@ -14,6 +14,7 @@ enum GemmEpilogue : int {
   EPI_DGELU = 4,         // C16 = acc * gelu_erf'(aux16)
   EPI_ATOMIC_F32 = 5,    // C32 (+)= alpha*acc with red.global.add (split-K), optional transpose
   EPI_STORE32 = 6,       // C32 = alpha*acc (+bias)
+  EPI_ADDMASK16 = 7,     // C16 += keep(row,col)/(1-p) * alpha*acc [* gelu_erf'(aux16)]   (adapter dgrad under dropout)
   EPI_COUNT
 };
 
@@ -27,6 +28,7 @@ struct GemmArgs {
   void* C2 = nullptr; int64_t ldc2 = 0;
   const float* bias = nullptr;
   const float* residual = nullptr; int64_t ldres = 0; int res_row_mod = 0;
+  float drop_p = 0.f; uint32_t drop_seed = 0;   // EPI_ADDMASK16: mask = rng.cuh dropout_keep(seed, row, col, N)
   const float* row_scale = nullptr; int rows_per_scale = 1;  // EPI_RESIDUAL_F32: out = res + row_scale[row / rows_per_scale] * (acc + bias)  (DropPath)
   const void* aux = nullptr; int64_t ldaux = 0;
   const float* rope = nullptr; int rope_period = 1; int rope_cols = 0;  // rope: [period][32] (cos,sin) pairs

@@ -92,6 +92,8 @@ def _declare(lib):
     lib.sam3b_vit_forward.restype = C.c_int
     lib.sam3b_vit_set_drop_path.argtypes = [C.c_void_p, C.c_void_p]
     lib.sam3b_vit_set_drop_path.restype = C.c_int
+    lib.sam3b_vit_set_lora_dropout.argtypes = [C.c_void_p, C.c_float, C.c_uint32]
+    lib.sam3b_vit_set_lora_dropout.restype = C.c_int
     lib.sam3b_vit_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sam3b_vit_backward.restype = C.c_int
     lib._vit_declared = True
@@ -213,6 +215,9 @@ class VitEngine:
         """scales: fp32 CUDA tensor [depth, 2, batch] (0 or 1/keep) or None; the caller keeps it alive until backward."""
         self._drop_scales = scales
         _lib.check(self.lib.sam3b_vit_set_drop_path(self._h, _lib.ptr(scales)))
+
+    def set_lora_dropout(self, p: float, seed: int):
+        _lib.check(self.lib.sam3b_vit_set_lora_dropout(self._h, float(p), int(seed) & 0xFFFFFFFF))
 
     def backward(self, gout, grad_flat):
         _lib.check(self.lib.sam3b_vit_backward(self._h, gout.data_ptr(), _lib.ptr(grad_flat), _lib.current_stream()))

@@ -163,10 +163,6 @@ class SAM3TrainerNative:
         tc = self.config["training"]
         self.batch_size = int(tc["batch_size"])
         dropout = float(lc.get("dropout", 0.0))
-        if dropout > 0:
-            print(f"[sam3_lora_b200] lora.dropout={dropout} requested; the trunk engine runs adapters without dropout "
-                  "this round (DESIGN.md §6) -> using 0.0")
-            dropout = 0.0
         self.model = TrunkWithProxyHead(max_batch=self.batch_size, **(vit_overrides or {}))
         lora_config = LoRAConfig(
             rank=lc["rank"], alpha=lc["alpha"], dropout=dropout, target_modules=lc["target_modules"],

@@ -97,6 +97,11 @@ class _TrunkFn(torch.autograd.Function):
         img = images.detach().float().contiguous()
         ctx.drop = vit._drop_scales_for(B, images.device)   # keeps the tensor alive until backward
         eng.set_drop_path(ctx.drop)
+        p_drop = vit._lora_dropout_p if (vit.training and need_grad) else 0.0
+        seed = vit.lora_dropout_seed_override
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        eng.set_lora_dropout(p_drop, seed)
         eng.forward(img, flat, out, save_for_backward=need_grad)
         ctx.vit = vit
         ctx.n = len(lora_params)
@@ -124,6 +129,8 @@ class ViT(nn.Module):
         # (model_builder.py:80); active in train() mode only.
         self.drop_path_rates = [drop_path_rate * i / (depth - 1) for i in range(depth)] if depth > 1 else [float(drop_path_rate)]
         self.drop_scales_override: Optional[torch.Tensor] = None  # tests: inject [depth, 2, B] branch scales
+        self.lora_dropout_seed_override: Optional[int] = None     # tests: fix the adapter-dropout mask seed
+        self._lora_dropout_p = 0.0
         self.spec = VitSpec(img_size=img_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim, depth=depth,
                             num_heads=num_heads, mlp_hidden=int(embed_dim * mlp_ratio), window_size=window_size,
                             global_blocks=tuple(global_att_blocks), pretrain_img_size=pretrain_img_size, ln_eps=ln_eps,
@@ -209,8 +216,10 @@ class ViT(nn.Module):
             per_block.setdefault(i, set()).add(t)
         if layers and (len(per_block) != self.spec.depth or any(v != set(targets) for v in per_block.values())):
             raise L.Sam3bError("the trunk engine needs the same adapter targets in every block")
-        if any(l.dropout_p > 0 for _, _, l in layers) and self.training:
-            raise L.Sam3bError("adapter dropout > 0 is not implemented in the trunk engine yet; set lora.dropout: 0.0")
+        pset = {float(l.dropout_p) for _, _, l in layers}
+        if len(pset) > 1:
+            raise L.Sam3bError("all trunk adapters must share one dropout probability")
+        self._lora_dropout_p = pset.pop() if pset else 0.0
         rank = ranks.pop() if ranks else 0
         scaling = scal.pop() if scal else 1.0
         key = (tuple(targets), rank, scaling, self.operand_dtype, str(images.device))

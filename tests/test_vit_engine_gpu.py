@@ -226,3 +226,43 @@ def test_vit_module_public_api_train_eval_and_droppath_statistics():
     for k, ref in g["grads"].items():
         assert rel_l2(named[k].grad.cpu(), ref) < GRAD_TOL, k
     assert named["blocks.0.attn.qkv.weight"].grad is None
+
+
+def test_adapter_dropout_mask_definition_matches_oracle_hash():
+    """sam3b_dropout_rows16 (csrc/rng.cuh) == oracle.dropout_scale_mask for the same (seed, rows, cols, p)."""
+    from sam3_lora_b200 import _lib as L
+
+    rows, cols, p, seed = 300, 608, 0.25, 0xC0FFEE
+    x = torch.ones(rows, cols + 8, device="cuda", dtype=torch.float16)
+    out = torch.zeros(rows, cols, device="cuda", dtype=torch.float16)
+    L.dropout_rows16(x[:, :cols], out, p, seed)
+    torch.cuda.synchronize()
+    ref = O.dropout_scale_mask(torch.arange(rows), cols, p, seed)
+    assert torch.equal(out.float().cpu() > 0, ref > 0)
+    assert abs((ref > 0).float().mean().item() - (1 - p)) < 0.01
+    assert torch.allclose(out.float().cpu(), ref, atol=1e-3)
+
+
+def test_adapter_dropout_forward_backward_matches_oracle():
+    """lora.dropout > 0 (full_lora_config.yaml uses 0.1): dropout on the adapter branch only, same mask in the oracle."""
+    g = load_small_golden()
+    cfg, spec, params = g["cfg"], g["spec"], g["params"]
+    p_drop, seed = 0.25, 12345
+    eng = _engine_for(cfg, spec, params)
+    dev = "cuda"
+    eng.bind(dev, 1, training=True)
+    eng.load_base({k: v.to(dev) for k, v in params.items() if ".lora." not in k})
+    flat = _flat_lora(eng, params, dev)
+    out = torch.empty(1, cfg.embed_dim, cfg.grid, cfg.grid, device=dev)
+    eng.set_lora_dropout(p_drop, seed)
+    eng.forward(g["img"].to(dev), flat, out, save_for_backward=True)
+    gflat = torch.zeros_like(flat)
+    eng.backward(g["gout"].to(dev).contiguous(), gflat)
+    torch.cuda.synchronize()
+    eng.set_lora_dropout(0.0, 0)
+    ref_out, ref_grads = O.train_step_reference(g["img"], params, cfg, spec, g["gout"], lora_dropout=(p_drop, seed))
+    assert rel_l2(out.cpu(), ref_out) < FWD_TOL
+    assert rel_l2(ref_out, g["out"]) > 1e-3          # the mask really changes the result
+    grads = _unflat_grads(eng, gflat)
+    for k, ref in ref_grads.items():
+        assert rel_l2(grads[k], ref) < GRAD_TOL, k
