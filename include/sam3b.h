@@ -96,10 +96,10 @@ typedef struct sam3b_attn_desc {
   const void* qkv; int64_t ldqkv;   /* [tokens][>=3D] 16-bit: q | k | v, head h at columns h*64 of each block */
   int32_t tokens, seg_len, D, heads, head_dim, dtype;
   void* O; int64_t ldo;             /* fwd out / bwd in: [tokens][>=D] 16-bit */
-  float* lse2;                      /* [tokens][heads], log2-domain log-sum-exp (fwd out / bwd in) */
+  float* lse2;                      /* [heads][tokens], log2-domain log-sum-exp (fwd out / bwd in) */
   /* backward only */
   const void* dO; int64_t lddo;
-  float* delta;                     /* [tokens][heads] scratch: rowsum(dO*O), written by the call */
+  float* delta;                     /* [heads][tokens] scratch: rowsum(dO*O), written by the call */
   void* dqkv; int64_t lddqkv;       /* [tokens][>=3D] 16-bit out: gradients w.r.t. the un-rotated q | k | v */
   const float* rope; int32_t rope_period;
 } sam3b_attn_desc;

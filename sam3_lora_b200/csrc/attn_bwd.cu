@@ -96,7 +96,7 @@ __device__ __forceinline__ void store_grad_chunk(const BwdParams& p, uint32_t ta
 // =========================================================================================
 // dK / dV
 // =========================================================================================
-constexpr int DKDV_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + 2 * A_BYTES + 2 * 2 * BI * 4 + 128;
+constexpr int DKDV_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + 2 * A_BYTES + 2 * 2 * BI * 4 + 128;  // stats: [2 stages][lse2 | delta][64]
 
 template <int DT>
 __global__ void __launch_bounds__(320, 2)
@@ -120,7 +120,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
   uint64_t* sdp_full = bars + 5;
   uint64_t* pds_full = bars + 6;
   uint64_t* acc_done = bars + 7;  // dV/dK MMAs of block j complete (also frees sP/sdS)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sdp_free = bars + 8;  // compute warps have S^T/dP^T of block j in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5;
   const int tile = blockIdx.x % p.tiles;
@@ -134,7 +135,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
     tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(acc_done, 1);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(acc_done, 1); mbar_init(sdp_free, 256);
     fence_barrier_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
@@ -152,9 +153,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j & 1;
         if (j >= 2) mbar_wait(&in_free[st], ((j >> 1) - 1) & 1, 10 + st);
-        mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES);
+        mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES + 2 * BI * 4);
         tma_load_2d(sQ + st * I_BYTES, &tmI, &in_full[st], head * HD, seg_row0 + j * BI);
         tma_load_2d(sdO + st * I_BYTES, &tmdO, &in_full[st], head * HD, seg_row0 + j * BI);
+        // per-query statistics of this block (head-major layout: 64 consecutive floats each)
+        const int64_t soff = (int64_t)head * p.total_rows + seg_row0 + j * BI;
+        bulk_load_1d(sStat + st * (2 * BI), p.lse2 + soff, BI * 4, &in_full[st]);
+        bulk_load_1d(sStat + st * (2 * BI) + BI, p.delta + soff, BI * 4, &in_full[st]);
       }
     }
   } else if (warp == 9) {
@@ -163,10 +168,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
       constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1); // A K-major, B MN-major, N=64
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
       mbar_wait(kv_full, 0, 20);
-      for (int j = 0; j < n_blocks; ++j) {
+      // S^T / dP^T of block j+1 are issued as soon as the compute warps hold block j in registers
+      // (sdp_free), i.e. they overlap the exp / pack / store work of block j instead of waiting for it.
+      auto issue_sdp = [&](int j) {
         const int st = j & 1;
         const uint32_t q_addr = smem_u32(sQ + st * I_BYTES), do_addr = smem_u32(sdO + st * I_BYTES);
         mbar_wait(&in_full[st], (j >> 1) & 1, 21);
+        if (j > 0) mbar_wait(sdp_free, (j - 1) & 1, 24);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // S^T = K . Q^T
@@ -175,6 +183,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
         for (int k = 0; k < 4; ++k)  // dP^T = V . dO^T
           umma_f16_ss(tm_dP, make_desc_kmajor(v_addr + k * 32), make_desc_kmajor(do_addr + k * 32), idesc_kk, k > 0);
         umma_commit(sdp_full);
+      };
+      issue_sdp(0);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        const uint32_t q_addr = smem_u32(sQ + st * I_BYTES), do_addr = smem_u32(sdO + st * I_BYTES);
+        if (j + 1 < n_blocks) issue_sdp(j + 1);
         mbar_wait(pds_full, j & 1, 22);
         tc_fence_after();
 #pragma unroll
@@ -198,22 +212,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
     uint8_t* ds_row = sdS + r * 128;
     const int sw = r & 7;
     for (int j = 0; j < n_blocks; ++j) {
-      // stage this block's per-query statistics (threads 0-63: lse2, 64-127: delta)
-      float* stat = sStat + (j & 1) * (2 * BI);
-      if (threadIdx.x < 128) {
-        const int q = seg_row0 + j * BI + (threadIdx.x & 63);
-        const float* src = (threadIdx.x < 64) ? p.lse2 : p.delta;
-        stat[threadIdx.x] = __ldg(src + (int64_t)q * p.H + head);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // per-query statistics were bulk-copied next to Q/dO by the producer (visible once in_full completed)
+      const float* stat = sStat + (j & 1) * (2 * BI);
+      mbar_wait(&in_full[j & 1], (j >> 1) & 1, 33);
       mbar_wait(sdp_full, j & 1, 30);
       tc_fence_after();
-      if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);  // previous dV/dK MMAs finished reading sP/sdS
       {
         uint32_t s[32], d[32];
         tmem_ld_x32(tm_S + lane_off + cc, s);
         tmem_ld_x32(tm_dP + lane_off + cc, d);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(sdp_free);  // TMEM S^T/dP^T may be overwritten by block j+1
         float pv[32], dsv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -221,6 +231,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
           pv[i] = pe;
           dsv[i] = pe * (__uint_as_float(d[i]) - stat[BI + cc + i]);
         }
+        if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);  // previous dV/dK MMAs finished reading sP/sdS
         store_row_chunk16<DT>(p_row, sw, cc >> 3, pv);
         store_row_chunk16<DT>(ds_row, sw, cc >> 3, dsv);
       }
@@ -265,7 +276,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
   uint64_t* sdp_full = bars + 5;
   uint64_t* ds_full = bars + 6;
   uint64_t* acc_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sdp_free = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5;
   const int tile = blockIdx.x % p.tiles;
@@ -279,7 +291,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
     tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(ds_full, 256); mbar_init(acc_done, 1);
+    mbar_init(sdp_full, 1); mbar_init(ds_full, 256); mbar_init(acc_done, 1); mbar_init(sdp_free, 256);
     fence_barrier_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
@@ -308,10 +320,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
       constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1);
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
       mbar_wait(q_full, 0, 20);
-      for (int j = 0; j < n_blocks; ++j) {
+      auto issue_sdp = [&](int j) {
         const int st = j & 1;
         const uint32_t k_addr = smem_u32(sK + st * I_BYTES), v_addr = smem_u32(sV + st * I_BYTES);
         mbar_wait(&in_full[st], (j >> 1) & 1, 21);
+        if (j > 0) mbar_wait(sdp_free, (j - 1) & 1, 24);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // S = Q . K^T
@@ -320,6 +333,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
         for (int k = 0; k < 4; ++k)  // dP = dO . V^T
           umma_f16_ss(tm_dP, make_desc_kmajor(do_addr + k * 32), make_desc_kmajor(v_addr + k * 32), idesc_kk, k > 0);
         umma_commit(sdp_full);
+      };
+      issue_sdp(0);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        const uint32_t k_addr = smem_u32(sK + st * I_BYTES);
+        if (j + 1 < n_blocks) issue_sdp(j + 1);
         mbar_wait(ds_full, j & 1, 22);
         tc_fence_after();
 #pragma unroll
@@ -337,25 +356,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
     const float c = p.scale_log2;
     const int row = t_row0 + r;
     const int row_c = min(row, p.total_rows - 1);
-    const float lse = __ldg(p.lse2 + (int64_t)row_c * p.H + head);
-    const float dlt = __ldg(p.delta + (int64_t)row_c * p.H + head);
+    const float lse = __ldg(p.lse2 + (int64_t)head * p.total_rows + row_c);   // head-major statistics
+    const float dlt = __ldg(p.delta + (int64_t)head * p.total_rows + row_c);
     uint8_t* ds_row = sdS + r * 128;
     const int sw = r & 7;
     for (int j = 0; j < n_blocks; ++j) {
       mbar_wait(sdp_full, j & 1, 30);
       tc_fence_after();
-      if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);
       {
         uint32_t s[32], d[32];
         tmem_ld_x32(tm_S + lane_off + cc, s);
         tmem_ld_x32(tm_dP + lane_off + cc, d);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(sdp_free);
         float dsv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float pe = ex2_approx(__uint_as_float(s[i]) * c - lse);
           dsv[i] = pe * (__uint_as_float(d[i]) - dlt);
         }
+        if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);
         store_row_chunk16<DT>(ds_row, sw, cc >> 3, dsv);
       }
       tc_fence_before();

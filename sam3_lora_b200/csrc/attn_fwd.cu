@@ -45,7 +45,7 @@ struct FwdParams {
   int q_tiles;    // ceil(L / 128)
   int D;          // model width (q/k/v column blocks are D apart)
   void* O; int64_t ldo;
-  float* lse2;    // [tokens][H]
+  float* lse2;    // [H][tokens]
   int H;
   float scale_log2;  // head_dim^-0.5 * log2(e)
   int total_rows;
@@ -174,10 +174,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 32; ++i) { s[i] = a[i]; s[32 + i] = b[i]; }
       }
+      // full blocks (every block when L % 64 == 0) take the predicate-free path: the per-element ISETP/FSEL
+      // of the tail mask were 27 % of this kernel's issued instructions (profiles/r01_ncu_summary.md)
+      const bool full = kv_valid == BKV;
       float m_blk = -INFINITY;
+      if (full) {
 #pragma unroll
-      for (int i = 0; i < BKV; ++i)
-        if (i < kv_valid) m_blk = fmaxf(m_blk, __uint_as_float(s[i]));
+        for (int i = 0; i < BKV; ++i) m_blk = fmaxf(m_blk, __uint_as_float(s[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < BKV; ++i)
+          if (i < kv_valid) m_blk = fmaxf(m_blk, __uint_as_float(s[i]));
+      }
       const bool need = m_blk > m_used + tau;  // always true on the first block (m_used = -inf)
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? m_blk : m_used;
@@ -208,10 +216,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float e[8];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float v = ex2_approx(__uint_as_float(s[q * 8 + i]) * c - mc);
-          e[i] = (q * 8 + i < kv_valid) ? v : 0.f;
+          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[q * 8 + i]), c, -mc));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float v = ex2_approx(fmaf(__uint_as_float(s[q * 8 + i]), c, -mc));
+            e[i] = (q * 8 + i < kv_valid) ? v : 0.f;
+          }
         }
         uint4 u;
         u.x = pack2<DT>(e[0], e[1]); u.y = pack2<DT>(e[2], e[3]); u.z = pack2<DT>(e[4], e[5]); u.w = pack2<DT>(e[6], e[7]);
@@ -248,7 +261,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-    if (valid) p.lse2[(int64_t)row * p.H + head] = m_used * c + log2f(l_run);
+    if (valid) p.lse2[(int64_t)head * p.total_rows + row] = m_used * c + log2f(l_run);  // [heads][tokens]
   }
 
   tc_fence_before();

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restr
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (ok && sub == 0) delta[(int64_t)row * heads + h] = s;
+  if (ok && sub == 0) delta[(int64_t)h * rows + row] = s;  // head-major, like the attention LSE
 }
 
 // patch gather: one block per token row, threads over k (coalesced along v within a patch row)

@@ -36,7 +36,7 @@ int dropout_rows16(const void* x16, int64_t ldx, int rows, int cols, void* out16
 // y16[row][0..D) = (16-bit) x[row][0..D)
 int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s);
 
-// delta[row][h] = sum_c dO[row][h*64+c] * O[row][h*64+c]
+// delta[h][row] = sum_c dO[row][h*64+c] * O[row][h*64+c]   (head-major)
 int attn_delta(const void* dO, int64_t lddo, const void* O, int64_t ldo, int rows, int heads, int dtype, float* delta,
                cudaStream_t s);
 

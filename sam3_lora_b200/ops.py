@@ -40,12 +40,13 @@ def _rpad(r: int) -> int:
 class _FrozenPack:
     """16-bit copies of a frozen weight with room for the adapter K-extension: W_ext [out, in+R],
     W^T_ext [in, out+R].  Cached per weight tensor (re-packed if the tensor is modified in place)."""
-    _cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+    _cache: dict = {}
 
     @classmethod
     def get(cls, W: torch.Tensor, R: int, dt) -> Tuple[torch.Tensor, torch.Tensor]:
-        key = (W._version, W.data_ptr(), R, dt)
-        hit = cls._cache.get(W)
+        ident = id(W)
+        key = (W._version, W.data_ptr(), tuple(W.shape), R, dt)
+        hit = cls._cache.get(ident)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
         out_f, in_f = W.shape
@@ -53,7 +54,9 @@ class _FrozenPack:
         wt_ext = torch.zeros(in_f, out_f + R, device=W.device, dtype=dt)
         w_ext[:, :in_f] = W.detach()
         wt_ext[:, :out_f] = W.detach().t()
-        cls._cache[W] = (key, w_ext, wt_ext)
+        if hit is None:
+            weakref.finalize(W, cls._cache.pop, ident, None)   # drop the packed copies with the weight
+        cls._cache[ident] = (key, w_ext, wt_ext)
         return w_ext, wt_ext
 
 

@@ -89,7 +89,7 @@ def run_case(name: str) -> dict:
         qkv[:, D:2 * D] = k_rot.detach().reshape(T, D).to(dt)
         qkv[:, 2 * D:3 * D] = v.detach().reshape(T, D).to(dt)
         O = torch.zeros(T, D + 64, device=dev, dtype=dt)
-        lse2 = torch.zeros(T, heads, device=dev)
+        lse2 = torch.zeros(heads, T, device=dev)   # head-major
         L.attention_fwd(qkv, Ls, D, heads, O, lse2)
         torch.cuda.synchronize()
         qf = qkv[:, :D].float().reshape(T, heads, 64)
@@ -97,11 +97,11 @@ def run_case(name: str) -> dict:
         vf = qkv[:, 2 * D:3 * D].float().reshape(T, heads, 64)
         O_ref, lse_ref = attn_ref(qf, kf, vf, Ls)
         res["err_O"] = rel_err(O[:, :D].reshape(T, heads, 64), O_ref)
-        res["err_lse"] = rel_err(lse2, lse_ref)
+        res["err_lse"] = rel_err(lse2, lse_ref.T)
         res["pad_untouched"] = bool((O[:, D:] == 0).all().item())
         if mode in ("bwd", "perf"):
             dO = (torch.randn(T, D, device=dev) * 0.5).to(dt)
-            delta = torch.zeros(T, heads, device=dev)
+            delta = torch.zeros(heads, T, device=dev)
             dqkv = torch.zeros(T, 3 * D + 64, device=dev, dtype=dt)
             L.attention_bwd(qkv, Ls, D, heads, O, lse2, dO, delta, dqkv, tab, period)
             torch.cuda.synchronize()
@@ -116,7 +116,7 @@ def run_case(name: str) -> dict:
             res["err_dk"] = rel_err(dqkv[:, D:2 * D].reshape(T, heads, 64), g[:, 1])
             res["err_dv"] = rel_err(dqkv[:, 2 * D:3 * D].reshape(T, heads, 64), g[:, 2])
             delta_ref = (dO.float().reshape(T, heads, 64) * O[:, :D].float().reshape(T, heads, 64)).sum(-1)
-            res["err_delta"] = rel_err(delta, delta_ref)
+            res["err_delta"] = rel_err(delta, delta_ref.T)
         if mode == "perf":
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for _ in range(3):
