@@ -179,8 +179,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool full = kv_valid == BKV;
       float m_blk = -INFINITY;
       if (full) {
+        // 8 independent max chains (a single 64-deep FMNMX dependency chain costs ~300 cycles per block)
+        float mx[8];
 #pragma unroll
-        for (int i = 0; i < BKV; ++i) m_blk = fmaxf(m_blk, __uint_as_float(s[i]));
+        for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(s[i]);
+#pragma unroll
+        for (int i = 8; i < BKV; ++i) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(s[i]));
+        m_blk = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
       } else {
 #pragma unroll
         for (int i = 0; i < BKV; ++i)
@@ -212,7 +217,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (j >= 2) mbar_wait(&pv_done[st], ((j - 2) >> 1) & 1, 32);
       const float mc = m_used * c;
       uint8_t* p_row = sP + st * P_BYTES + r * 128;
-      float l_blk = 0.f;
+      float l_part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float e[8];
@@ -230,10 +235,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         u.x = pack2<DT>(e[0], e[1]); u.y = pack2<DT>(e[2], e[3]); u.z = pack2<DT>(e[4], e[5]); u.w = pack2<DT>(e[6], e[7]);
         // fp32 row sum of the unrounded probabilities (no 16-bit -> fp32 conversions: the conversion pipe
         // shares its 16 lanes/clk with MUFU and is what bounds this loop)
-        l_blk += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+        l_part[q & 3] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
         *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) = u;
       }
-      l_run += l_blk;
+      l_run += (l_part[0] + l_part[1]) + (l_part[2] + l_part[3]);
       tc_fence_before();         // our tcgen05.ld/st are ordered before the MMA warp's next tcgen05 ops
       fence_proxy_async_smem();  // st.shared of P visible to the tensor core (async proxy)
       mbar_arrive(&p_full[st]);

@@ -53,31 +53,33 @@ struct GemmCfg {
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
 };
 
-// Exact-erf GELU (nn.GELU default, timm Mlp) with erf from Abramowitz-Stegun 7.1.26
-//   erf(x) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-x^2),  t = 1/(1 + p x),  x >= 0
-// (|abs error| <= 1.5e-7, i.e. fp32 round-off level) — 2 MUFU + ~12 FMA per element instead of the
-// ~40-instruction libdevice erff, which made the fc1 / fc2-dgrad epilogues slower than their MMAs.
-// exp(-x^2) with x = h/sqrt(2) is exp(-h^2/2): the Gaussian term of GELU' comes for free.
-__device__ __forceinline__ void erf_gauss(float h, float& erf_v, float& gauss) {
-  const float x = fabsf(h) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, x, 1.f));
-  gauss = ex2_approx(-1.4426950408889634f * x * x);  // exp(-h^2/2)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = fmaf(-poly * t, gauss, 1.f);
-  erf_v = __uint_as_float(__float_as_uint(e) | (__float_as_uint(h) & 0x80000000u));  // e >= 0
+// Exact-erf GELU (nn.GELU default, timm Mlp): gelu(h) = h * Phi(h), Phi = standard normal CDF, with
+// Phi(-|h|) = 0.5 * erfc(|h|/sqrt 2) from Abramowitz-Stegun 7.1.26 (|abs error| <= 7.5e-8 on Phi):
+//   q = (b1 t + b2 t^2 + b3 t^3 + b4 t^4 + b5 t^5) * exp(-h^2/2),   t = 1 / (1 + p |h| / sqrt 2),  b_i = a_i / 2
+//   Phi(h) = h >= 0 ? 1 - q : q
+// 2 MUFU (rcp, ex2) + 12 FMA-pipe ops per element; exp(-h^2/2) is also the Gaussian term of GELU'.
+// The libdevice erff / __frcp_rn / exp2f forms cost 30-45 instructions per element, which made the
+// fc1 and fc2-dgrad epilogues slower than their MMAs (profiles/r01_ncu_gemm2_kernelILi3.txt).
+__device__ __forceinline__ void phi_neg_abs(float h, float& q, float& gauss) {
+  const float t = rcp_approx(fmaf(0.23164189f, fabsf(h), 1.f));   // 0.3275911 / sqrt(2)
+  gauss = ex2_approx(h * h * -0.72134752f);                        // exp(-h^2/2)
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  q = poly * t * gauss;
 }
 __device__ __forceinline__ float gelu_erf(float h) {
-  float e, g;
-  erf_gauss(h, e, g);
-  return 0.5f * h * (1.f + e);
+  float q, g;
+  phi_neg_abs(h, q, g);
+  const float r = h * q;
+  return h >= 0.f ? h - r : r;
 }
 __device__ __forceinline__ float dgelu_erf(float h) {
-  float e, g;
-  erf_gauss(h, e, g);
-  return fmaf(h * 0.39894228040143268f, g, 0.5f * (1.f + e));
+  float q, g;
+  phi_neg_abs(h, q, g);
+  const float phi = h >= 0.f ? 1.f - q : q;
+  return fmaf(h * 0.39894228f, g, phi);
 }
 
 template <int DT>
@@ -105,13 +107,17 @@ __device__ __forceinline__ void store32x32(float* base, int64_t off, const float
 }
 
 // One epilogue step: this thread owns output row `row`, columns [col, col+32).
-template <int EPI, int DT>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col, const uint32_t (&r)[32]) {
-  if (row >= p.M || col >= p.N) return;
-  const int nvalid = min(32, p.N - col);  // multiple of 8 (host-checked)
+template <int EPI, int DT, bool FULL>
+__device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, int row, int col, const uint32_t (&r)[32]) {
+  const int nvalid = FULL ? 32 : min(32, p.N - col);  // multiple of 8 (host-checked); FULL folds every column predicate
   float v[32];
+  if (p.alpha == 1.f) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  }
 
   if constexpr (EPI != EPI_ATOMIC_F32 && EPI != EPI_DGELU && EPI != EPI_ADDMASK16) {
     if (p.bias != nullptr) {
@@ -218,6 +224,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
       }
     }
   }
+}
+
+template <int EPI, int DT>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col, const uint32_t (&r)[32]) {
+  if (row >= p.M || col >= p.N) return;
+  if (col + 32 <= p.N) epilogue_chunk_impl<EPI, DT, true>(p, row, col, r);
+  else epilogue_chunk_impl<EPI, DT, false>(p, row, col, r);
 }
 
 template <int BN, int EPI, int DT, bool A_MN, bool B_MN>
