@@ -93,15 +93,23 @@ int sam3b_cast_rows_16(const float* x, int32_t rows, int32_t D, void* y16, int64
 /* apply_rotary_enc + F.scaled_dot_product_attention, vitdet.py:68-90,485,502 (RoPE itself is the
  * SAM3B_EPI_QKV_ROPE epilogue of the qkv GEMM). */
 typedef struct sam3b_attn_desc {
-  const void* qkv; int64_t ldqkv;   /* [tokens][>=3D] 16-bit: q | k | v, head h at columns h*64 of each block */
-  int32_t tokens, seg_len, D, heads, head_dim, dtype;
-  void* O; int64_t ldo;             /* fwd out / bwd in: [tokens][>=D] 16-bit */
-  float* lse2;                      /* [heads][tokens], log2-domain log-sum-exp (fwd out / bwd in) */
+  /* 16-bit operands; head h of q at column q_col0 + 64*h of `q`, of k / v at k_col0 / v_col0 + 64*h of `kv`.
+   * head_dim 64, or 32 stored zero-padded to 64 columns per head (nn.MultiheadAttention sites, E=256, 8 heads). */
+  const void* q; int64_t ldq; int32_t q_cols, q_col0;
+  const void* kv; int64_t ldkv; int32_t kv_cols, k_col0, v_col0;
+  int32_t nseg, Lq, Lk, heads, dtype; /* nseg independent problems: q rows seg*Lq.., kv rows seg*Lk.. */
+  float scale;                         /* logical head_dim^-0.5 */
+  void* O; int64_t ldo; int32_t o_col0; /* fwd out / bwd in */
+  float* lse2;                         /* [heads][nseg*Lq_stat], Lq_stat = Lq rounded up to 64; log2-domain LSE */
+  /* optional: additive float attn_mask [nseg*heads][Lq][Lk], key_padding_mask [nseg][Lk] (non-zero = ignore),
+   * dropout on the attention probabilities (stateless hash mask, csrc/rng.cuh) */
+  const float* bias; const uint8_t* kpm; float drop_p; uint32_t drop_seed;
   /* backward only */
-  const void* dO; int64_t lddo;
-  float* delta;                     /* [heads][tokens] scratch: rowsum(dO*O), written by the call */
-  void* dqkv; int64_t lddqkv;       /* [tokens][>=3D] 16-bit out: gradients w.r.t. the un-rotated q | k | v */
-  const float* rope; int32_t rope_period;
+  const void* dO; int64_t lddo; int32_t do_col0;
+  float* delta;                        /* [heads][nseg*Lq_stat] scratch: rowsum(dO*O), written by the call */
+  void* dq; int64_t lddq; int32_t dq_col0;
+  void* dkv; int64_t lddkv; int32_t dk_col0, dv_col0;
+  const float* rope; int32_t rope_period; /* optional inverse RoPE on dq, dk (ViT); NULL otherwise */
 } sam3b_attn_desc;
 int sam3b_attention_fwd(const sam3b_attn_desc* d, void* stream);
 int sam3b_attention_bwd(const sam3b_attn_desc* d, void* stream);

@@ -12,13 +12,17 @@ i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 class AttnDesc(C.Structure):
     _fields_ = [
-        ("qkv", vp), ("ldqkv", i64),
-        ("tokens", i32), ("seg_len", i32), ("D", i32), ("heads", i32), ("head_dim", i32), ("dtype", i32),
-        ("O", vp), ("ldo", i64),
+        ("q", vp), ("ldq", i64), ("q_cols", i32), ("q_col0", i32),
+        ("kv", vp), ("ldkv", i64), ("kv_cols", i32), ("k_col0", i32), ("v_col0", i32),
+        ("nseg", i32), ("Lq", i32), ("Lk", i32), ("heads", i32), ("dtype", i32),
+        ("scale", f32),
+        ("O", vp), ("ldo", i64), ("o_col0", i32),
         ("lse2", vp),
-        ("dO", vp), ("lddo", i64),
+        ("bias", vp), ("kpm", vp), ("drop_p", f32), ("drop_seed", C.c_uint32),
+        ("dO", vp), ("lddo", i64), ("do_col0", i32),
         ("delta", vp),
-        ("dqkv", vp), ("lddqkv", i64),
+        ("dq", vp), ("lddq", i64), ("dq_col0", i32),
+        ("dkv", vp), ("lddkv", i64), ("dk_col0", i32), ("dv_col0", i32),
         ("rope", vp), ("rope_period", i32),
     ]
 

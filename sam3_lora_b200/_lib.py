@@ -166,13 +166,16 @@ def cast_rows_16(x, y16):
 
 
 def _attn_desc(qkv, seg_len, D, heads, O, lse2):
+    """ViT-style descriptor: q | k | v are column blocks of one buffer, segments of seg_len rows."""
     from ._abi import AttnDesc  # noqa: PLC0415
 
     d = AttnDesc()
-    d.qkv, d.ldqkv = ptr(qkv), qkv.stride(0)
-    d.tokens, d.seg_len, d.D, d.heads, d.head_dim = qkv.shape[0], seg_len, D, heads, D // heads
+    d.q, d.ldq, d.q_cols, d.q_col0 = ptr(qkv), qkv.stride(0), 3 * D, 0
+    d.kv, d.ldkv, d.kv_cols, d.k_col0, d.v_col0 = ptr(qkv), qkv.stride(0), 3 * D, D, 2 * D
+    d.nseg, d.Lq, d.Lk, d.heads = qkv.shape[0] // seg_len, seg_len, seg_len, heads
     d.dtype = torch_dtype_code(qkv.dtype)
-    d.O, d.ldo = ptr(O), O.stride(0)
+    d.scale = (D // heads) ** -0.5
+    d.O, d.ldo, d.o_col0 = ptr(O), O.stride(0), 0
     d.lse2 = ptr(lse2)
     return d
 
@@ -184,10 +187,42 @@ def attention_fwd(qkv, seg_len, D, heads, O, lse2):
 
 def attention_bwd(qkv, seg_len, D, heads, O, lse2, dO, delta, dqkv, rope, rope_period):
     d = _attn_desc(qkv, seg_len, D, heads, O, lse2)
-    d.dO, d.lddo = ptr(dO), dO.stride(0)
+    d.dO, d.lddo, d.do_col0 = ptr(dO), dO.stride(0), 0
     d.delta = ptr(delta)
-    d.dqkv, d.lddqkv = ptr(dqkv), dqkv.stride(0)
+    d.dq, d.lddq, d.dq_col0 = ptr(dqkv), dqkv.stride(0), 0
+    d.dkv, d.lddkv, d.dk_col0, d.dv_col0 = ptr(dqkv), dqkv.stride(0), D, 2 * D
     d.rope, d.rope_period = ptr(rope), rope_period
+    check(load().sam3b_attention_bwd(C.byref(d), current_stream()))
+
+
+def mha_desc(q, kv, nseg, Lq, Lk, heads, scale, O, lse2, *, q_col0=0, k_col0=0, v_col0=None, bias=None, kpm=None,
+             drop_p=0.0, drop_seed=0):
+    """General descriptor (cross attention, padded 32-wide heads, attn_mask / key_padding_mask / dropout)."""
+    from ._abi import AttnDesc  # noqa: PLC0415
+
+    d = AttnDesc()
+    d.q, d.ldq, d.q_cols, d.q_col0 = ptr(q), q.stride(0), q.shape[1], q_col0
+    d.kv, d.ldkv, d.kv_cols, d.k_col0 = ptr(kv), kv.stride(0), kv.shape[1], k_col0
+    d.v_col0 = heads * 64 if v_col0 is None else v_col0
+    d.nseg, d.Lq, d.Lk, d.heads = nseg, Lq, Lk, heads
+    d.dtype = torch_dtype_code(q.dtype)
+    d.scale = scale
+    d.O, d.ldo, d.o_col0 = ptr(O), O.stride(0), 0
+    d.lse2 = ptr(lse2)
+    d.bias, d.kpm, d.drop_p, d.drop_seed = ptr(bias), ptr(kpm), drop_p, drop_seed
+    return d
+
+
+def mha_fwd(d):
+    check(load().sam3b_attention_fwd(C.byref(d), current_stream()))
+
+
+def mha_bwd(d, dO, delta, dq, dkv, *, dk_col0=0, dv_col0=None):
+    d.dO, d.lddo, d.do_col0 = ptr(dO), dO.stride(0), 0
+    d.delta = ptr(delta)
+    d.dq, d.lddq, d.dq_col0 = ptr(dq), dq.stride(0), 0
+    d.dkv, d.lddkv, d.dk_col0 = ptr(dkv), dkv.stride(0), dk_col0
+    d.dv_col0 = d.heads * 64 if dv_col0 is None else dv_col0
     check(load().sam3b_attention_bwd(C.byref(d), current_stream()))
 
 

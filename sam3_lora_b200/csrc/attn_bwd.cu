@@ -22,6 +22,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace sam3b {
 
@@ -36,14 +37,24 @@ constexpr int A_BYTES = BT * BI * 2;   // 16 KB: [128][64] 16-bit A operand writ
 constexpr int TCOLS = 256;
 
 struct BwdParams {
-  int L, tiles, D, H;
+  int Lq, Lk, tiles, H;
+  int q_col0, k_col0, v_col0, do_col0;
   const float* lse2;
   const float* delta;
-  void* dqkv; int64_t lddqkv;
-  const float2* rope; int rope_period;
+  int Lq_stat; int64_t stat_stride;    // statistics layout [H][nseg * Lq_stat]
+  void* dq; int64_t lddq; int dq_col0;
+  void* dkv; int64_t lddkv; int dk_col0, dv_col0;
+  const float2* rope; int rope_period;  // null: no inverse rotation (MultiheadAttention sites)
   float scale_log2, scale;
-  int total_rows;
+  // GEN only
+  const float* bias; const uint8_t* kpm;
+  float drop_inv_keep; uint32_t drop_thr, drop_seed;
 };
+
+__device__ __forceinline__ uint32_t attn_drop_base(uint32_t seed, uint32_t bh) { return lowbias32(seed ^ (bh * 0x9E3779B1u + 0x85EBCA6Bu)); }
+__device__ __forceinline__ bool attn_drop_keep(uint32_t base, uint32_t q, uint32_t k, uint32_t Lk, uint32_t thr) {
+  return lowbias32(base ^ (q * Lk + k)) >= thr;
+}
 
 template <int DT>
 __device__ __forceinline__ void store_row_chunk16(uint8_t* row_base, int sw, int ch0, const float (&v)[32]) {
@@ -60,8 +71,8 @@ __device__ __forceinline__ void store_row_chunk16(uint8_t* row_base, int sw, int
 
 // out[row][col0 + cc .. col0 + cc + 32) = (optionally inverse-rotated) acc * mul, 16-bit
 template <int DT, bool ROPE>
-__device__ __forceinline__ void store_grad_chunk(const BwdParams& p, uint32_t taddr, int row, int col0, int cc, float mul,
-                                                 bool valid) {
+__device__ __forceinline__ void store_grad_chunk(const BwdParams& p, void* out, int64_t ld, uint32_t taddr, int row, int rope_row,
+                                                 int col0, int cc, float mul, bool valid) {
   uint32_t t[32];
   tmem_ld_x32(taddr + cc, t);
   tmem_ld_wait();
@@ -70,18 +81,20 @@ __device__ __forceinline__ void store_grad_chunk(const BwdParams& p, uint32_t ta
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]) * mul;
   if constexpr (ROPE) {
-    const float4* t4 = reinterpret_cast<const float4*>(p.rope + (int64_t)(row % p.rope_period) * 32 + (cc >> 1));
+    if (p.rope != nullptr) {
+      const float4* t4 = reinterpret_cast<const float4*>(p.rope + (int64_t)(rope_row % p.rope_period) * 32 + (cc >> 1));
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 cs = __ldg(t4 + q);
-      float a0 = v[q * 4], b0 = v[q * 4 + 1], a1 = v[q * 4 + 2], b1 = v[q * 4 + 3];
-      v[q * 4] = a0 * cs.x + b0 * cs.y;
-      v[q * 4 + 1] = -a0 * cs.y + b0 * cs.x;
-      v[q * 4 + 2] = a1 * cs.z + b1 * cs.w;
-      v[q * 4 + 3] = -a1 * cs.w + b1 * cs.z;
+      for (int q = 0; q < 8; ++q) {
+        float4 cs = __ldg(t4 + q);
+        float a0 = v[q * 4], b0 = v[q * 4 + 1], a1 = v[q * 4 + 2], b1 = v[q * 4 + 3];
+        v[q * 4] = a0 * cs.x + b0 * cs.y;
+        v[q * 4 + 1] = -a0 * cs.y + b0 * cs.x;
+        v[q * 4 + 2] = a1 * cs.z + b1 * cs.w;
+        v[q * 4 + 3] = -a1 * cs.w + b1 * cs.z;
+      }
     }
   }
-  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dqkv) + (int64_t)row * p.lddqkv + col0 + cc);
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + (int64_t)row * ld + col0 + cc);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint4 u;
@@ -98,11 +111,11 @@ __device__ __forceinline__ void store_grad_chunk(const BwdParams& p, uint32_t ta
 // =========================================================================================
 constexpr int DKDV_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + 2 * A_BYTES + 2 * 2 * BI * 4 + 128;  // stats: [2 stages][lse2 | delta][64]
 
-template <int DT>
+template <int DT, bool GEN>
 __global__ void __launch_bounds__(320, 2)
-attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][64]
-                     const __grid_constant__ CUtensorMap tmI,   // qkv, box [64][64]
-                     const __grid_constant__ CUtensorMap tmdO,  // dO,  box [64][64]
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, box [128][64]
+                     const __grid_constant__ CUtensorMap tmI,   // q buffer,  box [64][64]
+                     const __grid_constant__ CUtensorMap tmdO,  // dO,        box [64][64]
                      const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -127,9 +140,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
   const int tile = blockIdx.x % p.tiles;
   const int seg = blockIdx.x / p.tiles;
   const int head = blockIdx.y;
-  const int seg_row0 = seg * p.L;
-  const int t_row0 = seg_row0 + tile * BT;
-  const int n_blocks = p.L / BI;
+  const int q_row0_seg = seg * p.Lq;
+  const int t_row0 = seg * p.Lk + tile * BT;   // this CTA's 128 keys
+  const int n_blocks = (p.Lq + BI - 1) / BI;     // 64-query blocks
 
   if (warp == 8 && elect_one()) {
     tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
@@ -148,16 +161,16 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
   if (warp == 8) {
     if (elect_one()) {
       mbar_arrive_expect_tx(kv_full, 2 * T_BYTES);
-      tma_load_2d(sK, &tmT, kv_full, p.D + head * HD, t_row0);
-      tma_load_2d(sV, &tmT, kv_full, 2 * p.D + head * HD, t_row0);
+      tma_load_2d(sK, &tmT, kv_full, p.k_col0 + head * HD, t_row0);
+      tma_load_2d(sV, &tmT, kv_full, p.v_col0 + head * HD, t_row0);
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j & 1;
         if (j >= 2) mbar_wait(&in_free[st], ((j >> 1) - 1) & 1, 10 + st);
         mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES + 2 * BI * 4);
-        tma_load_2d(sQ + st * I_BYTES, &tmI, &in_full[st], head * HD, seg_row0 + j * BI);
-        tma_load_2d(sdO + st * I_BYTES, &tmdO, &in_full[st], head * HD, seg_row0 + j * BI);
+        tma_load_2d(sQ + st * I_BYTES, &tmI, &in_full[st], p.q_col0 + head * HD, q_row0_seg + j * BI);
+        tma_load_2d(sdO + st * I_BYTES, &tmdO, &in_full[st], p.do_col0 + head * HD, q_row0_seg + j * BI);
         // per-query statistics of this block (head-major layout: 64 consecutive floats each)
-        const int64_t soff = (int64_t)head * p.total_rows + seg_row0 + j * BI;
+        const int64_t soff = (int64_t)head * p.stat_stride + (int64_t)seg * p.Lq_stat + j * BI;
         bulk_load_1d(sStat + st * (2 * BI), p.lse2 + soff, BI * 4, &in_full[st]);
         bulk_load_1d(sStat + st * (2 * BI) + BI, p.delta + soff, BI * 4, &in_full[st]);
       }
@@ -211,9 +224,19 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
     uint8_t* p_row = sP + r * 128;
     uint8_t* ds_row = sdS + r * 128;
     const int sw = r & 7;
+    const int k_in_seg = min(tile * BT + r, p.Lk - 1);
+    bool key_masked = false;
+    const float* bias_col = nullptr;
+    uint32_t drop_base = 0;
+    if constexpr (GEN) {
+      if (p.kpm != nullptr) key_masked = __ldg(p.kpm + (int64_t)seg * p.Lk + k_in_seg) != 0;
+      if (p.bias != nullptr) bias_col = p.bias + (int64_t)(seg * p.H + head) * p.Lq * p.Lk + k_in_seg;
+      drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
+    }
     for (int j = 0; j < n_blocks; ++j) {
       // per-query statistics were bulk-copied next to Q/dO by the producer (visible once in_full completed)
       const float* stat = sStat + (j & 1) * (2 * BI);
+      const int q_valid = min(BI, p.Lq - j * BI);   // queries of this block that exist
       mbar_wait(&in_full[j & 1], (j >> 1) & 1, 33);
       mbar_wait(sdp_full, j & 1, 30);
       tc_fence_after();
@@ -225,11 +248,31 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
         tc_fence_before();
         mbar_arrive(sdp_free);  // TMEM S^T/dP^T may be overwritten by block j+1
         float pv[32], dsv[32];
+        if (!GEN && q_valid == BI) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pe = ex2_approx(__uint_as_float(s[i]) * c - stat[cc + i]);
-          pv[i] = pe;
-          dsv[i] = pe * (__uint_as_float(d[i]) - stat[BI + cc + i]);
+          for (int i = 0; i < 32; ++i) {
+            const float pe = ex2_approx(__uint_as_float(s[i]) * c - stat[cc + i]);
+            pv[i] = pe;
+            dsv[i] = pe * (__uint_as_float(d[i]) - stat[BI + cc + i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int qi = j * BI + cc + i;   // query index inside the segment
+            float t = __uint_as_float(s[i]) * c;
+            float dp = __uint_as_float(d[i]);
+            bool dead = (cc + i) >= q_valid;
+            float keep_scale = 1.f;
+            if constexpr (GEN) {
+              if (bias_col != nullptr && !dead) t = fmaf(__ldg(bias_col + (int64_t)qi * p.Lk), 1.4426950408889634f, t);
+              dead = dead || key_masked;
+              if (p.drop_thr != 0)
+                keep_scale = attn_drop_keep(drop_base, (uint32_t)qi, (uint32_t)k_in_seg, (uint32_t)p.Lk, p.drop_thr) ? p.drop_inv_keep : 0.f;
+            }
+            const float pe = dead ? 0.f : ex2_approx(t - stat[cc + i]);
+            pv[i] = pe * keep_scale;                                   // dropped probabilities feed dV
+            dsv[i] = dead ? 0.f : pe * (dp * keep_scale - stat[BI + cc + i]);
+          }
         }
         if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);  // previous dV/dK MMAs finished reading sP/sdS
         store_row_chunk16<DT>(p_row, sw, cc >> 3, pv);
@@ -242,9 +285,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
     mbar_wait(acc_done, (n_blocks - 1) & 1, 32);
     tc_fence_after();
     const int row = t_row0 + r;
-    const bool valid = (tile * BT + r) < p.L && row < p.total_rows;
-    store_grad_chunk<DT, false>(p, tm_dV + lane_off, row, 2 * p.D + head * HD, cc, 1.f, valid);
-    store_grad_chunk<DT, true>(p, tm_dK + lane_off, row, p.D + head * HD, cc, p.scale, valid);
+    const bool valid = (tile * BT + r) < p.Lk;
+    store_grad_chunk<DT, false>(p, p.dkv, p.lddkv, tm_dV + lane_off, row, row, p.dv_col0 + head * HD, cc, 1.f, valid);
+    store_grad_chunk<DT, true>(p, p.dkv, p.lddkv, tm_dK + lane_off, row, row, p.dk_col0 + head * HD, cc, p.scale, valid);
   }
   tc_fence_before();
   __syncthreads();
@@ -256,11 +299,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128
 // =========================================================================================
 constexpr int DQ_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + A_BYTES + 128;
 
-template <int DT>
+template <int DT, bool GEN>
 __global__ void __launch_bounds__(320, 2)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][64]
-                   const __grid_constant__ CUtensorMap tmI,   // qkv, box [64][64]
-                   const __grid_constant__ CUtensorMap tmdO,  // dO,  box [128][64]
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // q buffer,  box [128][64]
+                   const __grid_constant__ CUtensorMap tmI,   // kv buffer, box [64][64]
+                   const __grid_constant__ CUtensorMap tmdO,  // dO,        box [128][64]
                    const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -283,9 +326,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
   const int tile = blockIdx.x % p.tiles;
   const int seg = blockIdx.x / p.tiles;
   const int head = blockIdx.y;
-  const int seg_row0 = seg * p.L;
-  const int t_row0 = seg_row0 + tile * BT;
-  const int n_blocks = p.L / BI;
+  const int kv_row0_seg = seg * p.Lk;
+  const int t_row0 = seg * p.Lq + tile * BT;   // this CTA's 128 queries
+  const int n_blocks = (p.Lk + BI - 1) / BI;     // 64-key blocks
 
   if (warp == 8 && elect_one()) {
     tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
@@ -304,14 +347,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
   if (warp == 8) {
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * T_BYTES);
-      tma_load_2d(sQ, &tmT, q_full, head * HD, t_row0);
-      tma_load_2d(sdO, &tmdO, q_full, head * HD, t_row0);
+      tma_load_2d(sQ, &tmT, q_full, p.q_col0 + head * HD, t_row0);
+      tma_load_2d(sdO, &tmdO, q_full, p.do_col0 + head * HD, t_row0);
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j & 1;
         if (j >= 2) mbar_wait(&in_free[st], ((j >> 1) - 1) & 1, 10 + st);
         mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES);
-        tma_load_2d(sK + st * I_BYTES, &tmI, &in_full[st], p.D + head * HD, seg_row0 + j * BI);
-        tma_load_2d(sV + st * I_BYTES, &tmI, &in_full[st], 2 * p.D + head * HD, seg_row0 + j * BI);
+        tma_load_2d(sK + st * I_BYTES, &tmI, &in_full[st], p.k_col0 + head * HD, kv_row0_seg + j * BI);
+        tma_load_2d(sV + st * I_BYTES, &tmI, &in_full[st], p.v_col0 + head * HD, kv_row0_seg + j * BI);
       }
     }
   } else if (warp == 9) {
@@ -355,12 +398,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c = p.scale_log2;
     const int row = t_row0 + r;
-    const int row_c = min(row, p.total_rows - 1);
-    const float lse = __ldg(p.lse2 + (int64_t)head * p.total_rows + row_c);   // head-major statistics
-    const float dlt = __ldg(p.delta + (int64_t)head * p.total_rows + row_c);
+    const int q_in_seg = min(tile * BT + r, p.Lq - 1);
+    const int64_t sidx = (int64_t)head * p.stat_stride + (int64_t)seg * p.Lq_stat + q_in_seg;   // head-major statistics
+    const float lse = __ldg(p.lse2 + sidx);
+    const float dlt = __ldg(p.delta + sidx);
     uint8_t* ds_row = sdS + r * 128;
     const int sw = r & 7;
+    const float* bias_row = nullptr;
+    const uint8_t* kpm_row = nullptr;
+    uint32_t drop_base = 0;
+    if constexpr (GEN) {
+      if (p.bias != nullptr) bias_row = p.bias + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * p.Lk;
+      if (p.kpm != nullptr) kpm_row = p.kpm + (int64_t)seg * p.Lk;
+      drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
+    }
     for (int j = 0; j < n_blocks; ++j) {
+      const int k_valid = min(BI, p.Lk - j * BI);
       mbar_wait(sdp_full, j & 1, 30);
       tc_fence_after();
       {
@@ -371,10 +424,28 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
         tc_fence_before();
         mbar_arrive(sdp_free);
         float dsv[32];
+        if (!GEN && k_valid == BI) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pe = ex2_approx(__uint_as_float(s[i]) * c - lse);
-          dsv[i] = pe * (__uint_as_float(d[i]) - dlt);
+          for (int i = 0; i < 32; ++i) {
+            const float pe = ex2_approx(__uint_as_float(s[i]) * c - lse);
+            dsv[i] = pe * (__uint_as_float(d[i]) - dlt);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int ki = j * BI + cc + i;   // key index inside the segment
+            float t = __uint_as_float(s[i]) * c;
+            float dp = __uint_as_float(d[i]);
+            bool dead = (cc + i) >= k_valid;
+            if constexpr (GEN) {
+              if (bias_row != nullptr && !dead) t = fmaf(__ldg(bias_row + ki), 1.4426950408889634f, t);
+              if (kpm_row != nullptr && !dead) dead = __ldg(kpm_row + ki) != 0;
+              if (p.drop_thr != 0)
+                dp *= attn_drop_keep(drop_base, (uint32_t)q_in_seg, (uint32_t)ki, (uint32_t)p.Lk, p.drop_thr) ? p.drop_inv_keep : 0.f;
+            }
+            const float pe = dead ? 0.f : ex2_approx(t - lse);
+            dsv[i] = pe * (dp - dlt);
+          }
         }
         if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);
         store_row_chunk16<DT>(ds_row, sw, cc >> 3, dsv);
@@ -385,8 +456,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // qkv, box [128][
     }
     mbar_wait(acc_done, (n_blocks - 1) & 1, 32);
     tc_fence_after();
-    const bool valid = (tile * BT + r) < p.L && row < p.total_rows;
-    store_grad_chunk<DT, true>(p, tm_dQ + lane_off, row, head * HD, cc, p.scale, valid);
+    const bool valid = (tile * BT + r) < p.Lq;
+    store_grad_chunk<DT, true>(p, p.dq, p.lddq, tm_dQ + lane_off, row, row, p.dq_col0 + head * HD, cc, p.scale, valid);
   }
   tc_fence_before();
   __syncthreads();
@@ -402,46 +473,59 @@ static int set_smem_once(K kern, int bytes, bool& done) {
   return 0;
 }
 
-template <int DT>
-static int launch_bwd(const AttnBwdArgs& a, const BwdParams& p, const CUtensorMap& tmT, const CUtensorMap& tmI,
-                      const CUtensorMap& tmdO64, const CUtensorMap& tmdO128, cudaStream_t stream) {
+template <int DT, bool GEN>
+static int launch_bwd(const AttnArgs& a, const BwdParams& pk, const BwdParams& pq, const CUtensorMap& tmKV128, const CUtensorMap& tmQ64,
+                      const CUtensorMap& tmdO64, const CUtensorMap& tmQ128, const CUtensorMap& tmKV64, const CUtensorMap& tmdO128,
+                      cudaStream_t stream) {
   static bool s1 = false, s2 = false;
-  int rc = set_smem_once(attn_bwd_dkdv_kernel<DT>, DKDV_SMEM, s1);
+  int rc = set_smem_once(attn_bwd_dkdv_kernel<DT, GEN>, DKDV_SMEM, s1);
   if (rc) return rc;
-  rc = set_smem_once(attn_bwd_dq_kernel<DT>, DQ_SMEM, s2);
+  rc = set_smem_once(attn_bwd_dq_kernel<DT, GEN>, DQ_SMEM, s2);
   if (rc) return rc;
-  const int nseg = a.tokens / a.seg_len;
-  dim3 grid(p.tiles * nseg, a.heads);
-  attn_bwd_dkdv_kernel<DT><<<grid, 320, DKDV_SMEM, stream>>>(tmT, tmI, tmdO64, p);
+  attn_bwd_dkdv_kernel<DT, GEN><<<dim3(pk.tiles * a.nseg, a.heads), 320, DKDV_SMEM, stream>>>(tmKV128, tmQ64, tmdO64, pk);
   SAM3B_LAUNCHED();
-  attn_bwd_dq_kernel<DT><<<grid, 320, DQ_SMEM, stream>>>(tmT, tmI, tmdO128, p);
+  attn_bwd_dq_kernel<DT, GEN><<<dim3(pq.tiles * a.nseg, a.heads), 320, DQ_SMEM, stream>>>(tmQ128, tmKV64, tmdO128, pq);
   SAM3B_LAUNCHED();
   return 0;
 }
 
 }  // namespace
 
-int attn_bwd_launch(const AttnBwdArgs& a, cudaStream_t stream) {
-  SAM3B_REQUIRE(a.head_dim == 64, "attention bwd: head_dim %d not supported (64 only)", a.head_dim);
-  SAM3B_REQUIRE(a.tokens % a.seg_len == 0, "attention bwd: tokens %% seg_len != 0");
-  SAM3B_REQUIRE(a.seg_len % BI == 0, "attention bwd: seg_len %d must be a multiple of 64", a.seg_len);
-  SAM3B_REQUIRE(a.heads * 64 == a.D, "attention bwd: heads*64 != D");
-  SAM3B_REQUIRE(a.lddqkv % 8 == 0 && a.ldqkv % 8 == 0 && a.lddo % 8 == 0, "attention bwd: leading dimensions must be multiples of 8");
-  SAM3B_REQUIRE(a.rope != nullptr, "attention bwd: rope table required");
-  CUtensorMap tmT, tmI, tmdO64, tmdO128;
+int attn_bwd_launch(const AttnArgs& a, cudaStream_t stream) {
+  SAM3B_REQUIRE(a.q && a.kv && a.dO && a.lse2 && a.delta && a.dq && a.dkv, "attention bwd: null tensor");
+  SAM3B_REQUIRE(a.nseg > 0 && a.Lq > 0 && a.Lk > 0 && a.heads > 0, "attention bwd: empty problem");
+  SAM3B_REQUIRE(a.ldq % 8 == 0 && a.ldkv % 8 == 0 && a.lddo % 8 == 0 && a.lddq % 8 == 0 && a.lddkv % 8 == 0,
+                "attention bwd: leading dimensions must be multiples of 8");
+  SAM3B_REQUIRE(a.drop_p >= 0.f && a.drop_p < 1.f, "attention bwd: dropout p");
+  const uint64_t Mq = (uint64_t)a.nseg * a.Lq, Mk = (uint64_t)a.nseg * a.Lk;
+  CUtensorMap tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128;
   int rc;
-  if ((rc = make_tmap_2d(&tmT, a.qkv, a.tokens, 3 * a.D, a.ldqkv, BT, HD))) return rc;
-  if ((rc = make_tmap_2d(&tmI, a.qkv, a.tokens, 3 * a.D, a.ldqkv, BI, HD))) return rc;
-  if ((rc = make_tmap_2d(&tmdO64, a.dO, a.tokens, a.D, a.lddo, BI, HD))) return rc;
-  if ((rc = make_tmap_2d(&tmdO128, a.dO, a.tokens, a.D, a.lddo, BT, HD))) return rc;
+  if ((rc = make_tmap_2d(&tmKV128, a.kv, Mk, a.kv_cols, a.ldkv, BT, HD))) return rc;
+  if ((rc = make_tmap_2d(&tmKV64, a.kv, Mk, a.kv_cols, a.ldkv, BI, HD))) return rc;
+  if ((rc = make_tmap_2d(&tmQ128, a.q, Mq, a.q_cols, a.ldq, BT, HD))) return rc;
+  if ((rc = make_tmap_2d(&tmQ64, a.q, Mq, a.q_cols, a.ldq, BI, HD))) return rc;
+  const int do_cols = a.do_col0 + a.heads * HD;
+  if ((rc = make_tmap_2d(&tmdO64, a.dO, Mq, do_cols, a.lddo, BI, HD))) return rc;
+  if ((rc = make_tmap_2d(&tmdO128, a.dO, Mq, do_cols, a.lddo, BT, HD))) return rc;
   BwdParams p{};
-  p.L = a.seg_len; p.tiles = (a.seg_len + BT - 1) / BT; p.D = a.D; p.H = a.heads;
-  p.lse2 = a.lse2; p.delta = a.delta; p.dqkv = a.dqkv; p.lddqkv = a.lddqkv;
+  p.Lq = a.Lq; p.Lk = a.Lk; p.H = a.heads;
+  p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0; p.do_col0 = a.do_col0;
+  p.lse2 = a.lse2; p.delta = a.delta; p.Lq_stat = attn_lq_stat(a.Lq); p.stat_stride = (int64_t)a.nseg * p.Lq_stat;
+  p.dq = a.dq; p.lddq = a.lddq; p.dq_col0 = a.dq_col0;
+  p.dkv = a.dkv; p.lddkv = a.lddkv; p.dk_col0 = a.dk_col0; p.dv_col0 = a.dv_col0;
   p.rope = reinterpret_cast<const float2*>(a.rope); p.rope_period = a.rope_period > 0 ? a.rope_period : 1;
-  p.scale = 0.125f; p.scale_log2 = 0.125f * 1.4426950408889634f;
-  p.total_rows = a.tokens;
-  return a.dtype == 0 ? launch_bwd<0>(a, p, tmT, tmI, tmdO64, tmdO128, stream)
-                      : launch_bwd<1>(a, p, tmT, tmI, tmdO64, tmdO128, stream);
+  p.scale = a.scale; p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.bias = a.bias; p.kpm = a.kpm;
+  p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_thr = a.drop_p > 0.f ? dropout_threshold(a.drop_p) : 0u; p.drop_seed = a.drop_seed;
+  BwdParams pk = p, pq = p;
+  pk.tiles = (a.Lk + BT - 1) / BT;
+  pq.tiles = (a.Lq + BT - 1) / BT;
+  const bool gen = a.bias != nullptr || a.kpm != nullptr || a.drop_p > 0.f;
+  if (gen)
+    return a.dtype == 0 ? launch_bwd<0, true>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream)
+                        : launch_bwd<1, true>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream);
+  return a.dtype == 0 ? launch_bwd<0, false>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream)
+                      : launch_bwd<1, false>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream);
 }
 
 }  // namespace sam3b

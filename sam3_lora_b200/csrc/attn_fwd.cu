@@ -23,6 +23,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace sam3b {
 
@@ -41,17 +42,28 @@ constexpr int TCOLS = 256;  // S0: [0,64)  S1: [64,128)  O: [128,192)
 constexpr float RESCALE_LOG2 = 8.f;  // p <= 2^8 between rescales: safe in fp16/bf16 and fp32 sums
 
 struct FwdParams {
-  int L;          // tokens per segment
-  int q_tiles;    // ceil(L / 128)
-  int D;          // model width (q/k/v column blocks are D apart)
+  int Lq, Lk;     // rows per segment (queries / keys)
+  int q_tiles;    // ceil(Lq / 128)
+  int q_col0, k_col0, v_col0, o_col0;
   void* O; int64_t ldo;
-  float* lse2;    // [H][tokens]
+  float* lse2;    // [H][nseg * Lq_stat]
+  int Lq_stat;    // Lq rounded up to 64
+  int64_t stat_stride;  // nseg * Lq_stat
   int H;
-  float scale_log2;  // head_dim^-0.5 * log2(e)
-  int total_rows;
+  float scale_log2;  // scale * log2(e)
+  // GEN only
+  const float* bias;     // [nseg*H][Lq][Lk] or null
+  const uint8_t* kpm;    // [nseg][Lk] or null
+  float drop_inv_keep; uint32_t drop_thr, drop_seed;
 };
 
-template <int DT>
+// dropout mask on the attention probabilities: stateless hash of (seed, segment*H + head, query, key)
+__device__ __forceinline__ uint32_t attn_drop_base(uint32_t seed, uint32_t bh) { return lowbias32(seed ^ (bh * 0x9E3779B1u + 0x85EBCA6Bu)); }
+__device__ __forceinline__ bool attn_drop_keep(uint32_t base, uint32_t q, uint32_t k, uint32_t Lk, uint32_t thr) {
+  return lowbias32(base ^ (q * Lk + k)) >= thr;
+}
+
+template <int DT, bool GEN>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -75,9 +87,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int q_tile = blockIdx.x % p.q_tiles;
   const int seg = blockIdx.x / p.q_tiles;
   const int head = blockIdx.y;
-  const int seg_row0 = seg * p.L;
-  const int q_row0 = seg_row0 + q_tile * BQ;
-  const int n_blocks = (p.L + BKV - 1) / BKV;
+  const int kv_row0_seg = seg * p.Lk;
+  const int q_row0 = seg * p.Lq + q_tile * BQ;
+  const int n_blocks = (p.Lk + BKV - 1) / BKV;
 
   if (warp == 4 && elect_one()) {
     tma_prefetch_desc(&tmQ);
@@ -103,16 +115,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, head * HD, q_row0);
+      tma_load_2d(sQ, &tmQ, q_full, p.q_col0 + head * HD, q_row0);
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j & 1;
-        const int kv_row0 = seg_row0 + j * BKV;
+        const int kv_row0 = kv_row0_seg + j * BKV;
         if (j >= 2) mbar_wait(&k_free[st], ((j - 2) >> 1) & 1, 10);
         mbar_arrive_expect_tx(&k_full[st], KV_BYTES);
-        tma_load_2d(sK + st * KV_BYTES, &tmKV, &k_full[st], p.D + head * HD, kv_row0);
+        tma_load_2d(sK + st * KV_BYTES, &tmKV, &k_full[st], p.k_col0 + head * HD, kv_row0);
         if (j >= 2) mbar_wait(&v_free[st], ((j - 2) >> 1) & 1, 11);
         mbar_arrive_expect_tx(&v_full[st], KV_BYTES);
-        tma_load_2d(sV + st * KV_BYTES, &tmKV, &v_full[st], 2 * p.D + head * HD, kv_row0);
+        tma_load_2d(sV + st * KV_BYTES, &tmKV, &v_full[st], p.v_col0 + head * HD, kv_row0);
       }
     }
   } else if (warp == 5) {
@@ -156,13 +168,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = threadIdx.x;  // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     const float c = p.scale_log2;
-    const float tau = RESCALE_LOG2 / c;  // in raw-score units
+    const float tau = GEN ? RESCALE_LOG2 : RESCALE_LOG2 / c;  // in the units of the running max
     float m_used = -INFINITY, l_run = 0.f;
     const int sw = r & 7;
+    // GEN: scores are first moved to the log2 domain (t = s*c + bias*log2e, -inf where the key is padded) and the
+    // running max lives in that domain (c_eff = 1); the ViT instantiation keeps raw scores and folds c into the exp.
+    const int q_in_seg = min(q_tile * BQ + r, p.Lq - 1);
+    const float* bias_row = nullptr;
+    uint32_t drop_base = 0;
+    if constexpr (GEN) {
+      if (p.bias != nullptr) bias_row = p.bias + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * p.Lk;
+      drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
+    }
+    const float c_eff = GEN ? 1.f : c;
 
     for (int j = 0; j < n_blocks; ++j) {
       const int st = j & 1;
-      const int kv_valid = min(BKV, p.L - j * BKV);
+      const int kv_valid = min(BKV, p.Lk - j * BKV);
       mbar_wait(&s_full[st], (j >> 1) & 1, 30);
       tc_fence_after();
       uint32_t s[BKV];
@@ -174,8 +196,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 32; ++i) { s[i] = a[i]; s[32 + i] = b[i]; }
       }
-      // full blocks (every block when L % 64 == 0) take the predicate-free path: the per-element ISETP/FSEL
-      // of the tail mask were 27 % of this kernel's issued instructions (profiles/r01_ncu_summary.md)
+      if constexpr (GEN) {
+        // t = s*c (+ bias*log2e) ; padded keys -> -inf
+#pragma unroll
+        for (int i = 0; i < BKV; ++i) s[i] = __float_as_uint(__uint_as_float(s[i]) * c);
+        if (bias_row != nullptr) {
+          const float* bp = bias_row + j * BKV;
+#pragma unroll
+          for (int i = 0; i < BKV; ++i)
+            if (i < kv_valid) s[i] = __float_as_uint(fmaf(__ldg(bp + i), 1.4426950408889634f, __uint_as_float(s[i])));
+        }
+        if (p.kpm != nullptr) {
+          const uint8_t* kp = p.kpm + (int64_t)seg * p.Lk + j * BKV;
+#pragma unroll
+          for (int i = 0; i < BKV; ++i)
+            if (i < kv_valid && __ldg(kp + i) != 0) s[i] = __float_as_uint(-INFINITY);
+        }
+      }
+      // full blocks (every block when Lk % 64 == 0) take the predicate-free path: the per-element ISETP/FSEL
+      // of the tail mask were 27 % of this kernel's issued instructions (profiles/r01_ncu_attn_fwd.txt)
       const bool full = kv_valid == BKV;
       float m_blk = -INFINITY;
       if (full) {
@@ -191,10 +230,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int i = 0; i < BKV; ++i)
           if (i < kv_valid) m_blk = fmaxf(m_blk, __uint_as_float(s[i]));
       }
-      const bool need = m_blk > m_used + tau;  // always true on the first block (m_used = -inf)
+      // always true on the first block (m_used = -inf) unless every key so far is masked (m_blk = -inf)
+      const bool need = m_blk > m_used + tau;
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? m_blk : m_used;
-        const float alpha = ex2_approx((m_used - m_new) * c);  // 0 on the first block, 1 for rows that keep their max
+        const float alpha = ex2_approx((m_used - m_new) * c_eff);  // 0 on the first block, 1 for rows that keep their max
         if (j > 0) {
           // every earlier P.V has landed in the accumulator (MMAs complete in issue order)
           mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1, 31);
@@ -215,7 +255,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // P buffer `st` was last read by P.V of block j-2
       if (j >= 2) mbar_wait(&pv_done[st], ((j - 2) >> 1) & 1, 32);
-      const float mc = m_used * c;
+      const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_eff;  // all keys masked so far: exp2(-inf - 0) = 0
       uint8_t* p_row = sP + st * P_BYTES + r * 128;
       float l_part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -223,16 +263,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float e[8];
         if (full) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[q * 8 + i]), c, -mc));
+          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[q * 8 + i]), c_eff, -mc));
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float v = ex2_approx(fmaf(__uint_as_float(s[q * 8 + i]), c, -mc));
+            const float v = ex2_approx(fmaf(__uint_as_float(s[q * 8 + i]), c_eff, -mc));
             e[i] = (q * 8 + i < kv_valid) ? v : 0.f;
           }
         }
         uint4 u;
-        u.x = pack2<DT>(e[0], e[1]); u.y = pack2<DT>(e[2], e[3]); u.z = pack2<DT>(e[4], e[5]); u.w = pack2<DT>(e[6], e[7]);
+        if constexpr (GEN) {
+          if (p.drop_thr != 0) {   // dropout on the probabilities fed to P.V; the row sum stays un-dropped
+            float d[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              d[i] = attn_drop_keep(drop_base, (uint32_t)q_in_seg, (uint32_t)(j * BKV + q * 8 + i), (uint32_t)p.Lk, p.drop_thr)
+                         ? e[i] * p.drop_inv_keep : 0.f;
+            u.x = pack2<DT>(d[0], d[1]); u.y = pack2<DT>(d[2], d[3]); u.z = pack2<DT>(d[4], d[5]); u.w = pack2<DT>(d[6], d[7]);
+          } else {
+            u.x = pack2<DT>(e[0], e[1]); u.y = pack2<DT>(e[2], e[3]); u.z = pack2<DT>(e[4], e[5]); u.w = pack2<DT>(e[6], e[7]);
+          }
+        } else {
+          u.x = pack2<DT>(e[0], e[1]); u.y = pack2<DT>(e[2], e[3]); u.z = pack2<DT>(e[4], e[5]); u.w = pack2<DT>(e[6], e[7]);
+        }
         // fp32 row sum of the unrounded probabilities (no 16-bit -> fp32 conversions: the conversion pipe
         // shares its 16 lanes/clk with MUFU and is what bounds this loop)
         l_part[q & 3] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
@@ -245,16 +298,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     mbar_wait(&pv_done[(n_blocks - 1) & 1], ((n_blocks - 1) >> 1) & 1, 33);
     tc_fence_after();
-    const float inv_l = 1.f / l_run;
+    const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;  // a fully masked row yields zeros (torch would give NaN)
     const int row = q_row0 + r;
-    const bool valid = (q_tile * BQ + r) < p.L && row < p.total_rows;
+    const bool valid = (q_tile * BQ + r) < p.Lq;
 #pragma unroll
     for (int cc = 0; cc < HD; cc += 32) {
       uint32_t t[32];
       tmem_ld_x32(tmem_O + lane_off + cc, t);
       tmem_ld_wait();
       if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + (int64_t)row * p.ldo + head * HD + cc);
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + (int64_t)row * p.ldo + p.o_col0 + head * HD + cc);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 u;
@@ -266,7 +319,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-    if (valid) p.lse2[(int64_t)head * p.total_rows + row] = m_used * c + log2f(l_run);  // [heads][tokens]
+    if (valid)   // [heads][nseg * Lq_stat]
+      p.lse2[(int64_t)head * p.stat_stride + (int64_t)seg * p.Lq_stat + q_tile * BQ + r] = m_used * c_eff + log2f(l_run);
   }
 
   tc_fence_before();
@@ -274,40 +328,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 5) tmem_dealloc(tmem_base, TCOLS);
 }
 
-// one instantiation (and one cached smem attribute) per operand format
-template <int DT>
+// one instantiation (and one cached smem attribute) per (operand format, feature set)
+template <int DT, bool GEN>
 static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const FwdParams& p, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SAM3B_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    SAM3B_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr_set = true;
   }
-  attn_fwd_kernel<DT><<<grid, 192, FWD_SMEM, stream>>>(tmQ, tmKV, p);
+  attn_fwd_kernel<DT, GEN><<<grid, 192, FWD_SMEM, stream>>>(tmQ, tmKV, p);
   SAM3B_LAUNCHED();
   return 0;
 }
 
 }  // namespace
 
-int attn_fwd_launch(const AttnFwdArgs& a, cudaStream_t stream) {
-  SAM3B_REQUIRE(a.head_dim == 64, "attention: head_dim %d not supported (64 only)", a.head_dim);
-  SAM3B_REQUIRE(a.tokens % a.seg_len == 0, "attention: tokens %d not a multiple of seg_len %d", a.tokens, a.seg_len);
-  SAM3B_REQUIRE(a.heads * 64 == a.D, "attention: heads*64 != D");
-  SAM3B_REQUIRE(a.ldo % 8 == 0 && a.ldqkv % 8 == 0, "attention: leading dimensions must be multiples of 8");
+int attn_fwd_launch(const AttnArgs& a, cudaStream_t stream) {
+  SAM3B_REQUIRE(a.q && a.kv && a.O && a.lse2, "attention: null tensor");
+  SAM3B_REQUIRE(a.nseg > 0 && a.Lq > 0 && a.Lk > 0 && a.heads > 0, "attention: empty problem");
+  SAM3B_REQUIRE(a.ldo % 8 == 0 && a.ldq % 8 == 0 && a.ldkv % 8 == 0, "attention: leading dimensions must be multiples of 8");
+  SAM3B_REQUIRE(a.q_col0 % 8 == 0 && a.k_col0 % 8 == 0 && a.v_col0 % 8 == 0 && a.o_col0 % 8 == 0, "attention: column offsets must be multiples of 8");
   SAM3B_REQUIRE(a.dtype == 0 || a.dtype == 1, "attention: dtype");
+  SAM3B_REQUIRE(a.drop_p >= 0.f && a.drop_p < 1.f, "attention: dropout p=%f outside [0,1)", a.drop_p);
   CUtensorMap tmQ, tmKV;
-  int rc = make_tmap_2d(&tmQ, a.qkv, a.tokens, 3 * a.D, a.ldqkv, BQ, HD);
+  int rc = make_tmap_2d(&tmQ, a.q, (uint64_t)a.nseg * a.Lq, a.q_cols, a.ldq, BQ, HD);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmKV, a.qkv, a.tokens, 3 * a.D, a.ldqkv, BKV, HD);
+  rc = make_tmap_2d(&tmKV, a.kv, (uint64_t)a.nseg * a.Lk, a.kv_cols, a.ldkv, BKV, HD);
   if (rc) return rc;
   FwdParams p{};
-  p.L = a.seg_len; p.q_tiles = (a.seg_len + BQ - 1) / BQ; p.D = a.D;
+  p.Lq = a.Lq; p.Lk = a.Lk; p.q_tiles = (a.Lq + BQ - 1) / BQ;
+  p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0; p.o_col0 = a.o_col0;
   p.O = a.O; p.ldo = a.ldo; p.lse2 = a.lse2; p.H = a.heads;
-  p.scale_log2 = 0.125f * 1.4426950408889634f;
-  p.total_rows = a.tokens;
-  const int nseg = a.tokens / a.seg_len;
-  dim3 grid(p.q_tiles * nseg, a.heads);
-  return a.dtype == 0 ? launch_fwd<0>(tmQ, tmKV, p, grid, stream) : launch_fwd<1>(tmQ, tmKV, p, grid, stream);
+  p.Lq_stat = attn_lq_stat(a.Lq); p.stat_stride = (int64_t)a.nseg * p.Lq_stat;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.bias = a.bias; p.kpm = a.kpm;
+  p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_thr = a.drop_p > 0.f ? dropout_threshold(a.drop_p) : 0u; p.drop_seed = a.drop_seed;
+  dim3 grid(p.q_tiles * a.nseg, a.heads);
+  const bool gen = a.bias != nullptr || a.kpm != nullptr || a.drop_p > 0.f;
+  if (gen) return a.dtype == 0 ? launch_fwd<0, true>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, true>(tmQ, tmKV, p, grid, stream);
+  return a.dtype == 0 ? launch_fwd<0, false>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, false>(tmQ, tmKV, p, grid, stream);
 }
 
 }  // namespace sam3b

@@ -48,25 +48,33 @@ int sam3b_cast_rows_16(const float* x, int32_t rows, int32_t D, void* y16, int64
   return cast_rows_16(x, rows, D, y16, ldy, dtype, static_cast<cudaStream_t>(stream));
 }
 
+static AttnArgs to_attn_args(const sam3b_attn_desc* d) {
+  AttnArgs a;
+  a.q = d->q; a.ldq = d->ldq; a.q_cols = d->q_cols; a.q_col0 = d->q_col0;
+  a.kv = d->kv; a.ldkv = d->ldkv; a.kv_cols = d->kv_cols; a.k_col0 = d->k_col0; a.v_col0 = d->v_col0;
+  a.nseg = d->nseg; a.Lq = d->Lq; a.Lk = d->Lk; a.heads = d->heads; a.dtype = d->dtype; a.scale = d->scale;
+  a.O = d->O; a.ldo = d->ldo; a.o_col0 = d->o_col0; a.lse2 = d->lse2;
+  a.bias = d->bias; a.kpm = d->kpm; a.drop_p = d->drop_p; a.drop_seed = d->drop_seed;
+  a.dO = d->dO; a.lddo = d->lddo; a.do_col0 = d->do_col0; a.delta = d->delta;
+  a.dq = d->dq; a.lddq = d->lddq; a.dq_col0 = d->dq_col0;
+  a.dkv = d->dkv; a.lddkv = d->lddkv; a.dk_col0 = d->dk_col0; a.dv_col0 = d->dv_col0;
+  a.rope = d->rope; a.rope_period = d->rope_period;
+  return a;
+}
 int sam3b_attention_fwd(const sam3b_attn_desc* d, void* stream) {
   if (!d) return fail(-1, "sam3b_attention_fwd: null descriptor");
-  AttnFwdArgs a;
-  a.qkv = d->qkv; a.ldqkv = d->ldqkv; a.tokens = d->tokens; a.seg_len = d->seg_len; a.D = d->D; a.heads = d->heads;
-  a.head_dim = d->head_dim; a.dtype = d->dtype; a.O = d->O; a.ldo = d->ldo; a.lse2 = d->lse2;
-  if (!a.qkv || !a.O || !a.lse2) return fail(-1, "sam3b_attention_fwd: null tensor");
-  return attn_fwd_launch(a, static_cast<cudaStream_t>(stream));
+  return attn_fwd_launch(to_attn_args(d), static_cast<cudaStream_t>(stream));
 }
 int sam3b_attention_bwd(const sam3b_attn_desc* d, void* stream) {
   if (!d) return fail(-1, "sam3b_attention_bwd: null descriptor");
-  if (!d->qkv || !d->O || !d->lse2 || !d->dO || !d->delta || !d->dqkv) return fail(-1, "sam3b_attention_bwd: null tensor");
+  if (!d->O || !d->dO || !d->delta) return fail(-1, "sam3b_attention_bwd: null tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = attn_delta(d->dO, d->lddo, d->O, d->ldo, d->tokens, d->heads, d->dtype, d->delta, st);
+  // delta = rowsum(dO * O) per (row, head), in the statistics layout of lse2
+  const uint16_t* O16 = static_cast<const uint16_t*>(d->O) + d->o_col0;
+  const uint16_t* dO16 = static_cast<const uint16_t*>(d->dO) + d->do_col0;
+  int rc = attn_delta(dO16, d->lddo, O16, d->ldo, d->nseg * d->Lq, d->heads, d->dtype, d->delta, st, d->Lq);
   if (rc) return rc;
-  AttnBwdArgs a;
-  a.qkv = d->qkv; a.ldqkv = d->ldqkv; a.dO = d->dO; a.lddo = d->lddo; a.lse2 = d->lse2; a.delta = d->delta;
-  a.dqkv = d->dqkv; a.lddqkv = d->lddqkv; a.rope = d->rope; a.rope_period = d->rope_period;
-  a.tokens = d->tokens; a.seg_len = d->seg_len; a.D = d->D; a.heads = d->heads; a.head_dim = d->head_dim; a.dtype = d->dtype;
-  return attn_bwd_launch(a, st);
+  return attn_bwd_launch(to_attn_args(d), st);
 }
 
 int sam3b_patch_gather(const float* img, int32_t B, int32_t C, int32_t Himg, int32_t Wimg, int32_t P, int32_t ws,

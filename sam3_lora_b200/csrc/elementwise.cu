@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict_
 template <int DT>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restrict__ dO, int64_t lddo,
                                                          const uint16_t* __restrict__ O, int64_t ldo, int rows, int heads,
-                                                         float* __restrict__ delta) {
+                                                         float* __restrict__ delta, int Lq, int Lq_stat, int64_t stat_stride) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t pair = gid >> 3;  // (row, head)
   const int sub = (int)(gid & 7);
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restr
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (ok && sub == 0) delta[(int64_t)h * rows + row] = s;  // head-major, like the attention LSE
+  if (ok && sub == 0) delta[(int64_t)h * stat_stride + (int64_t)(row / Lq) * Lq_stat + row % Lq] = s;  // head-major, like the LSE
 }
 
 // patch gather: one block per token row, threads over k (coalesced along v within a patch row)
@@ -501,12 +501,16 @@ int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dt
 }
 
 int attn_delta(const void* dO, int64_t lddo, const void* O, int64_t ldo, int rows, int heads, int dtype, float* delta,
-               cudaStream_t s) {
+               cudaStream_t s, int Lq) {
+  if (Lq <= 0) Lq = rows;
+  SAM3B_REQUIRE(rows % Lq == 0, "attn_delta: rows %d not a multiple of Lq %d", rows, Lq);
+  const int Lq_stat = (Lq + 63) / 64 * 64;
+  const int64_t stat_stride = (int64_t)(rows / Lq) * Lq_stat;
   SAM3B_REQUIRE(lddo % 8 == 0 && ldo % 8 == 0, "attn_delta: ld %% 8 != 0");
   const int64_t threads = (int64_t)rows * heads * 8;
   const int blocks = (int)((threads + 255) / 256);
-  if (dtype == 0) attn_delta_kernel<0><<<blocks, 256, 0, s>>>((const uint16_t*)dO, lddo, (const uint16_t*)O, ldo, rows, heads, delta);
-  else attn_delta_kernel<1><<<blocks, 256, 0, s>>>((const uint16_t*)dO, lddo, (const uint16_t*)O, ldo, rows, heads, delta);
+  if (dtype == 0) attn_delta_kernel<0><<<blocks, 256, 0, s>>>((const uint16_t*)dO, lddo, (const uint16_t*)O, ldo, rows, heads, delta, Lq, Lq_stat, stat_stride);
+  else attn_delta_kernel<1><<<blocks, 256, 0, s>>>((const uint16_t*)dO, lddo, (const uint16_t*)O, ldo, rows, heads, delta, Lq, Lq_stat, stat_stride);
   SAM3B_LAUNCHED();
   return 0;
 }

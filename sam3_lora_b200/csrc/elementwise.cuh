@@ -37,8 +37,9 @@ int dropout_rows16(const void* x16, int64_t ldx, int rows, int cols, void* out16
 int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s);
 
 // delta[h][row] = sum_c dO[row][h*64+c] * O[row][h*64+c]   (head-major)
+// delta[h][seg*Lq_stat + i] for row = seg*Lq + i (Lq_stat = Lq rounded up to 64; pass Lq = rows for one flat segment)
 int attn_delta(const void* dO, int64_t lddo, const void* O, int64_t ldo, int rows, int heads, int dtype, float* delta,
-               cudaStream_t s);
+               cudaStream_t s, int Lq = 0);
 
 // Patch gather for the k=s=P patch-embed conv (vitdet.py:323-336): image fp32 NCHW ->
 // 16-bit rows [token][Kpad] with k = (c*P + u)*P + v, tokens in window-major order:

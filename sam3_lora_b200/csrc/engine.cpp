@@ -410,9 +410,12 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
       if ((rc = gemm_launch(g, s))) return rc;
     }
     {
-      AttnFwdArgs f;
-      f.qkv = a.qkv; f.ldqkv = 3 * D_; f.tokens = M; f.seg_len = w.global ? T_ : ws2; f.D = D_; f.heads = H_;
-      f.dtype = dt; f.O = a.O; f.ldo = ld_O; f.lse2 = a.lse2;
+      const int L = w.global ? T_ : ws2;
+      AttnArgs f;
+      f.q = a.qkv; f.ldq = 3 * D_; f.q_cols = 3 * D_; f.q_col0 = 0;
+      f.kv = a.qkv; f.ldkv = 3 * D_; f.kv_cols = 3 * D_; f.k_col0 = D_; f.v_col0 = 2 * D_;
+      f.nseg = M / L; f.Lq = L; f.Lk = L; f.heads = H_; f.scale = 0.125f; f.dtype = dt;
+      f.O = a.O; f.ldo = ld_O; f.lse2 = a.lse2;
       if ((rc = attn_fwd_launch(f, s))) return rc;
     }
     if ((rc = site_down(w.proj, a.O, ld_O, M, i, 1, s))) return rc;
@@ -526,11 +529,16 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
     if ((rc = site_dgrad(w.proj, dx16_, ld_dx16, EPI_STORE16, dO16_, D_, nullptr, 0, i, 1))) return rc;
     if ((rc = attn_delta(dO16_, D_, a.O, ld_O, M, H_, dt, delta_, s))) return rc;
     {
-      AttnBwdArgs b;
-      b.qkv = a.qkv; b.ldqkv = 3 * D_; b.dO = dO16_; b.lddo = D_; b.lse2 = a.lse2; b.delta = delta_;
-      b.dqkv = dqkv16_; b.lddqkv = ld_dqkv;
-      b.rope = w.global ? rope_glob_ : rope_win_; b.rope_period = w.global ? T_ : ws2;
-      b.tokens = M; b.seg_len = w.global ? T_ : ws2; b.D = D_; b.heads = H_; b.dtype = dt;
+      const int L = w.global ? T_ : ws2;
+      AttnArgs b;
+      b.q = a.qkv; b.ldq = 3 * D_; b.q_cols = 3 * D_; b.q_col0 = 0;
+      b.kv = a.qkv; b.ldkv = 3 * D_; b.kv_cols = 3 * D_; b.k_col0 = D_; b.v_col0 = 2 * D_;
+      b.nseg = M / L; b.Lq = L; b.Lk = L; b.heads = H_; b.scale = 0.125f; b.dtype = dt;
+      b.O = a.O; b.ldo = ld_O; b.lse2 = a.lse2;
+      b.dO = dO16_; b.lddo = D_; b.delta = delta_;
+      b.dq = dqkv16_; b.lddq = ld_dqkv; b.dq_col0 = 0;
+      b.dkv = dqkv16_; b.lddkv = ld_dqkv; b.dk_col0 = D_; b.dv_col0 = 2 * D_;
+      b.rope = w.global ? rope_glob_ : rope_win_; b.rope_period = L;
       if ((rc = attn_bwd_launch(b, s))) return rc;
     }
     if ((rc = site_up_grad(w.qkv, dqkv16_, ld_dqkv))) return rc;

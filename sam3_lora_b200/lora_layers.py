@@ -173,8 +173,15 @@ def apply_lora_to_model(model: nn.Module, config: LoRAConfig) -> nn.Module:
         if not isinstance(module, nn.Linear) or not _component_allows(name, config):
             continue
         base = name.rsplit(".", 1)[-1]
-        if base == "out_proj" or base not in config.target_modules:
+        if base not in config.target_modules:
             continue
+        if base == "out_proj":
+            # torch's nn.MultiheadAttention reads out_proj.weight directly, so the reference never wraps it; our fused
+            # MultiheadAttention (mha.py) declares that it understands a wrapped out_proj.
+            parent_name = name.rsplit(".", 1)[0] if "." in name else ""
+            parent = model.get_submodule(parent_name) if parent_name else model
+            if config.strict_reference_names or not getattr(parent, "lora_out_proj_ok", False):
+                continue
         _set_child(model, name, LoRALinear(module, rank=config.rank, alpha=config.alpha, dropout=config.dropout))
         applied.append(name)
     # (2) virtual targets on fused projections (skipped in strict mode)

@@ -1,0 +1,215 @@
+"""Drop-in for the `nn.MultiheadAttention` sites of the SAM3 detector (row a7 of the hot-path table).
+
+Reference call sites (all through `MultiheadAttentionWrapper`, sam3/model/model_misc.py:31-34, i.e.
+`need_weights=False`):
+    DETR encoder   self_attn / cross_attn_image   sam3/model/encoder.py:139-201   (E=256, 8 heads, dropout 0.1)
+    DETR decoder   self_attn / ca_text / cross_attn with additive box-RPB attn_mask   sam3/model/decoder.py:80-187
+    seg head       cross_attend_prompt            sam3/model/maskformer_segmentation.py:281-289
+
+Same constructor subset, parameter names (`in_proj_weight [3E,E]`, `in_proj_bias`, `out_proj.{weight,bias}`)
+and call signature as torch's module, so checkpoints and call sites are unchanged.  LoRA: the reference's
+q_proj / k_proj / v_proj / out_proj target names address the three row-slices of `in_proj_weight` and `out_proj`
+as virtual children — `out_proj` is a real adapter here, not the inert one of the reference.
+
+Arithmetic: the three projections and the output projection are fused LoRA GEMMs (ops.lora_linear);
+the attention core is the tcgen05 flash kernel of csrc/attn_fwd.cu / attn_bwd.cu in its GEN instantiation
+(additive float attn_mask, boolean key_padding_mask, dropout on the probabilities).  head_dim 32 runs as
+zero-padded 64-wide heads: the frozen weights are expanded once so the GEMMs emit / consume the padded layout.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .lora_layers import LoRALinear, LoRAVirtual
+from .ops import lora_linear, _OPERAND_DTYPE  # noqa: F401
+
+
+def _pad_index(E: int, H: int, device) -> torch.Tensor:
+    """positions of the E real features inside the padded [H*64] layout (head h at 64*h .. 64*h + E/H)."""
+    hd = E // H
+    return (torch.arange(H, device=device).view(H, 1) * 64 + torch.arange(hd, device=device).view(1, hd)).reshape(-1)
+
+
+class _AttnCoreFn(torch.autograd.Function):
+    """softmax(q k^T * scale + attn_mask + key_padding_mask) -> dropout -> @ v on padded 64-wide heads."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, nseg: int, Lq: int, Lk: int, heads: int, scale: float, bias, kpm, drop_p: float, seed: int):
+        from .ops import _OPERAND_DTYPE as dt  # noqa: PLC0415
+
+        Ep = heads * 64
+        dev = q.device
+        q16 = torch.empty(nseg * Lq, Ep, device=dev, dtype=dt)
+        kv16 = torch.empty(nseg * Lk, 2 * Ep, device=dev, dtype=dt)
+        L.cast_rows_16(q.float().contiguous(), q16)
+        L.cast_rows_16(k.float().contiguous(), kv16[:, :Ep])
+        L.cast_rows_16(v.float().contiguous(), kv16[:, Ep:])
+        O16 = torch.empty(nseg * Lq, Ep, device=dev, dtype=dt)
+        Ls = (Lq + 63) // 64 * 64
+        lse2 = torch.zeros(heads, nseg * Ls, device=dev, dtype=torch.float32)
+        d = L.mha_desc(q16, kv16, nseg, Lq, Lk, heads, scale, O16, lse2, bias=bias, kpm=kpm, drop_p=drop_p, drop_seed=seed)
+        L.mha_fwd(d)
+        ctx.save_for_backward(q16, kv16, O16, lse2, bias if bias is not None else torch.empty(0, device=dev),
+                              kpm if kpm is not None else torch.empty(0, device=dev, dtype=torch.uint8))
+        ctx.meta = (nseg, Lq, Lk, heads, scale, bias is not None, kpm is not None, drop_p, seed, q.dtype)
+        return O16.float()
+
+    @staticmethod
+    def backward(ctx, gO):
+        q16, kv16, O16, lse2, bias, kpm = ctx.saved_tensors
+        nseg, Lq, Lk, heads, scale, has_bias, has_kpm, drop_p, seed, qdt = ctx.meta
+        Ep = heads * 64
+        dev = gO.device
+        dO16 = torch.empty(nseg * Lq, Ep, device=dev, dtype=q16.dtype)
+        L.cast_rows_16(gO.float().contiguous(), dO16)
+        delta = torch.zeros_like(lse2)
+        dq16 = torch.empty(nseg * Lq, Ep, device=dev, dtype=q16.dtype)
+        dkv16 = torch.empty(nseg * Lk, 2 * Ep, device=dev, dtype=q16.dtype)
+        d = L.mha_desc(q16, kv16, nseg, Lq, Lk, heads, scale, O16, lse2, bias=bias if has_bias else None,
+                       kpm=kpm if has_kpm else None, drop_p=drop_p, drop_seed=seed)
+        L.mha_bwd(d, dO16, delta, dq16, dkv16)
+        return (dq16.float().to(qdt), dkv16[:, :Ep].float().to(qdt), dkv16[:, Ep:].float().to(qdt),
+                None, None, None, None, None, None, None, None, None)
+
+
+class MultiheadAttention(nn.Module):
+    lora_out_proj_ok = True   # apply_lora_to_model may wrap out_proj in a LoRALinear (see lora_layers.py)
+
+    def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0, bias: bool = True, batch_first: bool = False):
+        super().__init__()
+        if embed_dim % num_heads:
+            raise ValueError("embed_dim must be divisible by num_heads")
+        hd = embed_dim // num_heads
+        if hd not in (32, 64):
+            raise L.Sam3bError(f"head_dim {hd} not supported by the fused kernel (32 or 64)")
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, hd
+        self.dropout = dropout
+        self.batch_first = batch_first
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim)) if bias else None
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)   # NonDynamicallyQuantizableLinear in torch: same params
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        if bias:
+            nn.init.zeros_(self.out_proj.bias)
+        self.dropout_seed_override: Optional[int] = None
+        self._packed = None
+
+    # ---- LoRA -------------------------------------------------------------------------------
+    def lora_virtual_targets(self) -> Dict[str, Tuple[int, int]]:
+        e = self.embed_dim
+        return {"q_proj": (e, e), "k_proj": (e, e), "v_proj": (e, e)}   # out_proj is a real Linear: wrapped, not virtual
+
+    def _adapter(self, name: str):
+        m = getattr(self, name, None)
+        return m.lora if isinstance(m, (LoRAVirtual, LoRALinear)) else None
+
+    @property
+    def _out_linear(self) -> nn.Linear:
+        return self.out_proj.original_layer if isinstance(self.out_proj, LoRALinear) else self.out_proj
+
+    # ---- frozen weights in the padded-head layout (built once per device / weight version) ------
+    def _pack(self):
+        W, b = self.in_proj_weight, self.in_proj_bias
+        ow = self._out_linear.weight
+        key = (W._version, W.data_ptr(), ow._version, ow.data_ptr(), str(W.device))
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[1]
+        E, H = self.embed_dim, self.num_heads
+        Ep = H * 64
+        idx = _pad_index(E, H, W.device)
+        out = {"idx": idx}
+        for i, n in enumerate(("q", "k", "v")):
+            Wp = torch.zeros(Ep, E, device=W.device, dtype=torch.float32)
+            Wp[idx] = W.detach()[i * E:(i + 1) * E].float()
+            bp = torch.zeros(Ep, device=W.device, dtype=torch.float32)
+            if b is not None:
+                bp[idx] = b.detach()[i * E:(i + 1) * E].float()
+            out["W" + n], out["b" + n] = Wp, bp
+        Wo = torch.zeros(E, Ep, device=W.device, dtype=torch.float32)
+        Wo[:, idx] = ow.detach().float()
+        out["Wo"] = Wo
+        self._packed = (key, out)
+        return out
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights: bool = False, attn_mask=None, **_unused):
+        if need_weights:
+            raise L.Sam3bError("need_weights=True is not supported by the fused attention (the reference always passes False)")
+        if not query.is_cuda:
+            raise L.Sam3bError("MultiheadAttention: inputs are on the CPU; the fused path has no CPU fallback")
+        E, H, hd = self.embed_dim, self.num_heads, self.head_dim
+        Ep = H * 64
+        if self.batch_first:
+            B, Lq, _ = query.shape
+            Lk = key.shape[1]
+            q_in, k_in, v_in = query, key, value
+        else:
+            Lq, B, _ = query.shape
+            Lk = key.shape[0]
+            q_in, k_in, v_in = query.transpose(0, 1), key.transpose(0, 1), value.transpose(0, 1)
+        q_in, k_in, v_in = (t.reshape(-1, E) for t in (q_in.contiguous(), k_in.contiguous(), v_in.contiguous()))
+        pk = self._pack()
+        idx = pk["idx"]
+
+        def proj(x, n):
+            lo = self._adapter(n + "_proj")
+            if lo is None:
+                return lora_linear(x, pk["W" + n], pk["b" + n], None, None, 1.0)
+            Bp = lo.lora_B.new_zeros(lo.rank, Ep).index_copy(1, idx, lo.lora_B)   # differentiable scatter into the padded layout
+            p = lo.dropout_p if self.training else 0.0
+            return lora_linear(x, pk["W" + n], pk["b" + n], lo.lora_A, Bp, lo.scaling, dropout_p=p)
+
+        q, k, v = proj(q_in, "q"), proj(k_in, "k"), proj(v_in, "v")
+        bias = None
+        if attn_mask is not None:
+            if attn_mask.dtype == torch.bool:
+                bias = torch.zeros(attn_mask.shape, device=query.device, dtype=torch.float32).masked_fill_(attn_mask, float("-inf"))
+            else:
+                bias = attn_mask.float()
+            if bias.dim() == 2:
+                bias = bias.expand(B * H, Lq, Lk)
+            bias = bias.contiguous()
+        kpm = None
+        if key_padding_mask is not None:
+            kpm = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask.dtype == torch.bool \
+                else (key_padding_mask != 0).to(torch.uint8).contiguous()
+        p_drop = self.dropout if self.training else 0.0
+        seed = self.dropout_seed_override
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p_drop > 0 else 0
+        o = _AttnCoreFn.apply(q, k, v, B, Lq, Lk, H, 1.0 / math.sqrt(hd), bias, kpm, p_drop, seed)
+        lo = self._adapter("out_proj")
+        ob = self._out_linear.bias
+        if lo is None:
+            out = lora_linear(o, pk["Wo"], ob, None, None, 1.0)
+        else:
+            Ap = lo.lora_A.new_zeros(Ep, lo.rank).index_copy(0, idx, lo.lora_A)
+            p = lo.dropout_p if self.training else 0.0
+            out = lora_linear(o, pk["Wo"], ob, Ap, lo.lora_B, lo.scaling, dropout_p=p)
+        out = out.reshape(B, Lq, E)
+        if not self.batch_first:
+            out = out.transpose(0, 1)
+        return out.to(query.dtype), None
+
+
+def replace_torch_mha(model: nn.Module) -> int:
+    """Swap every nn.MultiheadAttention (incl. the reference's MultiheadAttentionWrapper subclass) for the fused
+    module, keeping parameters.  Returns the number of modules replaced."""
+    n = 0
+    for name, m in list(model.named_modules()):
+        if isinstance(m, nn.MultiheadAttention) and m._qkv_same_embed_dim:
+            new = MultiheadAttention(m.embed_dim, m.num_heads, dropout=m.dropout, bias=m.in_proj_bias is not None,
+                                     batch_first=m.batch_first)
+            new.load_state_dict(m.state_dict())
+            new.to(m.in_proj_weight.device)
+            *path, leaf = name.split(".")
+            parent = model
+            for p in path:
+                parent = getattr(parent, p)
+            setattr(parent, leaf, new)
+            n += 1
+    return n

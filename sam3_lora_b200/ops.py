@@ -74,21 +74,26 @@ class _LoRALinearFn(torch.autograd.Function):
         _require_cuda(x, "LoRALinear input")
         _require_cuda(W, "LoRALinear weight")
         dt = _OPERAND_DTYPE
-        in_f, r = A.shape
-        out_f = B.shape[1]
+        has_lora = A is not None
+        out_f, in_f = W.shape
+        r = A.shape[1] if has_lora else 0
         if in_f % 8 or out_f % 8:
             raise L.Sam3bError(f"LoRALinear {in_f}->{out_f}: feature sizes must be multiples of 8 for the TMA path")
-        R = _rpad(r)
+        R = _rpad(r) if has_lora else 0
         lead = x.shape[:-1]
         x2 = x.reshape(-1, in_f)
         M = x2.shape[0]
-        Af, Bf = A.detach().float().contiguous(), B.detach().float().contiguous()
         w_ext, wt_ext = _FrozenPack.get(W, R, dt)
-        site, down_T, up_pack = _pack_adapter(Af, Bf, in_f, out_f, r, R, w_ext, wt_ext, dt)
+        site = down_T = up_pack = None
+        if has_lora:
+            Af, Bf = A.detach().float().contiguous(), B.detach().float().contiguous()
+            site, down_T, up_pack = _pack_adapter(Af, Bf, in_f, out_f, r, R, w_ext, wt_ext, dt)
         x16 = torch.empty(M, in_f + R, device=x.device, dtype=dt)
         xf = x2.float().contiguous()
         L.cast_rows_16(xf, x16)
-        if dropout_p > 0.0:
+        if not has_lora:
+            mask, xd16 = None, x16
+        elif dropout_p > 0.0:
             # adapter branch sees inverted-dropout(x) (lora_layers.py:54); the base branch sees x
             mask = (torch.rand_like(xf) >= dropout_p).to(dt) * (1.0 / (1.0 - dropout_p))
             xd16 = torch.empty(M, in_f + R, device=x.device, dtype=dt)
@@ -100,8 +105,9 @@ class _LoRALinearFn(torch.autograd.Function):
             L.gemm(x16[:, :in_f], down_T, x16[:, in_f:], epilogue=L.EPI_STORE16, alpha=scaling, bn=64)
         y = torch.empty(M, out_f, device=x.device, dtype=torch.float32)
         L.gemm(x16, w_ext, y, epilogue=L.EPI_STORE32, bias=None if bias is None else bias.detach().float().contiguous())
-        ctx.save_for_backward(xd16, mask if mask is not None else torch.empty(0, device=x.device), wt_ext, up_pack)
-        ctx.meta = (in_f, out_f, r, R, scaling, dropout_p, lead, site, x.dtype, A.dtype)
+        ctx.save_for_backward(xd16, mask if mask is not None else torch.empty(0, device=x.device), wt_ext,
+                              up_pack if up_pack is not None else torch.empty(0, device=x.device))
+        ctx.meta = (in_f, out_f, r, R, scaling, dropout_p, lead, site, x.dtype, A.dtype if has_lora else torch.float32)
         return y.reshape(*lead, out_f).to(x.dtype)
 
     @staticmethod
@@ -113,7 +119,8 @@ class _LoRALinearFn(torch.autograd.Function):
         M = g2.shape[0]
         dy16 = torch.empty(M, out_f + R, device=gy.device, dtype=dt)
         L.cast_rows_16(g2, dy16)
-        L.gemm(dy16[:, :out_f], up_pack, dy16[:, out_f:], epilogue=L.EPI_STORE16, alpha=scaling, bn=64)
+        if R > 0:
+            L.gemm(dy16[:, :out_f], up_pack, dy16[:, out_f:], epilogue=L.EPI_STORE16, alpha=scaling, bn=64)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, in_f, device=gy.device, dtype=torch.float32)
@@ -125,6 +132,8 @@ class _LoRALinearFn(torch.autograd.Function):
             else:
                 L.gemm(dy16, wt_ext, dx, epilogue=L.EPI_STORE32)
             dx = dx.reshape(*lead, in_f).to(xdtype)
+        if R == 0:
+            return dx, None, None, None, None, None, None
         dA_pack = torch.zeros(in_f, R, device=gy.device, dtype=torch.float32)
         dB_pack = torch.zeros(R, out_f, device=gy.device, dtype=torch.float32)
         kb = max(1, (M + 63) // 64)
@@ -139,7 +148,7 @@ class _LoRALinearFn(torch.autograd.Function):
 
 
 def lora_linear(x, W, bias, A, B, scaling: float, dropout_p: float = 0.0):
-    """y = x W^T + b + scaling * (dropout(x) A) B, fused (see module docstring)."""
+    """y = x W^T + b + scaling * (dropout(x) A) B, fused (see module docstring).  A = B = None: frozen Linear only."""
     return _LoRALinearFn.apply(x, W, bias, A, B, float(scaling), float(dropout_p))
 
 

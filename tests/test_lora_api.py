@@ -139,3 +139,36 @@ def test_strict_reference_names_reproduces_readme_census():
         trunk2 = ViT()
     LL.apply_lora_to_model(trunk2, LL.LoRAConfig(rank=16, alpha=32, target_modules=["q_proj", "k_proj", "v_proj", "out_proj"]))
     assert LL.count_parameters(trunk2)["trainable_parameters"] == 32 * 4 * 2 * 1024 * 16   # 4.19 M
+
+
+def test_fused_mha_gets_q_k_v_virtual_and_wrapped_out_proj():
+    from sam3_lora_b200.mha import MultiheadAttention, replace_torch_mha
+
+    root = nn.Module()
+    root.transformer = nn.Module()
+    root.transformer.encoder = nn.Module()
+    root.transformer.encoder.self_attn = nn.MultiheadAttention(256, 8, dropout=0.1)
+    assert replace_torch_mha(root) == 1
+    m = root.transformer.encoder.self_attn
+    assert isinstance(m, MultiheadAttention) and m.dropout == 0.1 and not m.batch_first
+    keys = set(m.state_dict())
+    assert {"in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias"} <= keys
+    LL.apply_lora_to_model(root, LL.LoRAConfig(rank=8, alpha=16, target_modules=["q_proj", "k_proj", "v_proj", "out_proj"]))
+    sd = LL.lora_state_dict(root)
+    pre = "transformer.encoder.self_attn."
+    assert set(sd) == {pre + f"{n}.lora.lora_{ab}" for n in ("q_proj", "k_proj", "v_proj", "out_proj") for ab in "AB"}
+    assert sd[pre + "q_proj.lora.lora_A"].shape == (256, 8) and sd[pre + "out_proj.lora.lora_B"].shape == (8, 256)
+    assert isinstance(m.out_proj, LL.LoRALinear)
+    # strict mode keeps the reference's behaviour: nothing on a packed-in_proj attention, out_proj never wrapped
+    root2 = nn.Module()
+    root2.self_attn = nn.MultiheadAttention(256, 8)
+    replace_torch_mha(root2)
+    LL.apply_lora_to_model(root2, LL.LoRAConfig(rank=8, target_modules=["q_proj", "out_proj"], strict_reference_names=True))
+    assert LL.lora_state_dict(root2) == {}
+    # detr gate off -> untouched
+    root3 = nn.Module()
+    root3.transformer = nn.Module()
+    root3.transformer.decoder = nn.Module()
+    root3.transformer.decoder.cross_attn = MultiheadAttention(256, 8)
+    LL.apply_lora_to_model(root3, LL.LoRAConfig(rank=8, target_modules=["q_proj"], apply_to_detr_decoder=False))
+    assert LL.lora_state_dict(root3) == {}

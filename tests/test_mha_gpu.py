@@ -1,0 +1,111 @@
+"""Row a7: fused MultiheadAttention (E=256, 8 heads, head_dim 32 as padded 64-wide heads) vs the oracle:
+self / cross attention, additive attn_mask, key_padding_mask, dropout on the probabilities, LoRA on q/k/v/out."""
+import pytest
+import torch
+
+from oracle import mha_oracle as MO
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL, GRAD_TOL = 2e-3, 6e-3
+
+
+def _make(E=256, H=8, batch_first=True, dropout=0.0, lora=True, seed=0):
+    from sam3_lora_b200.lora_layers import LoRAConfig, apply_lora_to_model
+    from sam3_lora_b200.mha import MultiheadAttention
+
+    torch.manual_seed(seed)
+    m = MultiheadAttention(E, H, dropout=dropout, batch_first=batch_first)
+    torch.nn.init.normal_(m.in_proj_bias, std=0.1)
+    torch.nn.init.normal_(m.out_proj.bias, std=0.1)
+    holder = torch.nn.Module()
+    holder.attn = m
+    if lora:
+        apply_lora_to_model(holder, LoRAConfig(rank=8, alpha=16, target_modules=["q_proj", "k_proj", "v_proj", "out_proj"]))
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            torch.nn.init.normal_(getattr(m, n).lora.lora_B, std=0.05)
+    return holder.cuda(), m
+
+
+def _oracle_params(m):
+    p = {"in_proj_weight": m.in_proj_weight.detach().cpu(), "in_proj_bias": m.in_proj_bias.detach().cpu(),
+         "out_proj.weight": m._out_linear.weight.detach().cpu(), "out_proj.bias": m._out_linear.bias.detach().cpu()}
+    leaves = {}
+    for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+        mod = getattr(m, n, None)
+        if mod is not None and hasattr(mod, "lora"):
+            for ab in ("lora_A", "lora_B"):
+                t = getattr(mod.lora, ab).detach().cpu().clone().requires_grad_(True)
+                p[f"{n}.lora.{ab}"] = t
+                leaves[f"{n}.lora.{ab}"] = t
+    return p, leaves
+
+
+def _compare(m, q, k, v, attn_mask=None, kpm=None, dropout=None, batch_first=True):
+    m.dropout_seed_override = dropout[1] if dropout else None
+    qc, kc, vc = (t.clone().cuda().requires_grad_(True) for t in (q, k, v))
+    out = m(qc, kc, vc, key_padding_mask=None if kpm is None else kpm.cuda(), attn_mask=None if attn_mask is None else attn_mask.cuda())[0]
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    out.backward(g.cuda())
+    p, leaves = _oracle_params(m)
+    qo, ko, vo = (t.clone().requires_grad_(True) for t in (q, k, v))
+    bf = (lambda t: t) if batch_first else (lambda t: t.transpose(0, 1))
+    lo = getattr(m, "q_proj", None)
+    scaling = lo.lora.scaling if lo is not None and hasattr(lo, "lora") else 1.0
+    ref = MO.mha_forward(bf(qo), bf(ko), bf(vo), p, m.num_heads, attn_mask=attn_mask, key_padding_mask=kpm, scaling=scaling,
+                         dropout=dropout)
+    ref = bf(ref)
+    ref.backward(g)
+    assert rel_l2(out.detach().cpu(), ref.detach()) < FWD_TOL
+    assert rel_l2(qc.grad.cpu(), qo.grad) < GRAD_TOL
+    assert rel_l2(kc.grad.cpu(), ko.grad) < GRAD_TOL
+    assert rel_l2(vc.grad.cpu(), vo.grad) < GRAD_TOL
+    for n, t in leaves.items():
+        mod, ab = n.split(".lora.")
+        got = getattr(getattr(m, mod).lora, ab).grad.cpu()
+        assert rel_l2(got, t.grad) < GRAD_TOL, n
+    assert m.in_proj_weight.grad is None
+
+
+def test_self_attention_encoder_pattern_with_dropout():
+    holder, m = _make(dropout=0.1)
+    m.train()
+    gen = torch.Generator().manual_seed(0)
+    x, pos = torch.randn(2, 576, 256, generator=gen), torch.randn(2, 576, 256, generator=gen)
+    _compare(m, x + pos, x + pos, x, dropout=(0.1, 4242))
+
+
+def test_cross_attention_to_prompt_with_key_padding_mask():
+    holder, m = _make()
+    m.eval()
+    gen = torch.Generator().manual_seed(1)
+    q, mem = torch.randn(2, 300, 256, generator=gen), torch.randn(2, 33, 256, generator=gen)
+    kpm = torch.zeros(2, 33, dtype=torch.bool)
+    kpm[0, 12:] = True
+    kpm[1, 30:] = True
+    _compare(m, q, mem, mem, kpm=kpm)
+
+
+def test_decoder_cross_attention_with_additive_bias_seq_first():
+    holder, m = _make(batch_first=False)
+    m.eval()
+    gen = torch.Generator().manual_seed(2)
+    q, mem = torch.randn(201, 2, 256, generator=gen), torch.randn(640, 2, 256, generator=gen)
+    bias = torch.randn(2 * 8, 201, 640, generator=gen)
+    _compare(m, q, mem, mem, attn_mask=bias, batch_first=False)
+
+
+def test_no_adapters_matches_torch_module_directly():
+    from sam3_lora_b200.mha import replace_torch_mha
+
+    torch.manual_seed(5)
+    holder = torch.nn.Module()
+    holder.attn = torch.nn.MultiheadAttention(256, 8, batch_first=True)
+    ref_mod = holder.attn
+    x = torch.randn(2, 130, 256)
+    ref = ref_mod.eval()(x, x, x, need_weights=False)[0]
+    assert replace_torch_mha(holder) == 1
+    holder = holder.cuda().eval()
+    out = holder.attn(x.cuda(), x.cuda(), x.cuda())[0]
+    assert rel_l2(out.cpu(), ref.detach()) < FWD_TOL
