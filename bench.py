@@ -152,7 +152,7 @@ def workload_config(args, cpu=False):
                         "adapters; full_lora_config.yaml shape at r=16",
             "batch_per_gpu": args.batch, "global_batch": args.batch * (1 if cpu else args.gpus), "image": "3x1008x1008",
             "parallelism": f"dp{args.gpus}", "l2_policy": "per-step working set (>50 GB of activations) exceeds the 126 MB L2",
-            "depth": args.depth}
+            "depth": args.depth, "cuda_graph": not getattr(args, "no_graph", False)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -211,10 +211,30 @@ def run_native(args):
     eng = model._engine
     step_no = [0]
 
-    def native_step():
-        out = torch.empty(B, 1024, 72, 72, device=dev)
-        eng.forward(images, flat, out, save_for_backward=True)
+    out_buf = torch.empty(B, 1024, 72, 72, device=dev)
+
+    def fwd_bwd():
+        eng.forward(images, flat, out_buf, save_for_backward=True)
         eng.backward(gout, gflat)
+
+    # The ~1280 kernel launches of one forward+backward are captured once in a CUDA graph and replayed (all
+    # pointers are fixed, TMA descriptors are by-value kernel parameters); the all-reduce and AdamW stay eager.
+    graph = None
+    launches_per_fwd_bwd = None
+    if not args.no_graph:
+        fwd_bwd()                                   # first-use cudaFuncSetAttribute calls happen outside capture
+        torch.cuda.synchronize()
+        n_before = L.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fwd_bwd()
+        launches_per_fwd_bwd = L.launch_count() - n_before
+
+    def native_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            fwd_bwd()
         if world > 1:
             dist.all_reduce(gflat)
         step_no[0] += 1
@@ -240,6 +260,8 @@ def run_native(args):
     e1.record()
     sync_all()
     launches = (L.launch_count() - n0) // args.steps
+    if launches_per_fwd_bwd is not None:
+        launches += launches_per_fwd_bwd            # graph replays do not pass through the host-side counter
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -252,14 +274,34 @@ def run_native(args):
     if world > 1:
         model.grad_hook = lambda g: dist.all_reduce(g)
     opt = torch.optim.AdamW(params, lr=args.lr, weight_decay=0.01, fused=True)
-    dev_img = torch.empty_like(images)
+    # double-buffered input: the H2D copy of step i+1 (pinned host memory, side stream) overlaps the compute of
+    # step i, as an input pipeline would; every step still copies its own batch inside the timed region.
+    dev_bufs = [torch.empty_like(images), torch.empty_like(images)]
+    copy_stream = torch.cuda.Stream()
+    copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+    compute_done = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0}
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(compute_done[slot])     # the trunk has finished reading this buffer
+            dev_bufs[slot].copy_(host, non_blocking=True)
+            copy_done[slot].record(copy_stream)
+
+    for ev in compute_done:
+        ev.record()
+    issue_copy(0)
 
     def e2e_step():
-        dev_img.copy_(host, non_blocking=True)         # H2D from pinned memory, every step
-        f = model(dev_img)[0]
+        slot = state["i"] & 1
+        state["i"] += 1
+        issue_copy(slot ^ 1)                             # prefetch the next step's batch
+        torch.cuda.current_stream().wait_event(copy_done[slot])
+        f = model(dev_bufs[slot])[0]
         loss = (f * gout).sum()
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        compute_done[slot].record()
         if world > 1:
             for p in params:
                 p.grad.mul_(1.0 / world)
@@ -357,6 +399,7 @@ def main():
                     help="tensor-core operand format (fp32 accumulate, fp32 residual stream)")
     ap.add_argument("--lr", type=float, default=5e-5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
