@@ -196,6 +196,13 @@ int sam3b_dropout_rows16(const void* x16, int64_t ldx, int32_t rows, int32_t col
 /* gout: dLoss/dout fp32 NCHW; lora_grad_flat: flat fp32 gradients (overwritten, same layout as lora_flat) */
 int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, void* stream);
 
+/* ---- fused sigmoid focal loss (replaces the Triton kernels sam3/train/loss/sigmoid_focal_loss.py:35-208; arithmetic of
+ * sam3/train/loss/loss_fns.py:159-167).  fp32, n elements; `loss` (elementwise) and `sum` (scalar) are optional outputs. */
+int sam3b_focal_loss_fwd(const float* x, const float* y, int64_t n, float alpha, float gamma, float* loss, float* sum, void* stream);
+/* dx[i] = dL/dx[i] * gscale * (g ? g[i] : 1) */
+int sam3b_focal_loss_bwd(const float* x, const float* y, int64_t n, float alpha, float gamma, const float* g, float gscale,
+                         float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,8 @@ SIGNATURES: dict[str, tuple] = {
     "sam3b_lora_pack": (C.c_int, [C.POINTER(LoraSite), vp, vp, i64, vp, vp, i64, i32, vp]),
     "sam3b_lora_unpack_grads": (C.c_int, [C.POINTER(LoraSite), vp, vp, C.POINTER(vp), C.POINTER(vp), vp]),
     "sam3b_dropout_rows16": (C.c_int, [vp, i64, i32, i32, vp, i64, f32, C.c_uint32, i32, vp]),
+    "sam3b_focal_loss_fwd": (C.c_int, [vp, vp, i64, f32, f32, vp, vp, vp]),
+    "sam3b_focal_loss_bwd": (C.c_int, [vp, vp, i64, f32, f32, vp, f32, vp, vp]),
     "sam3b_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]),
 }
 

@@ -180,14 +180,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
       constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);  // A K-major, B K-major, N=64
       constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1); // A K-major, B MN-major, N=64
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-      mbar_wait(kv_full, 0, 20);
+      mbar_wait_sleep(kv_full, 0, 20, 20);
       // S^T / dP^T of block j+1 are issued as soon as the compute warps hold block j in registers
       // (sdp_free), i.e. they overlap the exp / pack / store work of block j instead of waiting for it.
       auto issue_sdp = [&](int j) {
         const int st = j & 1;
         const uint32_t q_addr = smem_u32(sQ + st * I_BYTES), do_addr = smem_u32(sdO + st * I_BYTES);
-        mbar_wait(&in_full[st], (j >> 1) & 1, 21);
-        if (j > 0) mbar_wait(sdp_free, (j - 1) & 1, 24);
+        mbar_wait_sleep(&in_full[st], (j >> 1) & 1, 21, 20);
+        if (j > 0) mbar_wait_sleep(sdp_free, (j - 1) & 1, 24, 20);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // S^T = K . Q^T
@@ -202,7 +202,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
         const int st = j & 1;
         const uint32_t q_addr = smem_u32(sQ + st * I_BYTES), do_addr = smem_u32(sdO + st * I_BYTES);
         if (j + 1 < n_blocks) issue_sdp(j + 1);
-        mbar_wait(pds_full, j & 1, 22);
+        mbar_wait_sleep(pds_full, j & 1, 22, 20);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // dV += P^T . dO   (K = 64 queries)
@@ -362,12 +362,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // q buffer,  box 
       constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);
       constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1);
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
-      mbar_wait(q_full, 0, 20);
+      mbar_wait_sleep(q_full, 0, 20, 20);
       auto issue_sdp = [&](int j) {
         const int st = j & 1;
         const uint32_t k_addr = smem_u32(sK + st * I_BYTES), v_addr = smem_u32(sV + st * I_BYTES);
-        mbar_wait(&in_full[st], (j >> 1) & 1, 21);
-        if (j > 0) mbar_wait(sdp_free, (j - 1) & 1, 24);
+        mbar_wait_sleep(&in_full[st], (j >> 1) & 1, 21, 20);
+        if (j > 0) mbar_wait_sleep(sdp_free, (j - 1) & 1, 24, 20);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // S = Q . K^T
@@ -382,7 +382,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // q buffer,  box 
         const int st = j & 1;
         const uint32_t k_addr = smem_u32(sK + st * I_BYTES);
         if (j + 1 < n_blocks) issue_sdp(j + 1);
-        mbar_wait(ds_full, j & 1, 22);
+        mbar_wait_sleep(ds_full, j & 1, 22, 20);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // dQ += dS . K   (K = 64 keys, K tile as MN-major B)

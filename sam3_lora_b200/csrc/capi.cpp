@@ -6,6 +6,7 @@
 #include "elementwise.cuh"
 #include "engine.h"
 #include "gemm.cuh"
+#include "loss.cuh"
 
 using namespace sam3b;
 
@@ -182,6 +183,14 @@ int sam3b_dropout_rows16(const void* x16, int64_t ldx, int32_t rows, int32_t col
 int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, void* stream) {
   if (!v) return fail(-1, "sam3b_vit_backward: null handle");
   return v->eng->backward(gout_nchw, lora_grad_flat, static_cast<cudaStream_t>(stream));
+}
+
+int sam3b_focal_loss_fwd(const float* x, const float* y, int64_t n, float alpha, float gamma, float* loss, float* sum, void* stream) {
+  return focal_loss_fwd(x, y, n, alpha, gamma, loss, sum, static_cast<cudaStream_t>(stream));
+}
+int sam3b_focal_loss_bwd(const float* x, const float* y, int64_t n, float alpha, float gamma, const float* g, float gscale,
+                         float* dx, void* stream) {
+  return focal_loss_bwd(x, y, n, alpha, gamma, g, gscale, dx, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -75,7 +75,7 @@ def _ann_to_mask(ann: Dict, h: int, w: int) -> np.ndarray:
 class COCOSegmentDataset(torch.utils.data.Dataset):
     """Same directory contract as the reference: `<data_dir>/<split>/_annotations.coco.json` + images."""
 
-    def __init__(self, data_dir, split: str = "train", mask_size: int = 72):
+    def __init__(self, data_dir, split: str = "train", mask_size: int = 72, resolution: int = RESOLUTION):
         self.split_dir = Path(data_dir) / split
         ann_file = self.split_dir / "_annotations.coco.json"
         if not ann_file.exists():
@@ -87,7 +87,7 @@ class COCOSegmentDataset(torch.utils.data.Dataset):
         for a in coco["annotations"]:
             self.img_to_anns.setdefault(a["image_id"], []).append(a)
         self.categories = {c["id"]: c["name"] for c in coco["categories"]}
-        self.resolution = RESOLUTION
+        self.resolution = resolution
         self.mask_size = mask_size
         print(f"Loaded COCO dataset: {split} split")
         print(f"  Images: {len(self.image_ids)}")
@@ -187,7 +187,8 @@ class SAM3TrainerNative:
         self.out_dir.mkdir(parents=True, exist_ok=True)
 
     def _loader(self, split: str, epoch: int, shuffle: bool):
-        ds = COCOSegmentDataset(self.config["training"]["data_dir"], split)
+        spec = self.model.trunk.spec
+        ds = COCOSegmentDataset(self.config["training"]["data_dir"], split, mask_size=spec.grid, resolution=spec.img_size)
         idx = D.shard_indices(len(ds), self.rank, self.world, epoch=epoch, shuffle=shuffle)
         sub = torch.utils.data.Subset(ds, idx)
         return torch.utils.data.DataLoader(sub, batch_size=self.batch_size, shuffle=False, num_workers=0, collate_fn=collate,
