@@ -104,6 +104,10 @@ def cpu_unit_seconds(reps: int, warm: int):
 
     from oracle import vit_oracle as O
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
     cfg = O.ViTConfig(depth=4, global_att_blocks=(3,))
     spec = O.LoRASpec(rank=16, alpha=32.0)
     params = O.make_params(cfg, spec, seed=0)
@@ -354,12 +358,12 @@ def run_native(args):
             traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             traffic = None
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN=256, EPI_GELU> M=%d N=%d K=%d" % (M, N, K),
+    roofline = {"bound": "tensor", "kernel": "gemm2_kernel<EPI_GELU> (CTA pair 256x256) M=%d N=%d K=%d" % (M, N, K),
                 "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s", "frac": achieved / peaks["burst"],
                 "peak_source": peaks["source"] + " cuBLAS bf16 burst", "traffic": traffic,
                 "algorithmic_bytes": M * K * 2 + N * K * 2 + M * N * 2 * 2,
-                "step_trunk_tflops": value * GF_TRUNK_TRAIN / 1e3,
-                "step_trunk_frac_of_sustained": value * GF_TRUNK_TRAIN / 1e3 / peaks["sustained"],
+                "step_trunk_tflops": value / world * GF_TRUNK_TRAIN / 1e3,
+                "step_trunk_frac_of_sustained": value / world * GF_TRUNK_TRAIN / 1e3 / peaks["sustained"],
                 "attn_gemm_roofline_frac": value / world * GF_ATTN_GEMM_TRAIN / 1e3 / peaks["sustained"]}
 
     # -------- CPU baseline beside it (rank 0, N=1 only) --------
