@@ -26,6 +26,15 @@
 
 namespace sam3b {
 
+#ifdef SAM3B_TRACE
+// Debug timeline (tools/attn_trace.py): one chosen CTA stamps clock64() at its pipeline events.
+__device__ unsigned long long g_attn_trace[16384];
+#define TR_CTA 1500
+#define TRACE(slot) do { if (blockIdx.x + blockIdx.y * gridDim.x == TR_CTA && (slot) < 16384) g_attn_trace[(slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int HD = 64;
@@ -137,6 +146,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) TRACE(0);
   const int tile = blockIdx.x % p.tiles;
   const int seg = blockIdx.x / p.tiles;
   const int head = blockIdx.y;
@@ -156,6 +166,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TRACE(1);
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 64, tm_dV = tmem_base + 128, tm_dK = tmem_base + 192;
 
   if (warp == 8) {
@@ -180,14 +191,15 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
       constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);  // A K-major, B K-major, N=64
       constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1); // A K-major, B MN-major, N=64
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-      mbar_wait_sleep(kv_full, 0, 20, 20);
+      mbar_wait(kv_full, 0, 20);
+      TRACE(2);
       // S^T / dP^T of block j+1 are issued as soon as the compute warps hold block j in registers
       // (sdp_free), i.e. they overlap the exp / pack / store work of block j instead of waiting for it.
       auto issue_sdp = [&](int j) {
         const int st = j & 1;
         const uint32_t q_addr = smem_u32(sQ + st * I_BYTES), do_addr = smem_u32(sdO + st * I_BYTES);
-        mbar_wait_sleep(&in_full[st], (j >> 1) & 1, 21, 20);
-        if (j > 0) mbar_wait_sleep(sdp_free, (j - 1) & 1, 24, 20);
+        mbar_wait(&in_full[st], (j >> 1) & 1, 21);
+        if (j > 0) mbar_wait(sdp_free, (j - 1) & 1, 24);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // S^T = K . Q^T
@@ -201,8 +213,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j & 1;
         const uint32_t q_addr = smem_u32(sQ + st * I_BYTES), do_addr = smem_u32(sdO + st * I_BYTES);
+        TRACE(64 + j * 16 + 8);
         if (j + 1 < n_blocks) issue_sdp(j + 1);
-        mbar_wait_sleep(pds_full, j & 1, 22, 20);
+        TRACE(64 + j * 16 + 9);
+        mbar_wait(pds_full, j & 1, 22);
+        TRACE(64 + j * 16 + 10);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // dV += P^T . dO   (K = 64 queries)
@@ -214,6 +229,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
                       (j > 0 || k > 0));
         umma_commit(&in_free[st]);
         umma_commit(acc_done);
+        TRACE(64 + j * 16 + 11);
       }
     }
   } else {
@@ -237,14 +253,17 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
       // per-query statistics were bulk-copied next to Q/dO by the producer (visible once in_full completed)
       const float* stat = sStat + (j & 1) * (2 * BI);
       const int q_valid = min(BI, p.Lq - j * BI);   // queries of this block that exist
+      if (threadIdx.x == 0) TRACE(64 + j * 16 + 0);
       mbar_wait(&in_full[j & 1], (j >> 1) & 1, 33);
       mbar_wait(sdp_full, j & 1, 30);
+      if (threadIdx.x == 0) TRACE(64 + j * 16 + 1);
       tc_fence_after();
       {
         uint32_t s[32], d[32];
         tmem_ld_x32(tm_S + lane_off + cc, s);
         tmem_ld_x32(tm_dP + lane_off + cc, d);
         tmem_ld_wait();
+        if (threadIdx.x == 0) TRACE(64 + j * 16 + 2);
         tc_fence_before();
         mbar_arrive(sdp_free);  // TMEM S^T/dP^T may be overwritten by block j+1
         float pv[32], dsv[32];
@@ -274,20 +293,25 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
             dsv[i] = dead ? 0.f : pe * (dp * keep_scale - stat[BI + cc + i]);
           }
         }
-        if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);  // previous dV/dK MMAs finished reading sP/sdS
+        if (threadIdx.x == 0) TRACE(64 + j * 16 + 3);
+        if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);
+        if (threadIdx.x == 0) TRACE(64 + j * 16 + 4);  // previous dV/dK MMAs finished reading sP/sdS
         store_row_chunk16<DT>(p_row, sw, cc >> 3, pv);
         store_row_chunk16<DT>(ds_row, sw, cc >> 3, dsv);
       }
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(pds_full);
+      if (threadIdx.x == 0) TRACE(64 + j * 16 + 5);
     }
     mbar_wait(acc_done, (n_blocks - 1) & 1, 32);
+    if (threadIdx.x == 0) TRACE(3);
     tc_fence_after();
     const int row = t_row0 + r;
     const bool valid = (tile * BT + r) < p.Lk;
     store_grad_chunk<DT, false>(p, p.dkv, p.lddkv, tm_dV + lane_off, row, row, p.dv_col0 + head * HD, cc, 1.f, valid);
     store_grad_chunk<DT, true>(p, p.dkv, p.lddkv, tm_dK + lane_off, row, row, p.dk_col0 + head * HD, cc, p.scale, valid);
+    if (threadIdx.x == 0) TRACE(4);
   }
   tc_fence_before();
   __syncthreads();
@@ -362,12 +386,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // q buffer,  box 
       constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);
       constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1);
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
-      mbar_wait_sleep(q_full, 0, 20, 20);
+      mbar_wait(q_full, 0, 20);
       auto issue_sdp = [&](int j) {
         const int st = j & 1;
         const uint32_t k_addr = smem_u32(sK + st * I_BYTES), v_addr = smem_u32(sV + st * I_BYTES);
-        mbar_wait_sleep(&in_full[st], (j >> 1) & 1, 21, 20);
-        if (j > 0) mbar_wait_sleep(sdp_free, (j - 1) & 1, 24, 20);
+        mbar_wait(&in_full[st], (j >> 1) & 1, 21);
+        if (j > 0) mbar_wait(sdp_free, (j - 1) & 1, 24);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // S = Q . K^T
@@ -382,7 +406,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // q buffer,  box 
         const int st = j & 1;
         const uint32_t k_addr = smem_u32(sK + st * I_BYTES);
         if (j + 1 < n_blocks) issue_sdp(j + 1);
-        mbar_wait_sleep(ds_full, j & 1, 22, 20);
+        mbar_wait(ds_full, j & 1, 22);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // dQ += dS . K   (K = 64 keys, K tile as MN-major B)
@@ -527,5 +551,16 @@ int attn_bwd_launch(const AttnArgs& a, cudaStream_t stream) {
   return a.dtype == 0 ? launch_bwd<0, false>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream)
                       : launch_bwd<1, false>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream);
 }
+
+#ifdef SAM3B_TRACE
+int attn_trace_read(unsigned long long* host, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(unsigned long long) * (size_t)n);
+}
+int attn_trace_clear() {
+  static unsigned long long z[16384];
+  return (int)cudaMemcpyToSymbol(g_attn_trace, z, sizeof(z));
+}
+#endif
 
 }  // namespace sam3b

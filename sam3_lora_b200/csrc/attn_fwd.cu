@@ -119,10 +119,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j & 1;
         const int kv_row0 = kv_row0_seg + j * BKV;
-        if (j >= 2) mbar_wait_sleep(&k_free[st], ((j - 2) >> 1) & 1, 10, 64);
+        if (j >= 2) mbar_wait(&k_free[st], ((j - 2) >> 1) & 1, 10);
         mbar_arrive_expect_tx(&k_full[st], KV_BYTES);
         tma_load_2d(sK + st * KV_BYTES, &tmKV, &k_full[st], p.k_col0 + head * HD, kv_row0);
-        if (j >= 2) mbar_wait_sleep(&v_free[st], ((j - 2) >> 1) & 1, 11, 64);
+        if (j >= 2) mbar_wait(&v_free[st], ((j - 2) >> 1) & 1, 11);
         mbar_arrive_expect_tx(&v_full[st], KV_BYTES);
         tma_load_2d(sV + st * KV_BYTES, &tmKV, &v_full[st], p.v_col0 + head * HD, kv_row0);
       }
@@ -135,7 +135,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t q_addr = smem_u32(sQ);
       auto issue_s = [&](int j) {
         const int st = j & 1;
-        mbar_wait_sleep(&k_full[st], (j >> 1) & 1, 21, 20);
+        mbar_wait(&k_full[st], (j >> 1) & 1, 21);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + st * KV_BYTES);
 #pragma unroll
@@ -144,15 +144,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(&s_full[st]);
         umma_commit(&k_free[st]);
       };
-      mbar_wait_sleep(q_full, 0, 20, 20);
+      mbar_wait(q_full, 0, 20);
       issue_s(0);
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j & 1;
         // S_{j+1} goes out before we block on the softmax of block j (its buffer was consumed when
         // p_full(j-1) completed, which the previous iteration waited for).
         if (j + 1 < n_blocks) issue_s(j + 1);
-        mbar_wait_sleep(&p_full[st], (j >> 1) & 1, 22, 20);
-        mbar_wait_sleep(&v_full[st], (j >> 1) & 1, 23, 20);
+        mbar_wait(&p_full[st], (j >> 1) & 1, 22);
+        mbar_wait(&v_full[st], (j >> 1) & 1, 23);
         tc_fence_after();
         const uint32_t p_addr = smem_u32(sP + st * P_BYTES), v_addr = smem_u32(sV + st * KV_BYTES);
 #pragma unroll

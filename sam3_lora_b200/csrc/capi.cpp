@@ -8,6 +8,10 @@
 #include "gemm.cuh"
 #include "loss.cuh"
 
+#ifdef SAM3B_TRACE
+namespace sam3b { int attn_trace_read(unsigned long long*, int); int attn_trace_clear(); }
+#endif
+
 using namespace sam3b;
 
 extern "C" {
@@ -192,5 +196,10 @@ int sam3b_focal_loss_bwd(const float* x, const float* y, int64_t n, float alpha,
                          float* dx, void* stream) {
   return focal_loss_bwd(x, y, n, alpha, gamma, g, gscale, dx, static_cast<cudaStream_t>(stream));
 }
+
+#ifdef SAM3B_TRACE
+int sam3b_debug_trace_read(unsigned long long* host, int n) { return attn_trace_read(host, n); }
+int sam3b_debug_trace_clear(void) { return attn_trace_clear(); }
+#endif
 
 }  // extern "C"
