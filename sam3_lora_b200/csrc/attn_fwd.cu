@@ -7,14 +7,16 @@
 // is kept in window-major order, so a window is a contiguous run of L rows ("segment").
 //
 // Layout: qkv [tokens][ld] 16-bit with q at column h*64, k at D + h*64, v at 2D + h*64.
-// One CTA = one (128-query tile, head, segment); 2 CTAs co-resident per SM (80 KB smem, 256 TMEM
-// columns each).  Everything that crosses a role boundary is double-buffered so the tensor core
-// works on block j+1 while the softmax warps work on block j:
-//   warps 0-3 : softmax + output (thread t owns query row t == TMEM lane t)
-//   warp  4   : TMA producer (Q once, then K_j / V_j into 2-stage rings)
+// One CTA = one (128-query tile, head, segment); 2 CTAs co-resident per SM (64 KB smem, 256 TMEM
+// columns each).  Both MMAs take their A operand FROM TENSOR MEMORY: the Q tile is parked in TMEM once
+// (16-bit, two elements per column) and P_j is written back over the S_j columns it was computed from, so
+// the only shared-memory traffic per block is the streamed K_j / V_j tiles (an SS-MMA with N=64 needs
+// 192 B/clk of smem operands against the SM's 128 B/clk: profiles/r01_attn_bwd_timeline.md).
+//   warps 0-3 : softmax + output (thread t owns query row t == TMEM lane t); they also load Q
+//   warp  4   : TMA producer (K_j / V_j into 4-stage rings)
 //   warp  5   : MMA issuer + TMEM allocator; issue order S_0, S_1, PV_0, S_2, PV_1, ...
 // Per 64-key block j:  S_j = Q K_j^T (fp32, TMEM buffer j&1) -> one pass over the 64 scores in
-// registers: row max, p = exp2(s*c - m*c), row sum -> P_j (16-bit) into swizzled smem buffer j&1 ->
+// registers: row max, p = exp2(s*c - m*c), row sum -> P_j (16-bit) into TMEM buffer j&1 ->
 // O += P_j V_j accumulated IN TMEM (V tile as MN-major B operand).  The running max only moves when
 // the block max exceeds it by more than 2^8 in the exp2 domain ("lazy rescale"): then the softmax
 // warps rescale the O accumulator in TMEM (tcgen05.ld / st) before publishing P_j.  Output: O
@@ -32,19 +34,19 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;  // queries per CTA
 constexpr int BKV = 64;  // keys per block: divides 576 and 5184
-constexpr int Q_BYTES = BQ * HD * 2;   // 16 KB
 constexpr int KV_BYTES = BKV * HD * 2; // 8 KB
-constexpr int P_BYTES = BQ * BKV * 2;  // 16 KB = one swizzle atom [128][64]
+constexpr int NS = 4;                  // K / V ring depth
 // 2 CTAs/SM: 2 x (dynamic + 1 KB reserved) must fit the SM's 228 KB: no alignment slack, the dynamic
 // window is declared 1024-byte aligned and checked at run time.
-constexpr int FWD_SMEM = Q_BYTES + 4 * KV_BYTES + 2 * P_BYTES + 256 /*barriers*/;
-constexpr int TCOLS = 256;  // S0: [0,64)  S1: [64,128)  O: [128,192)
+constexpr int FWD_SMEM = 2 * NS * KV_BYTES + 256 /*barriers*/;
+constexpr int TCOLS = 256;  // S0/P0: [0,64)  S1/P1: [64,128)  O: [128,192)  Q (16-bit A operand): [192,224)
 constexpr float RESCALE_LOG2 = 8.f;  // p <= 2^8 between rescales: safe in fp16/bf16 and fp32 sums
 
 struct FwdParams {
   int Lq, Lk;     // rows per segment (queries / keys)
   int q_tiles;    // ceil(Lq / 128)
   int q_col0, k_col0, v_col0, o_col0;
+  const void* q; int64_t ldq;
   void* O; int64_t ldo;
   float* lse2;    // [H][nseg * Lq_stat]
   int Lq_stat;    // Lq rounded up to 64
@@ -65,23 +67,22 @@ __device__ __forceinline__ bool attn_drop_keep(uint32_t base, uint32_t q, uint32
 
 template <int DT, bool GEN>
 __global__ void __launch_bounds__(192, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // swizzle-128B operands need 1024-byte alignment
-  uint8_t* sQ = smem_raw;
-  uint8_t* sK = sQ + Q_BYTES;          // 2 stages
-  uint8_t* sV = sK + 2 * KV_BYTES;     // 2 stages
-  uint8_t* sP = sV + 2 * KV_BYTES;     // 2 buffers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_free = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;   // [2]
-  uint64_t* v_free = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;   // [2]
-  uint64_t* p_full = bars + 11;  // [2]
-  uint64_t* pv_done = bars + 13; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint8_t* sK = smem_raw;              // NS stages
+  uint8_t* sV = sK + NS * KV_BYTES;    // NS stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * KV_BYTES);
+  uint64_t* q_ready = bars + 0;
+  uint64_t* k_full = bars + 1;            // [NS]
+  uint64_t* k_free = k_full + NS;         // [NS]
+  uint64_t* v_full = k_free + NS;         // [NS]
+  uint64_t* v_free = v_full + NS;         // [NS]
+  uint64_t* s_full = v_free + NS;         // [2]
+  uint64_t* p_full = s_full + 2;          // [2]
+  uint64_t* pv_done = p_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  static_assert((1 + 4 * NS + 6) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
 
   const int warp = threadIdx.x >> 5;
   const int q_tile = blockIdx.x % p.q_tiles;
@@ -92,13 +93,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_blocks = (p.Lk + BKV - 1) / BKV;
 
   if (warp == 4 && elect_one()) {
-    tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    mbar_init(q_ready, 128);
+    for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_free[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_free[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1);
     }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -110,19 +110,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 2 * BKV;
+  const uint32_t tmem_Q = tmem_base + 3 * BKV;
 
   if (warp == 4) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, p.q_col0 + head * HD, q_row0);
       for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
+        const int st = j % NS;
         const int kv_row0 = kv_row0_seg + j * BKV;
-        if (j >= 2) mbar_wait(&k_free[st], ((j - 2) >> 1) & 1, 10);
+        if (j >= NS) mbar_wait(&k_free[st], (j / NS - 1) & 1, 10);
         mbar_arrive_expect_tx(&k_full[st], KV_BYTES);
         tma_load_2d(sK + st * KV_BYTES, &tmKV, &k_full[st], p.k_col0 + head * HD, kv_row0);
-        if (j >= 2) mbar_wait(&v_free[st], ((j - 2) >> 1) & 1, 11);
+        if (j >= NS) mbar_wait(&v_free[st], (j / NS - 1) & 1, 11);
         mbar_arrive_expect_tx(&v_full[st], KV_BYTES);
         tma_load_2d(sV + st * KV_BYTES, &tmKV, &v_full[st], p.v_col0 + head * HD, kv_row0);
       }
@@ -132,34 +131,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, DT, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(BQ, HD, DT, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ);
+      // S_j = Q K_j^T: A = the Q tile in TMEM (K=16 elements = 8 columns per instruction), B = K_j in smem
       auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1, 21);
+        const int st = j % NS, sb = j & 1;
+        mbar_wait(&k_full[st], (j / NS) & 1, 21);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + st * KV_BYTES);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_f16_ss(tmem_base + st * BKV, make_desc_kmajor(q_addr + k * 32), make_desc_kmajor(k_addr + k * 32), idesc_s, k > 0);
-        umma_commit(&s_full[st]);
+          umma_f16_ts(tmem_base + sb * BKV, tmem_Q + k * 8, make_desc_kmajor(k_addr + k * 32), idesc_s, k > 0);
+        umma_commit(&s_full[sb]);
         umma_commit(&k_free[st]);
       };
-      mbar_wait(q_full, 0, 20);
+      mbar_wait(q_ready, 0, 20);
+      tc_fence_after();
       issue_s(0);
       for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
-        // S_{j+1} goes out before we block on the softmax of block j (its buffer was consumed when
-        // p_full(j-1) completed, which the previous iteration waited for).
+        const int st = j % NS, sb = j & 1;
+        // S_{j+1} goes out before we block on the softmax of block j.  It overwrites buffer (j+1)&1, i.e. P_{j-1}:
+        // P_{j-1}.V_{j-1} was issued in the previous iteration and the tensor pipe executes in issue order.
         if (j + 1 < n_blocks) issue_s(j + 1);
-        mbar_wait(&p_full[st], (j >> 1) & 1, 22);
-        mbar_wait(&v_full[st], (j >> 1) & 1, 23);
+        mbar_wait(&p_full[sb], (j >> 1) & 1, 22);
+        mbar_wait(&v_full[st], (j / NS) & 1, 23);
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(sP + st * P_BYTES), v_addr = smem_u32(sV + st * KV_BYTES);
+        const uint32_t v_addr = smem_u32(sV + st * KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
-          umma_f16_ss(tmem_O, make_desc_kmajor(p_addr + k * 32), make_desc_mnmajor(v_addr + k * 2048, 8192), idesc_pv,
+        for (int k = 0; k < BKV / 16; ++k)   // A = P_j (16-bit, packed over the first 32 columns of S buffer sb)
+          umma_f16_ts(tmem_O, tmem_base + sb * BKV + k * 8, make_desc_mnmajor(v_addr + k * 2048, 8192), idesc_pv,
                       (j > 0 || k > 0));
-        umma_commit(&pv_done[st]);
+        umma_commit(&pv_done[sb]);
         umma_commit(&v_free[st]);
       }
     }
@@ -170,7 +170,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float c = p.scale_log2;
     const float tau = GEN ? RESCALE_LOG2 : RESCALE_LOG2 / c;  // in the units of the running max
     float m_used = -INFINITY, l_run = 0.f;
-    const int sw = r & 7;
     // GEN: scores are first moved to the log2 domain (t = s*c + bias*log2e, -inf where the key is padded) and the
     // running max lives in that domain (c_eff = 1); the ViT instantiation keeps raw scores and folds c into the exp.
     const int q_in_seg = min(q_tile * BQ + r, p.Lq - 1);
@@ -181,6 +180,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
     }
     const float c_eff = GEN ? 1.f : c;
+
+    {  // park this thread's Q row (64 x 16-bit = 32 packed columns) in TMEM as the A operand of every S_j
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.q) +
+                                                        (int64_t)(seg * p.Lq + q_in_seg) * p.ldq + p.q_col0 + head * HD);
+      uint32_t qa[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = __ldg(src + i);
+        qa[4 * i] = u.x; qa[4 * i + 1] = u.y; qa[4 * i + 2] = u.z; qa[4 * i + 3] = u.w;
+      }
+      tmem_st_x32(tmem_Q + lane_off, qa);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(q_ready);
+    }
 
     for (int j = 0; j < n_blocks; ++j) {
       const int st = j & 1;
@@ -253,10 +267,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         l_run *= alpha;
         m_used = m_new;
       }
-      // P buffer `st` was last read by P.V of block j-2
-      if (j >= 2) mbar_wait(&pv_done[st], ((j - 2) >> 1) & 1, 32);
+      // P_j goes over the S_j columns: s_full(j) (a commit) already implies that P.V of block j-2, the last
+      // reader of this buffer, has completed.
       const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_eff;  // all keys masked so far: exp2(-inf - 0) = 0
-      uint8_t* p_row = sP + st * P_BYTES + r * 128;
+      uint32_t pk[32];
       float l_part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -289,11 +303,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // fp32 row sum of the unrounded probabilities (no 16-bit -> fp32 conversions: the conversion pipe
         // shares its 16 lanes/clk with MUFU and is what bounds this loop)
         l_part[q & 3] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-        *reinterpret_cast<uint4*>(p_row + ((q ^ sw) << 4)) = u;
+        pk[4 * q] = u.x; pk[4 * q + 1] = u.y; pk[4 * q + 2] = u.z; pk[4 * q + 3] = u.w;
       }
+      tmem_st_x32(tmem_base + lane_off + st * BKV, pk);
+      tmem_st_wait();
       l_run += (l_part[0] + l_part[1]) + (l_part[2] + l_part[3]);
       tc_fence_before();         // our tcgen05.ld/st are ordered before the MMA warp's next tcgen05 ops
-      fence_proxy_async_smem();  // st.shared of P visible to the tensor core (async proxy)
       mbar_arrive(&p_full[st]);
     }
     mbar_wait(&pv_done[(n_blocks - 1) & 1], ((n_blocks - 1) >> 1) & 1, 33);
@@ -330,13 +345,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 // one instantiation (and one cached smem attribute) per (operand format, feature set)
 template <int DT, bool GEN>
-static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const FwdParams& p, dim3 grid, cudaStream_t stream) {
+static int launch_fwd(const CUtensorMap& tmKV, const FwdParams& p, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     SAM3B_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr_set = true;
   }
-  attn_fwd_kernel<DT, GEN><<<grid, 192, FWD_SMEM, stream>>>(tmQ, tmKV, p);
+  attn_fwd_kernel<DT, GEN><<<grid, 192, FWD_SMEM, stream>>>(tmKV, p);
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -350,14 +365,13 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t stream) {
   SAM3B_REQUIRE(a.q_col0 % 8 == 0 && a.k_col0 % 8 == 0 && a.v_col0 % 8 == 0 && a.o_col0 % 8 == 0, "attention: column offsets must be multiples of 8");
   SAM3B_REQUIRE(a.dtype == 0 || a.dtype == 1, "attention: dtype");
   SAM3B_REQUIRE(a.drop_p >= 0.f && a.drop_p < 1.f, "attention: dropout p=%f outside [0,1)", a.drop_p);
-  CUtensorMap tmQ, tmKV;
-  int rc = make_tmap_2d(&tmQ, a.q, (uint64_t)a.nseg * a.Lq, a.q_cols, a.ldq, BQ, HD);
-  if (rc) return rc;
-  rc = make_tmap_2d(&tmKV, a.kv, (uint64_t)a.nseg * a.Lk, a.kv_cols, a.ldkv, BKV, HD);
+  CUtensorMap tmKV;
+  int rc = make_tmap_2d(&tmKV, a.kv, (uint64_t)a.nseg * a.Lk, a.kv_cols, a.ldkv, BKV, HD);
   if (rc) return rc;
   FwdParams p{};
   p.Lq = a.Lq; p.Lk = a.Lk; p.q_tiles = (a.Lq + BQ - 1) / BQ;
   p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0; p.o_col0 = a.o_col0;
+  p.q = a.q; p.ldq = a.ldq;
   p.O = a.O; p.ldo = a.ldo; p.lse2 = a.lse2; p.H = a.heads;
   p.Lq_stat = attn_lq_stat(a.Lq); p.stat_stride = (int64_t)a.nseg * p.Lq_stat;
   p.scale_log2 = a.scale * 1.4426950408889634f;
@@ -365,8 +379,8 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t stream) {
   p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_thr = a.drop_p > 0.f ? dropout_threshold(a.drop_p) : 0u; p.drop_seed = a.drop_seed;
   dim3 grid(p.q_tiles * a.nseg, a.heads);
   const bool gen = a.bias != nullptr || a.kpm != nullptr || a.drop_p > 0.f;
-  if (gen) return a.dtype == 0 ? launch_fwd<0, true>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, true>(tmQ, tmKV, p, grid, stream);
-  return a.dtype == 0 ? launch_fwd<0, false>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, false>(tmQ, tmKV, p, grid, stream);
+  if (gen) return a.dtype == 0 ? launch_fwd<0, true>(tmKV, p, grid, stream) : launch_fwd<1, true>(tmKV, p, grid, stream);
+  return a.dtype == 0 ? launch_fwd<0, false>(tmKV, p, grid, stream) : launch_fwd<1, false>(tmKV, p, grid, stream);
 }
 
 }  // namespace sam3b
