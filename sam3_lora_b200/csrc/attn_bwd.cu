@@ -9,16 +9,24 @@
 // so that dqkv is the gradient w.r.t. the *un-rotated* qkv projection output.
 //
 // Two deterministic kernels, no atomics (recompute S/dP in both, 7 matmuls instead of 5):
-//   attn_bwd_dkdv : one CTA per (128-key tile, head, segment), loops over 64-query blocks.
-//                   S^T = K Q^T and dP^T = V dO^T in TMEM (thread = key row), P^T / dS^T written
-//                   16-bit to swizzled smem as A operands, dV += P^T dO, dK += dS^T Q with the
-//                   same Q/dO tiles re-used as MN-major B operands.
-//   attn_bwd_dq   : one CTA per (128-query tile, head, segment), loops over 64-key blocks.
-//                   S = Q K^T, dP = dO V^T (thread = query row), dQ += dS K (K tile as MN-major B).
-// Both: warps 0-7 compute (two warps per TMEM lane quarter, each owning 32 of the 64 inner columns, so
-// 16 compute warps per SM hide the tcgen05.ld / MUFU latencies), warp 8 TMA, warp 9 MMA issue + TMEM
-// alloc; 256 TMEM columns and <= 100 KB smem so two CTAs share an SM.
+//   attn_bwd_dkdv : work item = (128-key tile, head, segment), loop over 64-query blocks.
+//                   S^T = K Q^T and dP^T = V dO^T in TMEM (thread = key row), dV += P^T dO, dK += dS^T Q.
+//   attn_bwd_dq   : work item = (128-query tile, head, segment), loop over 64-key blocks.
+//                   S = Q K^T, dP = dO V^T (thread = query row), dQ += dS K.
+// Every MMA takes its A operand FROM TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc): the item's stationary
+// tiles (K, V resp. Q, dO; 16-bit, two elements per column) are parked in TMEM once and P^T / dS^T / dS are
+// written back to TMEM by the compute warps.  Only the streamed 64-row B tiles live in shared memory: an
+// SS-MMA with N=64 needs 192 B/clk of smem operands against the SM's 128 B/clk, which is what bounded the first
+// version of these kernels (profiles/r01_attn_bwd_timeline.md).
+// One persistent CTA per SM owns all 512 TMEM columns: S / dP are double-buffered and two groups of 8 compute
+// warps alternate blocks (group g takes the blocks with (running block index & 1) == g), so the tensor core
+// works on block j+1, j+2 while a group is in the exp / pack phase of block j.  Warp 16 = TMA producer (4-stage
+// ring), warps 17 / 18 = the two MMA-issuing threads (17 also allocates TMEM).  The CTA walks a static list of work items; the next item's
+// stationary tiles are parked before the current item's epilogue so its first MMAs overlap the epilogue.
 #include "attn.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -29,8 +37,8 @@ namespace sam3b {
 #ifdef SAM3B_TRACE
 // Debug timeline (tools/attn_trace.py): one chosen CTA stamps clock64() at its pipeline events.
 __device__ unsigned long long g_attn_trace[16384];
-#define TR_CTA 1500
-#define TRACE(slot) do { if (blockIdx.x + blockIdx.y * gridDim.x == TR_CTA && (slot) < 16384) g_attn_trace[(slot)] = clock64(); } while (0)
+#define TR_CTA 70
+#define TRACE(slot) do { if (blockIdx.x == TR_CTA && (slot) < 16384) g_attn_trace[(slot)] = clock64(); } while (0)
 #else
 #define TRACE(slot) do { } while (0)
 #endif
@@ -40,13 +48,19 @@ namespace {
 constexpr int HD = 64;
 constexpr int BT = 128;  // rows owned by a CTA (keys in dkdv, queries in dq)
 constexpr int BI = 64;   // inner block (queries in dkdv, keys in dq)
-constexpr int T_BYTES = BT * HD * 2;   // 16 KB
 constexpr int I_BYTES = BI * HD * 2;   // 8 KB
-constexpr int A_BYTES = BT * BI * 2;   // 16 KB: [128][64] 16-bit A operand written by the compute warps
-constexpr int TCOLS = 256;
+constexpr int NSI = 8;                 // ring depth of the streamed tiles (even: a stage always serves the same group).  A stage is
+                                       // released by the block's LAST MMA but needed again by an MMA issued two blocks early, so the
+                                       // effective prefetch distance is NSI - 2 blocks; 4 stages left TMA latency exposed (~450 clk/block)
+constexpr int TCOLS = 512;
+constexpr int NTHREADS = 19 * 32;      // 16 compute warps (2 groups of 8) + TMA warp + 2 MMA-issuing warps
+constexpr int WARP_TMA = 16, WARP_MMA = 17, WARP_MMA2 = 18;
 
 struct BwdParams {
-  int Lq, Lk, tiles, H;
+  int Lq, Lk, tiles, H, nseg;
+  const void* q; int64_t ldq;
+  const void* kv; int64_t ldkv;
+  const void* dO; int64_t lddo;
   int q_col0, k_col0, v_col0, do_col0;
   const float* lse2;
   const float* delta;
@@ -65,17 +79,22 @@ __device__ __forceinline__ bool attn_drop_keep(uint32_t base, uint32_t q, uint32
   return lowbias32(base ^ (q * Lk + k)) >= thr;
 }
 
-template <int DT>
-__device__ __forceinline__ void store_row_chunk16(uint8_t* row_base, int sw, int ch0, const float (&v)[32]) {
+// 32 consecutive 16-bit elements of one global row -> 16 packed TMEM columns of this thread's lane (A-operand layout)
+__device__ __forceinline__ void park_row_half(uint32_t taddr, const void* base, int64_t row, int64_t ld, int col) {
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + row * ld + col);
+  uint32_t v[16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack2<DT>(v[q * 8 + 0], v[q * 8 + 1]);
-    u.y = pack2<DT>(v[q * 8 + 2], v[q * 8 + 3]);
-    u.z = pack2<DT>(v[q * 8 + 4], v[q * 8 + 5]);
-    u.w = pack2<DT>(v[q * 8 + 6], v[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(row_base + (((ch0 + q) ^ sw) << 4)) = u;
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = __ldg(src + i);
+    v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
   }
+  tmem_st_x16(taddr, v);
+}
+
+template <int DT>
+__device__ __forceinline__ void pack16(const float (&v)[32], uint32_t (&o)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = pack2<DT>(v[2 * i], v[2 * i + 1]);
 }
 
 // out[row][col0 + cc .. col0 + cc + 32) = (optionally inverse-rotated) acc * mul, 16-bit
@@ -115,164 +134,239 @@ __device__ __forceinline__ void store_grad_chunk(const BwdParams& p, void* out, 
   }
 }
 
+// 16-column variant: the item epilogue is spread over all 16 compute warps (4 column quarters x 4 lane quarters)
+template <int DT, bool ROPE>
+__device__ __forceinline__ void store_grad_chunk16(const BwdParams& p, void* out, int64_t ld, uint32_t taddr, int row, int rope_row,
+                                                   int col0, int cc, float mul, bool valid) {
+  uint32_t t[16];
+  tmem_ld_x16(taddr + cc, t);
+  tmem_ld_wait();
+  if (!valid) return;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(t[i]) * mul;
+  if constexpr (ROPE) {
+    if (p.rope != nullptr) {
+      const float4* t4 = reinterpret_cast<const float4*>(p.rope + (int64_t)(rope_row % p.rope_period) * 32 + (cc >> 1));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 cs = __ldg(t4 + q);
+        float a0 = v[q * 4], b0 = v[q * 4 + 1], a1 = v[q * 4 + 2], b1 = v[q * 4 + 3];
+        v[q * 4] = a0 * cs.x + b0 * cs.y;
+        v[q * 4 + 1] = -a0 * cs.y + b0 * cs.x;
+        v[q * 4 + 2] = a1 * cs.z + b1 * cs.w;
+        v[q * 4 + 3] = -a1 * cs.w + b1 * cs.z;
+      }
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + (int64_t)row * ld + col0 + cc);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint4 u;
+    u.x = pack2<DT>(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack2<DT>(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack2<DT>(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack2<DT>(v[q * 8 + 6], v[q * 8 + 7]);
+    dst[q] = u;
+  }
+}
+
 // =========================================================================================
 // dK / dV
 // =========================================================================================
-constexpr int DKDV_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + 2 * A_BYTES + 2 * 2 * BI * 4 + 128;  // stats: [2 stages][lse2 | delta][64]
+// TMEM columns: S^T x2 [0,128)  dP^T x2 [128,256)  dV [256,320)  dK [320,384)  K [384,416)  V [416,448)
+//               P^T [448,480)  dS^T [480,512)   (K, V, P^T, dS^T: 16-bit A operands, two elements per column)
+constexpr int DKDV_SMEM = 2 * NSI * I_BYTES + NSI * 2 * BI * 4 + 256;  // Q ring | dO ring | [lse2 | delta] ring | barriers
 
 template <int DT, bool GEN>
-__global__ void __launch_bounds__(320, 2)
-attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, box [128][64]
-                     const __grid_constant__ CUtensorMap tmI,   // q buffer,  box [64][64]
-                     const __grid_constant__ CUtensorMap tmdO,  // dO,        box [64][64]
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box [64][64]
+                     const __grid_constant__ CUtensorMap tmdO,  // dO,       box [64][64]
                      const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-  uint8_t* sK = smem_raw;
-  uint8_t* sV = sK + T_BYTES;
-  uint8_t* sQ = sV + T_BYTES;            // 2 stages x 8 KB
-  uint8_t* sdO = sQ + 2 * I_BYTES;       // 2 stages x 8 KB
-  uint8_t* sP = sdO + 2 * I_BYTES;       // P^T  [128 keys][64 q]
-  uint8_t* sdS = sP + A_BYTES;           // dS^T [128 keys][64 q]
-  float* sStat = reinterpret_cast<float*>(sdS + A_BYTES);  // [2 stages][2][64]: lse2 | delta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * BI);
-  uint64_t* kv_full = bars + 0;
-  uint64_t* in_full = bars + 1;   // [2]
-  uint64_t* in_free = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* pds_full = bars + 6;
-  uint64_t* acc_done = bars + 7;  // dV/dK MMAs of block j complete (also frees sP/sdS)
-  uint64_t* sdp_free = bars + 8;  // compute warps have S^T/dP^T of block j in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sQ = smem_raw;                 // NSI x 8 KB
+  uint8_t* sdO = sQ + NSI * I_BYTES;      // NSI x 8 KB
+  float* sStat = reinterpret_cast<float*>(sdO + NSI * I_BYTES);  // [NSI][lse2 | delta][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + NSI * 2 * BI);
+  uint64_t* in_full = bars;               // [NSI] TMA -> MMA, compute (statistics)
+  uint64_t* in_free = in_full + NSI;      // [NSI] MMA commit -> TMA
+  uint64_t* sdp_full = in_free + NSI;     // [2]   S^T/dP^T buffer b holds a new block
+  uint64_t* sdp_free = sdp_full + 2;      // [2]   group b has it in registers
+  uint64_t* pds_full = sdp_free + 2;      // [2]   group b has written P^T/dS^T
+  uint64_t* acc_done = pds_full + 2;      // [2]   dV/dK MMAs of a block of group b complete (P^T/dS^T free again)
+  uint64_t* kv_ready = acc_done + 2;      //       K, V of the item parked in TMEM
+  uint64_t* kv_free = kv_ready + 1;       //       last S^T/dP^T MMA of the item complete
+  uint64_t* all_done = kv_free + 1;       //       last dV/dK MMA of the item complete
+  uint64_t* epi_done = all_done + 1;      //       accumulators of the item read back
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 1);
 
   const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) TRACE(0);
-  const int tile = blockIdx.x % p.tiles;
-  const int seg = blockIdx.x / p.tiles;
-  const int head = blockIdx.y;
-  const int q_row0_seg = seg * p.Lq;
-  const int t_row0 = seg * p.Lk + tile * BT;   // this CTA's 128 keys
-  const int n_blocks = (p.Lq + BI - 1) / BI;     // 64-query blocks
+  const int n_blocks = (p.Lq + BI - 1) / BI;     // 64-query blocks per item
+  const int n_items = p.tiles * p.nseg * p.H;    // item = tile + tiles * (seg + nseg * head)
 
-  if (warp == 8 && elect_one()) {
-    tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(acc_done, 1); mbar_init(sdp_free, 256);
+  if (warp == WARP_TMA && elect_one()) {
+    tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
+    for (int i = 0; i < NSI; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&sdp_free[i], 256); mbar_init(&pds_full[i], 256); mbar_init(&acc_done[i], 1); }
+    mbar_init(kv_ready, 512); mbar_init(kv_free, 1); mbar_init(all_done, 1); mbar_init(epi_done, 512);
     fence_barrier_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
+  if (warp == WARP_MMA) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) TRACE(1);
-  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 64, tm_dV = tmem_base + 128, tm_dK = tmem_base + 192;
+  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
+  const uint32_t tm_K = tmem_base + 384, tm_V = tmem_base + 416, tm_P = tmem_base + 448, tm_dS = tmem_base + 480;
 
-  if (warp == 8) {
+  if (warp == WARP_TMA) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(kv_full, 2 * T_BYTES);
-      tma_load_2d(sK, &tmT, kv_full, p.k_col0 + head * HD, t_row0);
-      tma_load_2d(sV, &tmT, kv_full, p.v_col0 + head * HD, t_row0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
-        if (j >= 2) mbar_wait(&in_free[st], ((j >> 1) - 1) & 1, 10 + st);
-        mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES + 2 * BI * 4);
-        tma_load_2d(sQ + st * I_BYTES, &tmI, &in_full[st], p.q_col0 + head * HD, q_row0_seg + j * BI);
-        tma_load_2d(sdO + st * I_BYTES, &tmdO, &in_full[st], p.do_col0 + head * HD, q_row0_seg + j * BI);
-        // per-query statistics of this block (head-major layout: 64 consecutive floats each)
-        const int64_t soff = (int64_t)head * p.stat_stride + (int64_t)seg * p.Lq_stat + j * BI;
-        bulk_load_1d(sStat + st * (2 * BI), p.lse2 + soff, BI * 4, &in_full[st]);
-        bulk_load_1d(sStat + st * (2 * BI) + BI, p.delta + soff, BI * 4, &in_full[st]);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
+        const int q_row0_seg = seg * p.Lq;
+        for (int j = 0; j < n_blocks; ++j) {
+          const int jb = it * n_blocks + j, st = jb % NSI;
+          if (jb >= NSI) mbar_wait(&in_free[st], (jb / NSI - 1) & 1, 10);
+          mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES + 2 * BI * 4);
+          tma_load_2d(sQ + st * I_BYTES, &tmI, &in_full[st], p.q_col0 + head * HD, q_row0_seg + j * BI);
+          tma_load_2d(sdO + st * I_BYTES, &tmdO, &in_full[st], p.do_col0 + head * HD, q_row0_seg + j * BI);
+          // per-query statistics of this block (head-major layout: 64 consecutive floats each)
+          const int64_t soff = (int64_t)head * p.stat_stride + (int64_t)seg * p.Lq_stat + j * BI;
+          bulk_load_1d(sStat + st * (2 * BI), p.lse2 + soff, BI * 4, &in_full[st]);
+          bulk_load_1d(sStat + st * (2 * BI) + BI, p.delta + soff, BI * 4, &in_full[st]);
+        }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == WARP_MMA) {
+    // MMA stream 1: S^T / dP^T.  The issuing thread's scalar code (barrier polls, descriptor arithmetic) shares its
+    // scheduler with four busy compute warps; with ONE thread issuing all 16 MMAs of a block that code took ~1050 clk
+    // per block and was the kernel's critical path (profiles/r01_attn_bwd_timeline.md), hence two streams on two
+    // sub-partitions and descriptors derived from per-kernel constants by one 64-bit add.
     if (elect_one()) {
-      constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);  // A K-major, B K-major, N=64
-      constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1); // A K-major, B MN-major, N=64
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-      mbar_wait(kv_full, 0, 20);
-      TRACE(2);
-      // S^T / dP^T of block j+1 are issued as soon as the compute warps hold block j in registers
-      // (sdp_free), i.e. they overlap the exp / pack / store work of block j instead of waiting for it.
-      auto issue_sdp = [&](int j) {
-        const int st = j & 1;
-        const uint32_t q_addr = smem_u32(sQ + st * I_BYTES), do_addr = smem_u32(sdO + st * I_BYTES);
-        mbar_wait(&in_full[st], (j >> 1) & 1, 21);
-        if (j > 0) mbar_wait(sdp_free, (j - 1) & 1, 24);
-        tc_fence_after();
+      constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);  // A (TMEM) K-major, B K-major, N=64
+      constexpr uint32_t ST16 = I_BYTES >> 4;                          // one ring stage in descriptor address units
+      const uint64_t dQk = make_desc_kmajor(smem_u32(sQ)), dOk = make_desc_kmajor(smem_u32(sdO));
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int B0 = it * n_blocks;
+        mbar_wait(kv_ready, it & 1, 20);
+        // S^T / dP^T of block j go out as soon as group (j&1) holds block j-2 in registers (sdp_free), i.e. they
+        // overlap that group's exp / pack work; the other group is busy with block j-1 meanwhile.
+        for (int j = 0; j < n_blocks; ++j) {
+          const int jb = B0 + j, st = jb % NSI, b = jb & 1;
+          mbar_wait(&in_full[st], (jb / NSI) & 1, 21);
+          if (jb >= 2) mbar_wait(&sdp_free[b], ((jb >> 1) - 1) & 1, 24);
+          tc_fence_after();
+          const uint64_t q = dQk + (uint64_t)(st * ST16), o = dOk + (uint64_t)(st * ST16);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // S^T = K . Q^T
-          umma_f16_ss(tm_S, make_desc_kmajor(k_addr + k * 32), make_desc_kmajor(q_addr + k * 32), idesc_kk, k > 0);
+          for (int k = 0; k < 4; ++k)  // S^T = K . Q^T
+            umma_f16_ts(tm_S + b * 64, tm_K + k * 8, q + k * 2, idesc_kk, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // dP^T = V . dO^T
-          umma_f16_ss(tm_dP, make_desc_kmajor(v_addr + k * 32), make_desc_kmajor(do_addr + k * 32), idesc_kk, k > 0);
-        umma_commit(sdp_full);
-      };
-      issue_sdp(0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
-        const uint32_t q_addr = smem_u32(sQ + st * I_BYTES), do_addr = smem_u32(sdO + st * I_BYTES);
-        TRACE(64 + j * 16 + 8);
-        if (j + 1 < n_blocks) issue_sdp(j + 1);
-        TRACE(64 + j * 16 + 9);
-        mbar_wait(pds_full, j & 1, 22);
-        TRACE(64 + j * 16 + 10);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // dV += P^T . dO   (K = 64 queries)
-          umma_f16_ss(tm_dV, make_desc_kmajor(p_addr + k * 32), make_desc_mnmajor(do_addr + k * 2048, 8192), idesc_kmn,
-                      (j > 0 || k > 0));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // dK += dS^T . Q
-          umma_f16_ss(tm_dK, make_desc_kmajor(ds_addr + k * 32), make_desc_mnmajor(q_addr + k * 2048, 8192), idesc_kmn,
-                      (j > 0 || k > 0));
-        umma_commit(&in_free[st]);
-        umma_commit(acc_done);
-        TRACE(64 + j * 16 + 11);
+          for (int k = 0; k < 4; ++k)  // dP^T = V . dO^T
+            umma_f16_ts(tm_dP + b * 64, tm_V + k * 8, o + k * 2, idesc_kk, k > 0);
+          umma_commit(&sdp_full[b]);
+          if (j == n_blocks - 1) umma_commit(kv_free);
+          if (j < 64) TRACE(1024 + (j & 63) * 4 + 0);
+        }
       }
     }
-  } else {
+  } else if (warp == WARP_MMA2) {
+    // MMA stream 2: dV += P^T dO, dK += dS^T Q.  in_free may be signalled from here although the S^T/dP^T MMAs that
+    // read the same stage belong to stream 1: pds_full(j) is only reached after sdp_full(j), i.e. after they completed.
+    if (elect_one()) {
+      constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1); // A (TMEM) K-major, B MN-major, N=64
+      constexpr uint32_t ST16 = I_BYTES >> 4;
+      const uint64_t dQm = make_desc_mnmajor(smem_u32(sQ), 8192), dOm = make_desc_mnmajor(smem_u32(sdO), 8192);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int B0 = it * n_blocks;
+        for (int j = 0; j < n_blocks; ++j) {
+          const int jb = B0 + j, st = jb % NSI, b = jb & 1;
+          mbar_wait(&pds_full[b], (jb >> 1) & 1, 22);
+          if (j == 0 && it > 0) mbar_wait(epi_done, (it - 1) & 1, 25);  // previous item's dV/dK have been read back
+          tc_fence_after();
+          const uint64_t q = dQm + (uint64_t)(st * ST16), o = dOm + (uint64_t)(st * ST16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // dV += P^T . dO   (K = 64 queries; 16 rows = 2048 B per step)
+            umma_f16_ts(tm_dV, tm_P + k * 8, o + k * 128, idesc_kmn, (j > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // dK += dS^T . Q
+            umma_f16_ts(tm_dK, tm_dS + k * 8, q + k * 128, idesc_kmn, (j > 0 || k > 0));
+          umma_commit(&in_free[st]);
+          umma_commit(&acc_done[b]);
+          if (j == n_blocks - 1) umma_commit(all_done);
+          if (j < 64) TRACE(1024 + (j & 63) * 4 + 1);
+        }
+      }
+    }
+  } else if (warp < 16) {
+    const int g = warp >> 3;           // compute group
+    const int wi = warp & 7;
     const int r = threadIdx.x & 127;   // key row inside the tile == TMEM lane
-    const int cc = (warp >> 2) * 32;   // this warp's half of the 64 inner (query) columns
-    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int cc = (wi >> 2) * 32;     // this warp's half of the 64 inner (query) columns
+    const uint32_t lane_off = static_cast<uint32_t>((wi & 3) * 32) << 16;
     const float c = p.scale_log2;
-    uint8_t* p_row = sP + r * 128;
-    uint8_t* ds_row = sdS + r * 128;
-    const int sw = r & 7;
-    const int k_in_seg = min(tile * BT + r, p.Lk - 1);
-    bool key_masked = false;
-    const float* bias_col = nullptr;
-    uint32_t drop_base = 0;
-    if constexpr (GEN) {
-      if (p.kpm != nullptr) key_masked = __ldg(p.kpm + (int64_t)seg * p.Lk + k_in_seg) != 0;
-      if (p.bias != nullptr) bias_col = p.bias + (int64_t)(seg * p.H + head) * p.Lq * p.Lk + k_in_seg;
-      drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
-    }
-    for (int j = 0; j < n_blocks; ++j) {
-      // per-query statistics were bulk-copied next to Q/dO by the producer (visible once in_full completed)
-      const float* stat = sStat + (j & 1) * (2 * BI);
-      const int q_valid = min(BI, p.Lq - j * BI);   // queries of this block that exist
-      if (threadIdx.x == 0) TRACE(64 + j * 16 + 0);
-      mbar_wait(&in_full[j & 1], (j >> 1) & 1, 33);
-      mbar_wait(sdp_full, j & 1, 30);
-      if (threadIdx.x == 0) TRACE(64 + j * 16 + 1);
-      tc_fence_after();
-      {
+
+    // K (group 0) / V (group 1) rows of an item -> TMEM; each thread parks 32 of its row's 64 elements
+    auto park = [&](int item) {
+      const int tile = item % p.tiles, seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
+      const int64_t grow = (int64_t)seg * p.Lk + min(tile * BT + r, p.Lk - 1);
+      park_row_half((g == 0 ? tm_K : tm_V) + lane_off + (wi >> 2) * 16, p.kv, grow, p.ldkv,
+                    (g == 0 ? p.k_col0 : p.v_col0) + head * HD + (wi >> 2) * 32);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(kv_ready);
+    };
+    if ((int)blockIdx.x < n_items) park(blockIdx.x);
+
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int tile = item % p.tiles, seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
+      const int B0 = it * n_blocks;
+      const int t_row0 = seg * p.Lk + tile * BT;   // this item's 128 keys
+      const int k_in_seg = min(tile * BT + r, p.Lk - 1);
+      bool key_masked = false;
+      const float* bias_col = nullptr;
+      uint32_t drop_base = 0;
+      if constexpr (GEN) {
+        if (p.kpm != nullptr) key_masked = __ldg(p.kpm + (int64_t)seg * p.Lk + k_in_seg) != 0;
+        if (p.bias != nullptr) bias_col = p.bias + (int64_t)(seg * p.H + head) * p.Lq * p.Lk + k_in_seg;
+        drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
+      }
+      for (int j = (B0 + g) & 1; j < n_blocks; j += 2) {   // blocks whose running index has parity g
+        const int jb = B0 + j, st = jb % NSI;
+        const float* stat = sStat + st * (2 * BI);
+        const int q_valid = min(BI, p.Lq - j * BI);   // queries of this block that exist
+        const bool tr = (threadIdx.x == 0 || threadIdx.x == 256) && j < 64;
+        if (tr) TRACE(64 + j * 8 + 0);
+        mbar_wait(&in_full[st], (jb / NSI) & 1, 33);     // statistics landed next to Q / dO
+        mbar_wait(&sdp_full[g], (jb >> 1) & 1, 30);
+        tc_fence_after();
+        if (tr) TRACE(64 + j * 8 + 1);
         uint32_t s[32], d[32];
-        tmem_ld_x32(tm_S + lane_off + cc, s);
-        tmem_ld_x32(tm_dP + lane_off + cc, d);
+        tmem_ld_x32(tm_S + g * 64 + lane_off + cc, s);
+        tmem_ld_x32(tm_dP + g * 64 + lane_off + cc, d);
         tmem_ld_wait();
-        if (threadIdx.x == 0) TRACE(64 + j * 16 + 2);
         tc_fence_before();
-        mbar_arrive(sdp_free);  // TMEM S^T/dP^T may be overwritten by block j+1
+        mbar_arrive(&sdp_free[g]);  // S^T/dP^T buffer g may be overwritten by block j+2
+        if (tr) TRACE(64 + j * 8 + 2);
         float pv[32], dsv[32];
         if (!GEN && q_valid == BI) {
+          const float4* l4 = reinterpret_cast<const float4*>(stat + cc);
+          const float4* d4 = reinterpret_cast<const float4*>(stat + BI + cc);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float pe = ex2_approx(__uint_as_float(s[i]) * c - stat[cc + i]);
-            pv[i] = pe;
-            dsv[i] = pe * (__uint_as_float(d[i]) - stat[BI + cc + i]);
+          for (int q = 0; q < 8; ++q) {
+            const float4 l = l4[q], dl = d4[q];
+            const float lv[4] = {l.x, l.y, l.z, l.w}, dv[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = q * 4 + e;
+              const float pe = ex2_approx(fmaf(__uint_as_float(s[i]), c, -lv[e]));
+              pv[i] = pe;
+              dsv[i] = pe * (__uint_as_float(d[i]) - dv[e]);
+            }
           }
         } else {
 #pragma unroll
@@ -293,165 +387,208 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmT,   // kv buffer, bo
             dsv[i] = dead ? 0.f : pe * (dp * keep_scale - stat[BI + cc + i]);
           }
         }
-        if (threadIdx.x == 0) TRACE(64 + j * 16 + 3);
-        if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);
-        if (threadIdx.x == 0) TRACE(64 + j * 16 + 4);  // previous dV/dK MMAs finished reading sP/sdS
-        store_row_chunk16<DT>(p_row, sw, cc >> 3, pv);
-        store_row_chunk16<DT>(ds_row, sw, cc >> 3, dsv);
+        uint32_t pp[16], dd[16];
+        pack16<DT>(pv, pp);
+        pack16<DT>(dsv, dd);
+        if (tr) TRACE(64 + j * 8 + 3);
+        // P^T / dS^T were last read by the dV/dK MMAs of the previous block (the other group's)
+        if (jb > 0) mbar_wait(&acc_done[g ^ 1], ((jb - 1) >> 1) & 1, 31);
+        tc_fence_after();
+        if (tr) TRACE(64 + j * 8 + 4);
+        tmem_st_x16(tm_P + lane_off + (cc >> 1), pp);
+        tmem_st_x16(tm_dS + lane_off + (cc >> 1), dd);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&pds_full[g]);
+        if (tr) TRACE(64 + j * 8 + 5);
       }
+      // park the next item's K / V before this item's epilogue so that its first MMAs overlap the epilogue
+      const int next = item + gridDim.x;
+      if (next < n_items) {
+        mbar_wait(kv_free, it & 1, 34);
+        tc_fence_after();
+        park(next);
+      }
+      mbar_wait(all_done, it & 1, 32);
+      tc_fence_after();
+      const int row = t_row0 + r;
+      const bool valid = (tile * BT + r) < p.Lk;
+      const int ec = (wi >> 2) * 32 + g * 16;   // this warp's 16-column quarter of both accumulators
+      store_grad_chunk16<DT, false>(p, p.dkv, p.lddkv, tm_dV + lane_off, row, row, p.dv_col0 + head * HD, ec, 1.f, valid);
+      store_grad_chunk16<DT, true>(p, p.dkv, p.lddkv, tm_dK + lane_off, row, row, p.dk_col0 + head * HD, ec, p.scale, valid);
       tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(pds_full);
-      if (threadIdx.x == 0) TRACE(64 + j * 16 + 5);
+      mbar_arrive(epi_done);
     }
-    mbar_wait(acc_done, (n_blocks - 1) & 1, 32);
-    if (threadIdx.x == 0) TRACE(3);
-    tc_fence_after();
-    const int row = t_row0 + r;
-    const bool valid = (tile * BT + r) < p.Lk;
-    store_grad_chunk<DT, false>(p, p.dkv, p.lddkv, tm_dV + lane_off, row, row, p.dv_col0 + head * HD, cc, 1.f, valid);
-    store_grad_chunk<DT, true>(p, p.dkv, p.lddkv, tm_dK + lane_off, row, row, p.dk_col0 + head * HD, cc, p.scale, valid);
-    if (threadIdx.x == 0) TRACE(4);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, TCOLS);
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, TCOLS);
 }
 
 // =========================================================================================
 // dQ
 // =========================================================================================
-constexpr int DQ_SMEM = 2 * T_BYTES + 2 * (2 * I_BYTES) + A_BYTES + 128;
+// TMEM columns: S x2 [0,128)  dP x2 [128,256)  dQ [256,320)  Q [320,352)  dO [352,384)  dS x2 [384,448)
+constexpr int DQ_SMEM = 2 * NSI * I_BYTES + 256;   // K ring | V ring | barriers
 
 template <int DT, bool GEN>
-__global__ void __launch_bounds__(320, 2)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // q buffer,  box [128][64]
-                   const __grid_constant__ CUtensorMap tmI,   // kv buffer, box [64][64]
-                   const __grid_constant__ CUtensorMap tmdO,  // dO,        box [128][64]
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box [64][64]
                    const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem_raw;
-  uint8_t* sdO = sQ + T_BYTES;
-  uint8_t* sK = sdO + T_BYTES;           // 2 stages x 8 KB
-  uint8_t* sV = sK + 2 * I_BYTES;        // 2 stages x 8 KB
-  uint8_t* sdS = sV + 2 * I_BYTES;       // dS [128 q][64 keys]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + A_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* in_full = bars + 1;   // [2]
-  uint64_t* in_free = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* ds_full = bars + 6;
-  uint64_t* acc_done = bars + 7;
-  uint64_t* sdp_free = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sK = smem_raw;                // NSI x 8 KB
+  uint8_t* sV = sK + NSI * I_BYTES;      // NSI x 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSI * I_BYTES);
+  uint64_t* in_full = bars;              // [NSI]
+  uint64_t* in_free = in_full + NSI;     // [NSI]
+  uint64_t* sdp_full = in_free + NSI;    // [2]
+  uint64_t* sdp_free = sdp_full + 2;     // [2]
+  uint64_t* ds_full = sdp_free + 2;      // [2]
+  uint64_t* dq_done = ds_full + 2;       // [2] dQ MMA of a block of group b complete (dS buffer b free again)
+  uint64_t* qdo_ready = dq_done + 2;
+  uint64_t* qdo_free = qdo_ready + 1;
+  uint64_t* all_done = qdo_free + 1;
+  uint64_t* epi_done = all_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 1);
 
   const int warp = threadIdx.x >> 5;
-  const int tile = blockIdx.x % p.tiles;
-  const int seg = blockIdx.x / p.tiles;
-  const int head = blockIdx.y;
-  const int kv_row0_seg = seg * p.Lk;
-  const int t_row0 = seg * p.Lq + tile * BT;   // this CTA's 128 queries
-  const int n_blocks = (p.Lk + BI - 1) / BI;     // 64-key blocks
+  const int n_blocks = (p.Lk + BI - 1) / BI;     // 64-key blocks per item
+  const int n_items = p.tiles * p.nseg * p.H;
 
-  if (warp == 8 && elect_one()) {
-    tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmI); tma_prefetch_desc(&tmdO);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(ds_full, 256); mbar_init(acc_done, 1); mbar_init(sdp_free, 256);
+  if (warp == WARP_TMA && elect_one()) {
+    tma_prefetch_desc(&tmI);
+    for (int i = 0; i < NSI; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_free[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&sdp_free[i], 256); mbar_init(&ds_full[i], 256); mbar_init(&dq_done[i], 1); }
+    mbar_init(qdo_ready, 512); mbar_init(qdo_free, 1); mbar_init(all_done, 1); mbar_init(epi_done, 512);
     fence_barrier_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
+  if (warp == WARP_MMA) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 64, tm_dQ = tmem_base + 128;
+  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dQ = tmem_base + 256;
+  const uint32_t tm_Q = tmem_base + 320, tm_dO = tmem_base + 352, tm_dS = tmem_base + 384;
 
-  if (warp == 8) {
+  if (warp == WARP_TMA) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, 2 * T_BYTES);
-      tma_load_2d(sQ, &tmT, q_full, p.q_col0 + head * HD, t_row0);
-      tma_load_2d(sdO, &tmdO, q_full, p.do_col0 + head * HD, t_row0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
-        if (j >= 2) mbar_wait(&in_free[st], ((j >> 1) - 1) & 1, 10 + st);
-        mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES);
-        tma_load_2d(sK + st * I_BYTES, &tmI, &in_full[st], p.k_col0 + head * HD, kv_row0_seg + j * BI);
-        tma_load_2d(sV + st * I_BYTES, &tmI, &in_full[st], p.v_col0 + head * HD, kv_row0_seg + j * BI);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
+        const int kv_row0_seg = seg * p.Lk;
+        for (int j = 0; j < n_blocks; ++j) {
+          const int jb = it * n_blocks + j, st = jb % NSI;
+          if (jb >= NSI) mbar_wait(&in_free[st], (jb / NSI - 1) & 1, 10);
+          mbar_arrive_expect_tx(&in_full[st], 2 * I_BYTES);
+          tma_load_2d(sK + st * I_BYTES, &tmI, &in_full[st], p.k_col0 + head * HD, kv_row0_seg + j * BI);
+          tma_load_2d(sV + st * I_BYTES, &tmI, &in_full[st], p.v_col0 + head * HD, kv_row0_seg + j * BI);
+        }
       }
     }
-  } else if (warp == 9) {
-    if (elect_one()) {
+  } else if (warp == WARP_MMA) {
+    if (elect_one()) {   // MMA stream 1: S, dP (see attn_bwd_dkdv_kernel for the two-stream split)
       constexpr uint32_t idesc_kk = make_idesc_f16(BT, BI, DT, 0, 0);
-      constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
-      mbar_wait(q_full, 0, 20);
-      auto issue_sdp = [&](int j) {
-        const int st = j & 1;
-        const uint32_t k_addr = smem_u32(sK + st * I_BYTES), v_addr = smem_u32(sV + st * I_BYTES);
-        mbar_wait(&in_full[st], (j >> 1) & 1, 21);
-        if (j > 0) mbar_wait(sdp_free, (j - 1) & 1, 24);
-        tc_fence_after();
+      constexpr uint32_t ST16 = I_BYTES >> 4;
+      const uint64_t dKk = make_desc_kmajor(smem_u32(sK)), dVk = make_desc_kmajor(smem_u32(sV));
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int B0 = it * n_blocks;
+        mbar_wait(qdo_ready, it & 1, 20);
+        for (int j = 0; j < n_blocks; ++j) {
+          const int jb = B0 + j, st = jb % NSI, b = jb & 1;
+          mbar_wait(&in_full[st], (jb / NSI) & 1, 21);
+          if (jb >= 2) mbar_wait(&sdp_free[b], ((jb >> 1) - 1) & 1, 24);
+          tc_fence_after();
+          const uint64_t kd = dKk + (uint64_t)(st * ST16), vd = dVk + (uint64_t)(st * ST16);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // S = Q . K^T
-          umma_f16_ss(tm_S, make_desc_kmajor(q_addr + k * 32), make_desc_kmajor(k_addr + k * 32), idesc_kk, k > 0);
+          for (int k = 0; k < 4; ++k)  // S = Q . K^T
+            umma_f16_ts(tm_S + b * 64, tm_Q + k * 8, kd + k * 2, idesc_kk, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // dP = dO . V^T
-          umma_f16_ss(tm_dP, make_desc_kmajor(do_addr + k * 32), make_desc_kmajor(v_addr + k * 32), idesc_kk, k > 0);
-        umma_commit(sdp_full);
-      };
-      issue_sdp(0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
-        const uint32_t k_addr = smem_u32(sK + st * I_BYTES);
-        if (j + 1 < n_blocks) issue_sdp(j + 1);
-        mbar_wait(ds_full, j & 1, 22);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // dQ += dS . K   (K = 64 keys, K tile as MN-major B)
-          umma_f16_ss(tm_dQ, make_desc_kmajor(ds_addr + k * 32), make_desc_mnmajor(k_addr + k * 2048, 8192), idesc_kmn,
-                      (j > 0 || k > 0));
-        umma_commit(&in_free[st]);
-        umma_commit(acc_done);
+          for (int k = 0; k < 4; ++k)  // dP = dO . V^T
+            umma_f16_ts(tm_dP + b * 64, tm_dO + k * 8, vd + k * 2, idesc_kk, k > 0);
+          umma_commit(&sdp_full[b]);
+          if (j == n_blocks - 1) umma_commit(qdo_free);
+        }
       }
     }
-  } else {
-    const int r = threadIdx.x & 127;   // query row inside the tile == TMEM lane
-    const int cc = (warp >> 2) * 32;   // this warp's half of the 64 inner (key) columns
-    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const float c = p.scale_log2;
-    const int row = t_row0 + r;
-    const int q_in_seg = min(tile * BT + r, p.Lq - 1);
-    const int64_t sidx = (int64_t)head * p.stat_stride + (int64_t)seg * p.Lq_stat + q_in_seg;   // head-major statistics
-    const float lse = __ldg(p.lse2 + sidx);
-    const float dlt = __ldg(p.delta + sidx);
-    uint8_t* ds_row = sdS + r * 128;
-    const int sw = r & 7;
-    const float* bias_row = nullptr;
-    const uint8_t* kpm_row = nullptr;
-    uint32_t drop_base = 0;
-    if constexpr (GEN) {
-      if (p.bias != nullptr) bias_row = p.bias + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * p.Lk;
-      if (p.kpm != nullptr) kpm_row = p.kpm + (int64_t)seg * p.Lk;
-      drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
+  } else if (warp == WARP_MMA2) {
+    if (elect_one()) {   // MMA stream 2: dQ += dS . K
+      constexpr uint32_t idesc_kmn = make_idesc_f16(BT, HD, DT, 0, 1);
+      constexpr uint32_t ST16 = I_BYTES >> 4;
+      const uint64_t dKm = make_desc_mnmajor(smem_u32(sK), 8192);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int B0 = it * n_blocks;
+        for (int j = 0; j < n_blocks; ++j) {
+          const int jb = B0 + j, st = jb % NSI, b = jb & 1;
+          mbar_wait(&ds_full[b], (jb >> 1) & 1, 22);
+          if (j == 0 && it > 0) mbar_wait(epi_done, (it - 1) & 1, 25);
+          tc_fence_after();
+          const uint64_t kd = dKm + (uint64_t)(st * ST16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // dQ += dS . K   (K = 64 keys, K tile as MN-major B)
+            umma_f16_ts(tm_dQ, tm_dS + b * 32 + k * 8, kd + k * 128, idesc_kmn, (j > 0 || k > 0));
+          umma_commit(&in_free[st]);
+          umma_commit(&dq_done[b]);
+          if (j == n_blocks - 1) umma_commit(all_done);
+        }
+      }
     }
-    for (int j = 0; j < n_blocks; ++j) {
-      const int k_valid = min(BI, p.Lk - j * BI);
-      mbar_wait(sdp_full, j & 1, 30);
-      tc_fence_after();
-      {
+  } else if (warp < 16) {
+    const int g = warp >> 3;
+    const int wi = warp & 7;
+    const int r = threadIdx.x & 127;   // query row inside the tile == TMEM lane
+    const int cc = (wi >> 2) * 32;     // this warp's half of the 64 inner (key) columns
+    const uint32_t lane_off = static_cast<uint32_t>((wi & 3) * 32) << 16;
+    const float c = p.scale_log2;
+
+    // Q (group 0) / dO (group 1) rows of an item -> TMEM
+    auto park = [&](int item) {
+      const int tile = item % p.tiles, seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
+      const int64_t grow = (int64_t)seg * p.Lq + min(tile * BT + r, p.Lq - 1);
+      if (g == 0) park_row_half(tm_Q + lane_off + (wi >> 2) * 16, p.q, grow, p.ldq, p.q_col0 + head * HD + (wi >> 2) * 32);
+      else        park_row_half(tm_dO + lane_off + (wi >> 2) * 16, p.dO, grow, p.lddo, p.do_col0 + head * HD + (wi >> 2) * 32);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(qdo_ready);
+    };
+    if ((int)blockIdx.x < n_items) park(blockIdx.x);
+
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int tile = item % p.tiles, seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
+      const int B0 = it * n_blocks;
+      const int t_row0 = seg * p.Lq + tile * BT;   // this item's 128 queries
+      const int row = t_row0 + r;
+      const int q_in_seg = min(tile * BT + r, p.Lq - 1);
+      const int64_t sidx = (int64_t)head * p.stat_stride + (int64_t)seg * p.Lq_stat + q_in_seg;   // head-major statistics
+      const float lse = __ldg(p.lse2 + sidx);
+      const float dlt = __ldg(p.delta + sidx);
+      const float* bias_row = nullptr;
+      const uint8_t* kpm_row = nullptr;
+      uint32_t drop_base = 0;
+      if constexpr (GEN) {
+        if (p.bias != nullptr) bias_row = p.bias + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * p.Lk;
+        if (p.kpm != nullptr) kpm_row = p.kpm + (int64_t)seg * p.Lk;
+        drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
+      }
+      for (int j = (B0 + g) & 1; j < n_blocks; j += 2) {
+        const int jb = B0 + j;
+        const int k_valid = min(BI, p.Lk - j * BI);
+        mbar_wait(&sdp_full[g], (jb >> 1) & 1, 30);
+        tc_fence_after();
         uint32_t s[32], d[32];
-        tmem_ld_x32(tm_S + lane_off + cc, s);
-        tmem_ld_x32(tm_dP + lane_off + cc, d);
+        tmem_ld_x32(tm_S + g * 64 + lane_off + cc, s);
+        tmem_ld_x32(tm_dP + g * 64 + lane_off + cc, d);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(sdp_free);
+        mbar_arrive(&sdp_free[g]);
         float dsv[32];
         if (!GEN && k_valid == BI) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float pe = ex2_approx(__uint_as_float(s[i]) * c - lse);
+            const float pe = ex2_approx(fmaf(__uint_as_float(s[i]), c, -lse));
             dsv[i] = pe * (__uint_as_float(d[i]) - dlt);
           }
         } else {
@@ -471,21 +608,33 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmT,   // q buffer,  box 
             dsv[i] = pe * (dp - dlt);
           }
         }
-        if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 31);
-        store_row_chunk16<DT>(ds_row, sw, cc >> 3, dsv);
+        uint32_t dd[16];
+        pack16<DT>(dsv, dd);
+        // dS buffer g was last read by the dQ MMA of this group's previous block
+        if (jb >= 2) mbar_wait(&dq_done[g], ((jb >> 1) - 1) & 1, 31);
+        tc_fence_after();
+        tmem_st_x16(tm_dS + g * 32 + lane_off + (cc >> 1), dd);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&ds_full[g]);
       }
+      const int next = item + gridDim.x;
+      if (next < n_items) {
+        mbar_wait(qdo_free, it & 1, 34);
+        tc_fence_after();
+        park(next);
+      }
+      mbar_wait(all_done, it & 1, 32);
+      tc_fence_after();
+      const bool valid = (tile * BT + r) < p.Lq;
+      store_grad_chunk16<DT, true>(p, p.dq, p.lddq, tm_dQ + lane_off, row, row, p.dq_col0 + head * HD, (wi >> 2) * 32 + g * 16, p.scale, valid);
       tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(ds_full);
+      mbar_arrive(epi_done);
     }
-    mbar_wait(acc_done, (n_blocks - 1) & 1, 32);
-    tc_fence_after();
-    const bool valid = (tile * BT + r) < p.Lq;
-    store_grad_chunk<DT, true>(p, p.dq, p.lddq, tm_dQ + lane_off, row, row, p.dq_col0 + head * HD, cc, p.scale, valid);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, TCOLS);
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, TCOLS);
 }
 
 template <typename K>
@@ -498,17 +647,21 @@ static int set_smem_once(K kern, int bytes, bool& done) {
 }
 
 template <int DT, bool GEN>
-static int launch_bwd(const AttnArgs& a, const BwdParams& pk, const BwdParams& pq, const CUtensorMap& tmKV128, const CUtensorMap& tmQ64,
-                      const CUtensorMap& tmdO64, const CUtensorMap& tmQ128, const CUtensorMap& tmKV64, const CUtensorMap& tmdO128,
-                      cudaStream_t stream) {
+static int launch_bwd(const AttnArgs& a, const BwdParams& pk, const BwdParams& pq, const CUtensorMap& tmQ64, const CUtensorMap& tmdO64,
+                      const CUtensorMap& tmKV64, cudaStream_t stream) {
   static bool s1 = false, s2 = false;
   int rc = set_smem_once(attn_bwd_dkdv_kernel<DT, GEN>, DKDV_SMEM, s1);
   if (rc) return rc;
   rc = set_smem_once(attn_bwd_dq_kernel<DT, GEN>, DQ_SMEM, s2);
   if (rc) return rc;
-  attn_bwd_dkdv_kernel<DT, GEN><<<dim3(pk.tiles * a.nseg, a.heads), 320, DKDV_SMEM, stream>>>(tmKV128, tmQ64, tmdO64, pk);
+  // persistent: one CTA per SM walks the item list (SAM3B_ATTN_PERSIST=0: one CTA per item, for debugging)
+  static const bool persist = [] { const char* e = getenv("SAM3B_ATTN_PERSIST"); return !(e && e[0] == '0'); }();
+  const int items_k = pk.tiles * a.nseg * a.heads, items_q = pq.tiles * a.nseg * a.heads;
+  const int grid_k = persist ? std::min(items_k, num_sms()) : items_k;
+  const int grid_q = persist ? std::min(items_q, num_sms()) : items_q;
+  attn_bwd_dkdv_kernel<DT, GEN><<<grid_k, NTHREADS, DKDV_SMEM, stream>>>(tmQ64, tmdO64, pk);
   SAM3B_LAUNCHED();
-  attn_bwd_dq_kernel<DT, GEN><<<dim3(pq.tiles * a.nseg, a.heads), 320, DQ_SMEM, stream>>>(tmQ128, tmKV64, tmdO128, pq);
+  attn_bwd_dq_kernel<DT, GEN><<<grid_q, NTHREADS, DQ_SMEM, stream>>>(tmKV64, pq);
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -522,17 +675,17 @@ int attn_bwd_launch(const AttnArgs& a, cudaStream_t stream) {
                 "attention bwd: leading dimensions must be multiples of 8");
   SAM3B_REQUIRE(a.drop_p >= 0.f && a.drop_p < 1.f, "attention bwd: dropout p");
   const uint64_t Mq = (uint64_t)a.nseg * a.Lq, Mk = (uint64_t)a.nseg * a.Lk;
-  CUtensorMap tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128;
+  SAM3B_REQUIRE(a.q_col0 % 8 == 0 && a.k_col0 % 8 == 0 && a.v_col0 % 8 == 0 && a.do_col0 % 8 == 0,
+                "attention bwd: column offsets must be multiples of 8");
+  CUtensorMap tmQ64, tmdO64, tmKV64;
   int rc;
-  if ((rc = make_tmap_2d(&tmKV128, a.kv, Mk, a.kv_cols, a.ldkv, BT, HD))) return rc;
   if ((rc = make_tmap_2d(&tmKV64, a.kv, Mk, a.kv_cols, a.ldkv, BI, HD))) return rc;
-  if ((rc = make_tmap_2d(&tmQ128, a.q, Mq, a.q_cols, a.ldq, BT, HD))) return rc;
   if ((rc = make_tmap_2d(&tmQ64, a.q, Mq, a.q_cols, a.ldq, BI, HD))) return rc;
   const int do_cols = a.do_col0 + a.heads * HD;
   if ((rc = make_tmap_2d(&tmdO64, a.dO, Mq, do_cols, a.lddo, BI, HD))) return rc;
-  if ((rc = make_tmap_2d(&tmdO128, a.dO, Mq, do_cols, a.lddo, BT, HD))) return rc;
   BwdParams p{};
-  p.Lq = a.Lq; p.Lk = a.Lk; p.H = a.heads;
+  p.Lq = a.Lq; p.Lk = a.Lk; p.H = a.heads; p.nseg = a.nseg;
+  p.q = a.q; p.ldq = a.ldq; p.kv = a.kv; p.ldkv = a.ldkv; p.dO = a.dO; p.lddo = a.lddo;
   p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0; p.do_col0 = a.do_col0;
   p.lse2 = a.lse2; p.delta = a.delta; p.Lq_stat = attn_lq_stat(a.Lq); p.stat_stride = (int64_t)a.nseg * p.Lq_stat;
   p.dq = a.dq; p.lddq = a.lddq; p.dq_col0 = a.dq_col0;
@@ -546,10 +699,10 @@ int attn_bwd_launch(const AttnArgs& a, cudaStream_t stream) {
   pq.tiles = (a.Lq + BT - 1) / BT;
   const bool gen = a.bias != nullptr || a.kpm != nullptr || a.drop_p > 0.f;
   if (gen)
-    return a.dtype == 0 ? launch_bwd<0, true>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream)
-                        : launch_bwd<1, true>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream);
-  return a.dtype == 0 ? launch_bwd<0, false>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream)
-                      : launch_bwd<1, false>(a, pk, pq, tmKV128, tmQ64, tmdO64, tmQ128, tmKV64, tmdO128, stream);
+    return a.dtype == 0 ? launch_bwd<0, true>(a, pk, pq, tmQ64, tmdO64, tmKV64, stream)
+                        : launch_bwd<1, true>(a, pk, pq, tmQ64, tmdO64, tmKV64, stream);
+  return a.dtype == 0 ? launch_bwd<0, false>(a, pk, pq, tmQ64, tmdO64, tmKV64, stream)
+                      : launch_bwd<1, false>(a, pk, pq, tmQ64, tmdO64, tmKV64, stream);
 }
 
 #ifdef SAM3B_TRACE

@@ -29,6 +29,14 @@
 
 namespace sam3b {
 
+#ifdef SAM3B_TRACE
+// Debug timeline (tools/attn_trace.py fwd): one chosen CTA stamps clock64() at its pipeline events.
+__device__ unsigned long long g_attn_trace_fwd[4096];
+#define TRACE(slot) do { if (blockIdx.x == 200 && blockIdx.y == 3 && (slot) < 4096) g_attn_trace_fwd[(slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int HD = 64;
@@ -142,6 +150,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
           umma_f16_ts(tmem_base + sb * BKV, tmem_Q + k * 8, make_desc_kmajor(k_addr + k * 32), idesc_s, k > 0);
         umma_commit(&s_full[sb]);
         umma_commit(&k_free[st]);
+        if (j < 96) TRACE(1024 + j * 4 + 0);
       };
       mbar_wait(q_ready, 0, 20);
       tc_fence_after();
@@ -161,6 +170,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
                       (j > 0 || k > 0));
         umma_commit(&pv_done[sb]);
         umma_commit(&v_free[st]);
+        if (j < 96) TRACE(1024 + j * 4 + 1);
       }
     }
   } else {
@@ -199,8 +209,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
     for (int j = 0; j < n_blocks; ++j) {
       const int st = j & 1;
       const int kv_valid = min(BKV, p.Lk - j * BKV);
+      const bool tr = threadIdx.x == 0 && j < 96;
+      if (tr) TRACE(64 + j * 8 + 0);
       mbar_wait(&s_full[st], (j >> 1) & 1, 30);
       tc_fence_after();
+      if (tr) TRACE(64 + j * 8 + 1);
       uint32_t s[BKV];
       {
         uint32_t a[32], b[32];
@@ -230,6 +243,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
       // full blocks (every block when Lk % 64 == 0) take the predicate-free path: the per-element ISETP/FSEL
       // of the tail mask were 27 % of this kernel's issued instructions (profiles/r01_ncu_attn_fwd.txt)
       const bool full = kv_valid == BKV;
+      if (tr) TRACE(64 + j * 8 + 2);
       float m_blk = -INFINITY;
       if (full) {
         // 8 independent max chains (a single 64-deep FMNMX dependency chain costs ~300 cycles per block)
@@ -269,6 +283,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
       }
       // P_j goes over the S_j columns: s_full(j) (a commit) already implies that P.V of block j-2, the last
       // reader of this buffer, has completed.
+      if (tr) TRACE(64 + j * 8 + 3);
       const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_eff;  // all keys masked so far: exp2(-inf - 0) = 0
       uint32_t pk[32];
       float l_part[4] = {0.f, 0.f, 0.f, 0.f};
@@ -305,11 +320,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
         l_part[q & 3] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
         pk[4 * q] = u.x; pk[4 * q + 1] = u.y; pk[4 * q + 2] = u.z; pk[4 * q + 3] = u.w;
       }
+      if (tr) TRACE(64 + j * 8 + 4);
       tmem_st_x32(tmem_base + lane_off + st * BKV, pk);
       tmem_st_wait();
       l_run += (l_part[0] + l_part[1]) + (l_part[2] + l_part[3]);
       tc_fence_before();         // our tcgen05.ld/st are ordered before the MMA warp's next tcgen05 ops
       mbar_arrive(&p_full[st]);
+      if (tr) TRACE(64 + j * 8 + 5);
     }
     mbar_wait(&pv_done[(n_blocks - 1) & 1], ((n_blocks - 1) >> 1) & 1, 33);
     tc_fence_after();
@@ -382,5 +399,12 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t stream) {
   if (gen) return a.dtype == 0 ? launch_fwd<0, true>(tmKV, p, grid, stream) : launch_fwd<1, true>(tmKV, p, grid, stream);
   return a.dtype == 0 ? launch_fwd<0, false>(tmKV, p, grid, stream) : launch_fwd<1, false>(tmKV, p, grid, stream);
 }
+
+#ifdef SAM3B_TRACE
+int attn_trace_read_fwd(unsigned long long* host, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, g_attn_trace_fwd, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 }  // namespace sam3b

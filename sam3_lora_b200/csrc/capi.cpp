@@ -9,7 +9,7 @@
 #include "loss.cuh"
 
 #ifdef SAM3B_TRACE
-namespace sam3b { int attn_trace_read(unsigned long long*, int); int attn_trace_clear(); }
+namespace sam3b { int attn_trace_read(unsigned long long*, int); int attn_trace_clear(); int attn_trace_read_fwd(unsigned long long*, int); }
 #endif
 
 using namespace sam3b;
@@ -200,6 +200,7 @@ int sam3b_focal_loss_bwd(const float* x, const float* y, int64_t n, float alpha,
 #ifdef SAM3B_TRACE
 int sam3b_debug_trace_read(unsigned long long* host, int n) { return attn_trace_read(host, n); }
 int sam3b_debug_trace_clear(void) { return attn_trace_clear(); }
+int sam3b_debug_trace_read_fwd(unsigned long long* host, int n) { return attn_trace_read_fwd(host, n); }
 #endif
 
 }  // extern "C"

@@ -35,6 +35,26 @@ def main():
     tab[..., 0] = 1.0
     L.attention_fwd(qkv, Ls, D, heads, O, lse2)
     lib = L.load()
+    torch.cuda.synchronize()
+    # ---- forward timeline (CTA x=200, head 3): softmax thread 0 and the MMA thread ----
+    nbf = (Ls + 63) // 64
+    fb = (C.c_ulonglong * 4096)()
+    lib.sam3b_debug_trace_read_fwd.argtypes = [C.c_void_p, C.c_int]
+    lib.sam3b_debug_trace_read_fwd(fb, 4096)
+    ft = list(fb)
+    f0 = ft[64]
+    print(json.dumps({"case": f"fwd_{Ls}_{segs}_{heads}", "blocks": nbf}))
+    frows = []
+    for j in range(min(nbf, 96)):
+        e = ft[64 + j * 8:64 + j * 8 + 8]
+        m = ft[1024 + j * 4:1024 + j * 4 + 4]
+        frows.append({"j": j, "c_start": e[0] - f0, "c_wait_s": e[1] - e[0], "c_ld": e[2] - e[1], "c_max": e[3] - e[2], "c_exp_pack": e[4] - e[3],
+                      "c_st_arrive": e[5] - e[4], "m_s_issued": m[0] - f0, "m_pv_issued": m[1] - f0})
+    fshow = frows if len(frows) <= 12 else frows[:3] + frows[len(frows) // 2:len(frows) // 2 + 3] + frows[-2:]
+    for r in fshow:
+        print(json.dumps(r))
+    if len(frows) > 4:
+        print(json.dumps({"fwd_steady_clk_per_block": (frows[-1]["c_start"] - frows[1]["c_start"]) / (len(frows) - 2)}))
     lib.sam3b_debug_trace_read.argtypes = [C.c_void_p, C.c_int]
     for _ in range(2):
         L.attention_bwd(qkv, Ls, D, heads, O, lse2, dO, delta, dqkv, tab, Ls)
@@ -47,24 +67,21 @@ def main():
     lib.sam3b_debug_trace_read(buf, n)
     t = list(buf)
     nb = (Ls + 63) // 64
-    t0 = t[0]
-    hdr = {"setup_done": t[1] - t0, "kv_ready(mma)": t[2] - t0, "last_acc_done": t[3] - t0, "epilogue_end": t[4] - t0}
-    print(json.dumps({"case": f"dkdv_{Ls}_{segs}_{heads}", "blocks": nb, "header_clk": hdr}))
+    # slots (csrc/attn_bwd.cu): compute thread 0 / 256 (group 0 / 1): 64 + j*8 + {0 start, 1 S^T/dP^T ready, 2 in registers,
+    # 3 math+pack done, 4 P^T/dS^T buffer free, 5 stored + signalled}; MMA thread: 1024 + j*4 + {0 S^T/dP^T(j) issued, 1 dV/dK(j) issued}
+    t0 = min(x for x in t[64:64 + 8 * min(nb, 64)] if x) if any(t[64:64 + 8 * min(nb, 64)]) else 0
+    print(json.dumps({"case": f"dkdv_{Ls}_{segs}_{heads}", "blocks": nb, "note": "first work item of CTA 70; clocks relative to its first stamp"}))
     rows = []
-    for j in range(nb):
-        b = 64 + j * 16
-        e = t[b:b + 16]
-        rows.append({
-            "j": j,
-            "c_start": e[0] - t0,
-            "c_wait_sdp": e[1] - e[0], "c_ld": e[2] - e[1], "c_math": e[3] - e[2], "c_wait_acc": e[4] - e[3], "c_store": e[5] - e[4],
-            "m_start": e[8] - t0, "m_issue_sdp(wait+issue)": e[9] - e[8], "m_wait_pds": e[10] - e[9], "m_issue_acc": e[11] - e[10],
-        })
-    show = rows if nb <= 12 else rows[:4] + rows[nb // 2:nb // 2 + 3] + rows[-3:]
+    for j in range(min(nb, 64)):
+        e = t[64 + j * 8:64 + j * 8 + 8]
+        m = t[1024 + j * 4:1024 + j * 4 + 4]
+        rows.append({"j": j, "grp": j & 1, "c_start": e[0] - t0, "c_wait_sdp": e[1] - e[0], "c_ld": e[2] - e[1], "c_math": e[3] - e[2],
+                     "c_wait_acc": e[4] - e[3], "c_store": e[5] - e[4], "m_sdp_issued": m[0] - t0, "m_dvdk_issued": m[1] - t0})
+    show = rows if len(rows) <= 12 else rows[:4] + rows[len(rows) // 2:len(rows) // 2 + 3] + rows[-3:]
     for r in show:
         print(json.dumps(r))
-    if nb > 2:
-        per = (rows[-1]["c_start"] - rows[1]["c_start"]) / (nb - 2)
+    if len(rows) > 4:
+        per = (rows[-1]["m_dvdk_issued"] - rows[1]["m_dvdk_issued"]) / (len(rows) - 2)
         print(json.dumps({"steady_clk_per_block": per}))
 
 
