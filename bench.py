@@ -258,11 +258,15 @@ def run_native(args):
         sampler.start()
     n0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_range:
+        torch.cuda.profiler.start()    # ncu --profile-from-start off: only the timed steps are captured
     e0.record()
     for _ in range(args.steps):
         native_step()
     e1.record()
     sync_all()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     launches = (L.launch_count() - n0) // args.steps
     if launches_per_fwd_bwd is not None:
         launches += launches_per_fwd_bwd            # graph replays do not pass through the host-side counter
@@ -403,6 +407,8 @@ def main():
                     help="tensor-core operand format (fp32 accumulate, fp32 residual stream)")
     ap.add_argument("--lr", type=float, default=5e-5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (use with `ncu --profile-from-start off`)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

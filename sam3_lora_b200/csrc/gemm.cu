@@ -42,6 +42,8 @@ struct GemmParams {
   uint32_t mn_lbo, mn_sbo;
 };
 
+constexpr int STG_BYTES = 2048;   // epilogue staging tile per epilogue warp (see "Coalesced epilogue I/O" below)
+
 template <int BN>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
@@ -50,7 +52,7 @@ struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TCOLS = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 8 * STG_BYTES + 1024;
 };
 
 // Exact-erf GELU (nn.GELU default, timm Mlp): gelu(h) = h * Phi(h), Phi = standard normal CDF, with
@@ -82,34 +84,102 @@ __device__ __forceinline__ float dgelu_erf(float h) {
   return fmaf(h * 0.39894228f, g, phi);
 }
 
-template <int DT>
-__device__ __forceinline__ void store16x32(void* base, int64_t off, const float (&v)[32], int ncols_valid) {
-  // 32 consecutive 16-bit outputs = 64 B = 4 x 16 B; each 16 B vector is predicated on N.
-  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + off);
+// ---------------------------------------------------------------------------------------
+// Coalesced epilogue I/O.  tcgen05.ld 32x32b hands every lane one output ROW, so a direct 16-byte store per lane
+// touches 32 different 128-byte lines per instruction (32 LSU wavefronts, half-filled sectors): with two 16-bit outputs
+// the GELU epilogue kept the L1->XBAR path ~60 % busy and the epilogue, not the MMA, paced the kernel
+// (profiles/r01_ncu_gemm2_kernelILi3.txt).  Each epilogue warp therefore owns a 2 KB staging tile in shared memory
+// (32 rows x 64 bytes): lanes write / read their own row segment, and global memory is accessed with 4 lanes per row, so
+// one instruction covers 8 rows x 64 contiguous bytes (16 full sectors).  The 16-byte chunks are XOR-swizzled by
+// (row >> 1) & 3, which is conflict-free for both access patterns.
+// ---------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t stg_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+
+__device__ __forceinline__ void stage_put_row(uint8_t* stg, int lane, const uint32_t (&w)[16]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (q * 8 < ncols_valid) {
-      uint4 u;
-      u.x = pack2<DT>(v[q * 8 + 0], v[q * 8 + 1]);
-      u.y = pack2<DT>(v[q * 8 + 2], v[q * 8 + 3]);
-      u.z = pack2<DT>(v[q * 8 + 4], v[q * 8 + 5]);
-      u.w = pack2<DT>(v[q * 8 + 6], v[q * 8 + 7]);
-      dst[q] = u;
-    }
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(stg + stg_off(lane, c)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+__device__ __forceinline__ void stage_get_row(const uint8_t* stg, int lane, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(lane, c));
+    w[4 * c] = u.x; w[4 * c + 1] = u.y; w[4 * c + 2] = u.z; w[4 * c + 3] = u.w;
   }
 }
-__device__ __forceinline__ void store32x32(float* base, int64_t off, const float (&v)[32], int ncols_valid) {
-  float4* dst = reinterpret_cast<float4*>(base + off);
+// staging -> global.  g = address of (first row of the warp, first byte of the segment); rows_valid / bytes_valid clip.
+__device__ __forceinline__ void stage_flush(const uint8_t* stg, int lane, uint8_t* g, int64_t ld_bytes, int rows_valid, int bytes_valid) {
+  const int c = lane & 3;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    if (q * 4 < ncols_valid) dst[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2);
+    const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(row, c));
+    if (row < rows_valid && c * 16 < bytes_valid) *reinterpret_cast<uint4*>(g + (int64_t)row * ld_bytes + c * 16) = u;
+  }
+}
+// global -> staging (same access shape)
+__device__ __forceinline__ void stage_fill(uint8_t* stg, int lane, const uint8_t* g, int64_t ld_bytes, int rows_valid, int bytes_valid) {
+  const int c = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2);
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (row < rows_valid && c * 16 < bytes_valid) u = *reinterpret_cast<const uint4*>(g + (int64_t)row * ld_bytes + c * 16);
+    *reinterpret_cast<uint4*>(stg + stg_off(row, c)) = u;
   }
 }
 
-// One epilogue step: this thread owns output row `row`, columns [col, col+32).
+// this lane's 32 values -> 16-bit -> rows [row0, row0+32) x columns [col, col+32) of `base` (leading dimension ld elements)
+template <int DT>
+__device__ __forceinline__ void store16x32(uint8_t* stg, int lane, void* base, int64_t ld, int row0, int col, const float (&v)[32],
+                                           int rows_valid, int ncols_valid) {
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = pack2<DT>(v[2 * i], v[2 * i + 1]);
+  stage_put_row(stg, lane, w);
+  __syncwarp();
+  stage_flush(stg, lane, reinterpret_cast<uint8_t*>(reinterpret_cast<uint16_t*>(base) + (int64_t)row0 * ld + col), ld * 2, rows_valid,
+              ncols_valid * 2);
+  __syncwarp();
+}
+__device__ __forceinline__ void store32x32(uint8_t* stg, int lane, float* base, int64_t ld, int row0, int col, const float (&v)[32],
+                                           int rows_valid, int ncols_valid) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {   // 16 fp32 columns = 64 bytes per pass
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(v[h * 16 + i]);
+    stage_put_row(stg, lane, w);
+    __syncwarp();
+    stage_flush(stg, lane, reinterpret_cast<uint8_t*>(base + (int64_t)row0 * ld + col + h * 16), ld * 4, rows_valid,
+                (ncols_valid - h * 16) * 4);
+    __syncwarp();
+  }
+}
+// rows [row0 + ..) x 32 fp32 columns of `base` -> this lane's row (v[i] += )
+__device__ __forceinline__ void addload32x32(uint8_t* stg, int lane, const float* base, int64_t ld, int64_t grow0, bool contiguous_rows,
+                                             int col, float (&v)[32], int rows_valid, int ncols_valid) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    stage_fill(stg, lane, reinterpret_cast<const uint8_t*>(base + grow0 * ld + col + h * 16), ld * 4, rows_valid, (ncols_valid - h * 16) * 4);
+    __syncwarp();
+    uint32_t w[16];
+    stage_get_row(stg, lane, w);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[h * 16 + i] += __uint_as_float(w[i]);
+  }
+}
+
+// One epilogue step: the warp owns output rows [row0, row0+32) (this lane: row0 + lane), columns [col, col+32).
+// Executed by all 32 lanes (the staged stores are cooperative); rows >= M are clipped by rows_valid.
 template <int EPI, int DT, bool FULL>
-__device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, int row, int col, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t* stg, int lane, int row0, int col, const uint32_t (&r)[32]) {
   const int nvalid = FULL ? 32 : min(32, p.N - col);  // multiple of 8 (host-checked); FULL folds every column predicate
+  const int row = row0 + lane;
+  const int rows_valid = min(32, p.M - row0);
+  const bool row_ok = lane < rows_valid;
   float v[32];
   if (p.alpha == 1.f) {
 #pragma unroll
@@ -133,9 +203,9 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, int row
   }
 
   if constexpr (EPI == EPI_STORE16) {
-    store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
+    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_STORE32) {
-    store32x32(reinterpret_cast<float*>(p.C), (int64_t)row * p.ldc + col, v, nvalid);
+    store32x32(stg, lane, reinterpret_cast<float*>(p.C), p.ldc, row0, col, v, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_QKV_ROPE) {
     // 2-D axial RoPE on adjacent pairs (vitdet.py:68-90): (a,b) -> (a*cos - b*sin, a*sin + b*cos).
     // The table row is the token's position inside its rope period (window or image); the pair
@@ -153,44 +223,51 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, int row
         v[q * 4 + 3] = a1 * cs.w + b1 * cs.z;
       }
     }
-    store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
+    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_RESIDUAL_F32) {
-    const int rr = p.res_row_mod > 0 ? (row % p.res_row_mod) : row;
     if (p.row_scale != nullptr) {  // stochastic depth: per-image 0 or 1/keep on the branch (vitdet.py:610-611)
-      const float sc = __ldg(p.row_scale + row / p.rows_per_scale);
+      const float sc = __ldg(p.row_scale + min(row, p.M - 1) / p.rows_per_scale);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] *= sc;
     }
-    const float4* r4 = reinterpret_cast<const float4*>(p.res + (int64_t)rr * p.ldres + col);
+    // residual rows: row itself, or row % res_row_mod (positional table of the patch embedding).  A warp's 32 rows map to
+    // 32 consecutive residual rows unless they wrap around the table, in which case each lane loads its own row.
+    const int rr0 = p.res_row_mod > 0 ? (row0 % p.res_row_mod) : row0;
+    if (p.res_row_mod > 0 && rr0 + 32 > p.res_row_mod) {
+      const float4* r4 = reinterpret_cast<const float4*>(p.res + (int64_t)(row % p.res_row_mod) * p.ldres + col);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (q * 4 < nvalid) {
-        float4 x = r4[q];
-        v[q * 4] += x.x; v[q * 4 + 1] += x.y; v[q * 4 + 2] += x.z; v[q * 4 + 3] += x.w;
+      for (int q = 0; q < 8; ++q) {
+        if (row_ok && q * 4 < nvalid) {
+          float4 x = r4[q];
+          v[q * 4] += x.x; v[q * 4 + 1] += x.y; v[q * 4 + 2] += x.z; v[q * 4 + 3] += x.w;
+        }
       }
+    } else {
+      addload32x32(stg, lane, p.res, p.ldres, rr0, true, col, v, rows_valid, nvalid);
     }
-    store32x32(reinterpret_cast<float*>(p.C), (int64_t)row * p.ldc + col, v, nvalid);
+    store32x32(stg, lane, reinterpret_cast<float*>(p.C), p.ldc, row0, col, v, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_GELU) {
-    store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
+    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-    store16x32<DT>(p.C2, (int64_t)row * p.ldc2 + col, v, nvalid);
+    store16x32<DT>(stg, lane, p.C2, p.ldc2, row0, col, v, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_DGELU) {
-    const uint4* h4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux) +
-                                                     (int64_t)row * p.ldaux + col);
+    // h (the fc1 pre-activation, 16-bit) through the staging tile: 64 bytes per row
+    stage_fill(stg, lane, reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row0 * p.ldaux + col),
+               p.ldaux * 2, rows_valid, nvalid * 2);
+    __syncwarp();
+    uint32_t hw[16];
+    stage_get_row(stg, lane, hw);
+    __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (q * 8 < nvalid) {
-        uint4 u = h4[q];
-        float2 h0 = unpack2<DT>(u.x), h1 = unpack2<DT>(u.y), h2 = unpack2<DT>(u.z), h3 = unpack2<DT>(u.w);
-        v[q * 8 + 0] *= dgelu_erf(h0.x); v[q * 8 + 1] *= dgelu_erf(h0.y);
-        v[q * 8 + 2] *= dgelu_erf(h1.x); v[q * 8 + 3] *= dgelu_erf(h1.y);
-        v[q * 8 + 4] *= dgelu_erf(h2.x); v[q * 8 + 5] *= dgelu_erf(h2.y);
-        v[q * 8 + 6] *= dgelu_erf(h3.x); v[q * 8 + 7] *= dgelu_erf(h3.y);
-      }
+    for (int i = 0; i < 16; ++i) {
+      const float2 hh = unpack2<DT>(hw[i]);
+      v[2 * i] *= dgelu_erf(hh.x);
+      v[2 * i + 1] *= dgelu_erf(hh.y);
     }
-    store16x32<DT>(p.C, (int64_t)row * p.ldc + col, v, nvalid);
+    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_ADDMASK16) {
+    if (row_ok) {
     // data-gradient of the adapter branch under dropout: dx += mask/(1-p) * (dT''.A^T) [* gelu'(h) on the fc2 site]
     uint4* c4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.C) + (int64_t)row * p.ldc + col);
     const uint4* h4 = p.aux == nullptr ? nullptr
@@ -214,11 +291,12 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, int row
         c4[q] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
       }
     }
+    }
   } else if constexpr (EPI == EPI_ATOMIC_F32) {
     float* C = reinterpret_cast<float*>(p.C);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      if (i < nvalid) {
+      if (row_ok && i < nvalid) {
         int64_t off = p.c_trans ? ((int64_t)(col + i) * p.ldc + row) : ((int64_t)row * p.ldc + col + i);
         atomicAdd(C + off, v[i]);
       }
@@ -227,10 +305,10 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, int row
 }
 
 template <int EPI, int DT>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col, const uint32_t (&r)[32]) {
-  if (row >= p.M || col >= p.N) return;
-  if (col + 32 <= p.N) epilogue_chunk_impl<EPI, DT, true>(p, row, col, r);
-  else epilogue_chunk_impl<EPI, DT, false>(p, row, col, r);
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* stg, int lane, int row0, int col, const uint32_t (&r)[32]) {
+  if (row0 >= p.M || col >= p.N) return;   // warp-uniform
+  if (col + 32 <= p.N) epilogue_chunk_impl<EPI, DT, true>(p, stg, lane, row0, col, r);
+  else epilogue_chunk_impl<EPI, DT, false>(p, stg, lane, row0, col, r);
 }
 
 template <int BN, int EPI, int DT, bool A_MN, bool B_MN>
@@ -248,6 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES + ((threadIdx.x >> 5) >= 4 ? ((threadIdx.x >> 5) - 4) * STG_BYTES : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -352,14 +431,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
       mbar_wait(&tfull[acc], acc_phase, 400 + acc);
       tc_fence_after();
-      const int row = m_blk * 128 + ew * 32 + lane;
+      const int row0 = m_blk * 128 + ew * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = c_lo; c < c_lo + BN / 2; c += 32) {
         uint32_t r[32];
         tmem_ld_x32(t_row + c, r);
         tmem_ld_wait();
-        epilogue_chunk<EPI, DT>(p, row, n_blk * BN + c, r);
+        epilogue_chunk<EPI, DT>(p, stg, lane, row0, n_blk * BN + c, r);
       }
       tc_fence_before();
       __syncwarp();
@@ -389,7 +468,7 @@ struct Gemm2Cfg {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB (this CTA's half of the N tile)
   static constexpr int STAGES = 6;
   static constexpr int TCOLS = 512;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 256 + 8 * STG_BYTES + 1024;
 };
 
 template <int EPI, int DT>
@@ -408,6 +487,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = bars + 2 * STAGES;   // in both CTAs (multicast commit)
   uint64_t* tempty = tfull + 2;          // used in the leader CTA only, 16 arrivals (8 epilogue warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 256 + ((threadIdx.x >> 5) >= 4 ? ((threadIdx.x >> 5) - 4) * STG_BYTES : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -489,14 +569,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n_blk = w % n_tiles, m_pair = w / n_tiles;
       mbar_wait(&tfull[acc], acc_phase, 400 + acc);
       tc_fence_after();
-      const int row = m_pair * 256 + (int)rank * 128 + ew * 32 + lane;
+      const int row0 = m_pair * 256 + (int)rank * 128 + ew * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = c_lo; c < c_lo + BN / 2; c += 32) {
         uint32_t r[32];
         tmem_ld_x32(t_row + c, r);
         tmem_ld_wait();
-        epilogue_chunk<EPI, DT>(p, row, n_blk * BN + c, r);
+        epilogue_chunk<EPI, DT>(p, stg, lane, row0, n_blk * BN + c, r);
       }
       tc_fence_before();
       __syncwarp();
