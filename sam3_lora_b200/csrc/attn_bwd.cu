@@ -80,13 +80,15 @@ __device__ __forceinline__ bool attn_drop_keep(uint32_t base, uint32_t q, uint32
 }
 
 // 32 consecutive 16-bit elements of one global row -> 16 packed TMEM columns of this thread's lane (A-operand layout)
-__device__ __forceinline__ void load_row_half(uint32_t (&v)[16], const void* base, int64_t row, int64_t ld, int col) {
+__device__ __forceinline__ void park_row_half(uint32_t taddr, const void* base, int64_t row, int64_t ld, int col) {
   const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + row * ld + col);
+  uint32_t v[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint4 u = __ldg(src + i);
     v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
   }
+  tmem_st_x16(taddr, v);
 }
 
 template <int DT>
@@ -133,22 +135,9 @@ __device__ __forceinline__ void store_grad_chunk(const BwdParams& p, void* out, 
 }
 
 // 16-column variant: the item epilogue is spread over all 16 compute warps (4 column quarters x 4 lane quarters)
-// (cos, sin) pairs of 16 columns of one rope-table row: fetched BEFORE the wait for the item's last MMA so that the
-// global-load latency is off the item-to-item critical path
-__device__ __forceinline__ void load_rope16(const BwdParams& p, int rope_row, int cc, float4 (&rp)[4]) {
-  if (p.rope != nullptr) {
-    const float4* t4 = reinterpret_cast<const float4*>(p.rope + (int64_t)(rope_row % p.rope_period) * 32 + (cc >> 1));
-#pragma unroll
-    for (int q = 0; q < 4; ++q) rp[q] = __ldg(t4 + q);
-  } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) rp[q] = make_float4(1.f, 0.f, 1.f, 0.f);
-  }
-}
-
 template <int DT, bool ROPE>
-__device__ __forceinline__ void store_grad_chunk16(const float4 (&rp)[4], void* out, int64_t ld, uint32_t taddr, int row, int col0, int cc,
-                                                   float mul, bool valid) {
+__device__ __forceinline__ void store_grad_chunk16(const BwdParams& p, void* out, int64_t ld, uint32_t taddr, int row, int rope_row,
+                                                   int col0, int cc, float mul, bool valid) {
   uint32_t t[16];
   tmem_ld_x16(taddr + cc, t);
   tmem_ld_wait();
@@ -157,10 +146,11 @@ __device__ __forceinline__ void store_grad_chunk16(const float4 (&rp)[4], void* 
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(t[i]) * mul;
   if constexpr (ROPE) {
-    {
+    if (p.rope != nullptr) {
+      const float4* t4 = reinterpret_cast<const float4*>(p.rope + (int64_t)(rope_row % p.rope_period) * 32 + (cc >> 1));
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 cs = rp[q];
+        float4 cs = __ldg(t4 + q);
         float a0 = v[q * 4], b0 = v[q * 4 + 1], a1 = v[q * 4 + 2], b1 = v[q * 4 + 3];
         v[q * 4] = a0 * cs.x + b0 * cs.y;
         v[q * 4 + 1] = -a0 * cs.y + b0 * cs.x;
@@ -320,19 +310,16 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
     const float c = p.scale_log2;
 
     // K (group 0) / V (group 1) rows of an item -> TMEM; each thread parks 32 of its row's 64 elements
-    uint32_t nk[16];   // this thread's 32-element segment of the (next) item's K or V row
-    auto fetch = [&](int item) {
+    auto park = [&](int item) {
       const int tile = item % p.tiles, seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
       const int64_t grow = (int64_t)seg * p.Lk + min(tile * BT + r, p.Lk - 1);
-      load_row_half(nk, p.kv, grow, p.ldkv, (g == 0 ? p.k_col0 : p.v_col0) + head * HD + (wi >> 2) * 32);
-    };
-    auto park = [&]() {
-      tmem_st_x16((g == 0 ? tm_K : tm_V) + lane_off + (wi >> 2) * 16, nk);
+      park_row_half((g == 0 ? tm_K : tm_V) + lane_off + (wi >> 2) * 16, p.kv, grow, p.ldkv,
+                    (g == 0 ? p.k_col0 : p.v_col0) + head * HD + (wi >> 2) * 32);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(kv_ready);
     };
-    if ((int)blockIdx.x < n_items) { fetch(blockIdx.x); park(); }
+    if ((int)blockIdx.x < n_items) park(blockIdx.x);
 
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -415,25 +402,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
         mbar_arrive(&pds_full[g]);
         if (tr) TRACE(64 + j * 8 + 5);
       }
-      // Item transition.  Global loads first (next item's K / V segment, this item's rope-table entries), so that their
-      // latency hides behind the waits; then park the next K / V before this item's epilogue so that the next item's
-      // first MMAs overlap the epilogue.
+      // park the next item's K / V before this item's epilogue so that its first MMAs overlap the epilogue
       const int next = item + gridDim.x;
-      const int row = t_row0 + r;
-      const int ec = (wi >> 2) * 32 + g * 16;   // this warp's 16-column quarter of both accumulators
-      if (next < n_items) fetch(next);
-      float4 rp[4];
-      load_rope16(p, row, ec, rp);
       if (next < n_items) {
         mbar_wait(kv_free, it & 1, 34);
         tc_fence_after();
-        park();
+        park(next);
       }
       mbar_wait(all_done, it & 1, 32);
       tc_fence_after();
+      const int row = t_row0 + r;
       const bool valid = (tile * BT + r) < p.Lk;
-      store_grad_chunk16<DT, false>(rp, p.dkv, p.lddkv, tm_dV + lane_off, row, p.dv_col0 + head * HD, ec, 1.f, valid);
-      store_grad_chunk16<DT, true>(rp, p.dkv, p.lddkv, tm_dK + lane_off, row, p.dk_col0 + head * HD, ec, p.scale, valid);
+      const int ec = (wi >> 2) * 32 + g * 16;   // this warp's 16-column quarter of both accumulators
+      store_grad_chunk16<DT, false>(p, p.dkv, p.lddkv, tm_dV + lane_off, row, row, p.dv_col0 + head * HD, ec, 1.f, valid);
+      store_grad_chunk16<DT, true>(p, p.dkv, p.lddkv, tm_dK + lane_off, row, row, p.dk_col0 + head * HD, ec, p.scale, valid);
       tc_fence_before();
       mbar_arrive(epi_done);
     }
@@ -562,20 +544,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
     const float c = p.scale_log2;
 
     // Q (group 0) / dO (group 1) rows of an item -> TMEM
-    uint32_t nk[16];   // this thread's 32-element segment of the (next) item's Q or dO row
-    auto fetch = [&](int item) {
+    auto park = [&](int item) {
       const int tile = item % p.tiles, seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
       const int64_t grow = (int64_t)seg * p.Lq + min(tile * BT + r, p.Lq - 1);
-      if (g == 0) load_row_half(nk, p.q, grow, p.ldq, p.q_col0 + head * HD + (wi >> 2) * 32);
-      else        load_row_half(nk, p.dO, grow, p.lddo, p.do_col0 + head * HD + (wi >> 2) * 32);
-    };
-    auto park = [&]() {
-      tmem_st_x16((g == 0 ? tm_Q : tm_dO) + lane_off + (wi >> 2) * 16, nk);
+      if (g == 0) park_row_half(tm_Q + lane_off + (wi >> 2) * 16, p.q, grow, p.ldq, p.q_col0 + head * HD + (wi >> 2) * 32);
+      else        park_row_half(tm_dO + lane_off + (wi >> 2) * 16, p.dO, grow, p.lddo, p.do_col0 + head * HD + (wi >> 2) * 32);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(qdo_ready);
     };
-    if ((int)blockIdx.x < n_items) { fetch(blockIdx.x); park(); }
+    if ((int)blockIdx.x < n_items) park(blockIdx.x);
 
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -641,19 +619,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
         mbar_arrive(&ds_full[g]);
       }
       const int next = item + gridDim.x;
-      const int ec = (wi >> 2) * 32 + g * 16;
-      if (next < n_items) fetch(next);
-      float4 rp[4];
-      load_rope16(p, row, ec, rp);
       if (next < n_items) {
         mbar_wait(qdo_free, it & 1, 34);
         tc_fence_after();
-        park();
+        park(next);
       }
       mbar_wait(all_done, it & 1, 32);
       tc_fence_after();
       const bool valid = (tile * BT + r) < p.Lq;
-      store_grad_chunk16<DT, true>(rp, p.dq, p.lddq, tm_dQ + lane_off, row, p.dq_col0 + head * HD, ec, p.scale, valid);
+      store_grad_chunk16<DT, true>(p, p.dq, p.lddq, tm_dQ + lane_off, row, row, p.dq_col0 + head * HD, (wi >> 2) * 32 + g * 16, p.scale, valid);
       tc_fence_before();
       mbar_arrive(epi_done);
     }

@@ -7,20 +7,22 @@
 // is kept in window-major order, so a window is a contiguous run of L rows ("segment").
 //
 // Layout: qkv [tokens][ld] 16-bit with q at column h*64, k at D + h*64, v at 2D + h*64.
-// One CTA = one (128-query tile, head, segment); 2 CTAs co-resident per SM (64 KB smem, 256 TMEM
-// columns each).  Both MMAs take their A operand FROM TENSOR MEMORY: the Q tile is parked in TMEM once
-// (16-bit, two elements per column) and P_j is written back over the S_j columns it was computed from, so
-// the only shared-memory traffic per block is the streamed K_j / V_j tiles (an SS-MMA with N=64 needs
-// 192 B/clk of smem operands against the SM's 128 B/clk: profiles/r01_attn_bwd_timeline.md).
-//   warps 0-3 : softmax + output (thread t owns query row t == TMEM lane t); they also load Q
-//   warp  4   : TMA producer (K_j / V_j into 4-stage rings)
-//   warp  5   : MMA issuer + TMEM allocator; issue order S_0, S_1, PV_0, S_2, PV_1, ...
-// Per 64-key block j:  S_j = Q K_j^T (fp32, TMEM buffer j&1) -> one pass over the 64 scores in
-// registers: row max, p = exp2(s*c - m*c), row sum -> P_j (16-bit) into TMEM buffer j&1 ->
-// O += P_j V_j accumulated IN TMEM (V tile as MN-major B operand).  The running max only moves when
+// One CTA = one (128-query tile, head, segment), 192 threads, FOUR CTAs co-resident per SM (48 KB smem, 128 TMEM
+// columns and <= 85 registers each).  The exp2 of the softmax is the floor of this kernel (MUFU: 512 clk per
+// 128x64 block per SM, tools/micro/mufu_rate.cu); one CTA alone keeps the MUFU pipe ~30 % busy because its
+// MMA -> softmax -> MMA chain is serial, so the design goal is simply "as many independent chains per SM as TMEM allows":
+//   warps 0-3 : softmax + output (thread t owns query row t == TMEM lane t)
+//   warp  4   : TMA producer (Q once, then K_j / V_j into 2-stage rings)
+//   warp  5   : MMA issuer + TMEM allocator; issue order S_0, PV_0, S_1, PV_1, ...
+// Per 64-key block j:  S_j = Q K_j^T (SS MMA, fp32, TMEM columns [0,64)) -> two passes over the 64 scores, 32 at a time
+// from TMEM (row max; then p = exp2(s*c - m*c), row sum) -> P_j (16-bit) written back over S_j's first 32 columns with
+// tcgen05.st -> O += P_j V_j with P_j as the TMEM A operand (no shared-memory round trip, no proxy fence) and V_j as
+// MN-major B.  The running max only moves when
 // the block max exceeds it by more than 2^8 in the exp2 domain ("lazy rescale"): then the softmax
 // warps rescale the O accumulator in TMEM (tcgen05.ld / st) before publishing P_j.  Output: O
 // 16-bit, LSE in log2 units.
+// History (profiles/r01_attn_bwd_timeline.md): v1 kept Q, P in shared memory (smem-bandwidth bound, 2 CTAs/SM, 542 TF/s
+// on the global blocks); v2 moved Q and P to TMEM (646 TF/s); v3 (this) trades the S double buffer for a third and fourth CTA (window 0.183 ms = 534 TF/s, global 1.25 ms = 706 TF/s).
 #include "attn.cuh"
 
 #include "common.h"
@@ -42,12 +44,16 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;  // queries per CTA
 constexpr int BKV = 64;  // keys per block: divides 576 and 5184
+constexpr int Q_BYTES = BQ * HD * 2;   // 16 KB
 constexpr int KV_BYTES = BKV * HD * 2; // 8 KB
-constexpr int NS = 4;                  // K / V ring depth
-// 2 CTAs/SM: 2 x (dynamic + 1 KB reserved) must fit the SM's 228 KB: no alignment slack, the dynamic
+#ifndef SAM3B_FWD_CTAS
+#define SAM3B_FWD_CTAS 4               // co-resident CTAs per SM (TMEM: 128 columns each); measured 3 -> 4: window 0.211 -> 0.183 ms, global 1.43 -> 1.25 ms
+#endif
+constexpr int NS = SAM3B_FWD_CTAS >= 4 ? 2 : 3;   // K / V ring depth
+// N CTAs/SM: N x (dynamic + 1 KB reserved) must fit the SM's 228 KB: no alignment slack, the dynamic
 // window is declared 1024-byte aligned and checked at run time.
-constexpr int FWD_SMEM = 2 * NS * KV_BYTES + 256 /*barriers*/;
-constexpr int TCOLS = 256;  // S0/P0: [0,64)  S1/P1: [64,128)  O: [128,192)  Q (16-bit A operand): [192,224)
+constexpr int FWD_SMEM = Q_BYTES + 2 * NS * KV_BYTES + 256 /*barriers*/;
+constexpr int TCOLS = 128;  // S / P: [0,64)   O: [64,128)
 constexpr float RESCALE_LOG2 = 8.f;  // p <= 2^8 between rescales: safe in fp16/bf16 and fp32 sums
 
 struct FwdParams {
@@ -74,23 +80,24 @@ __device__ __forceinline__ bool attn_drop_keep(uint32_t base, uint32_t q, uint32
 }
 
 template <int DT, bool GEN>
-__global__ void __launch_bounds__(192, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
+__global__ void __launch_bounds__(192, GEN ? 3 : SAM3B_FWD_CTAS)   // the masked / dropout instantiation needs ~95 registers
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // swizzle-128B operands need 1024-byte alignment
-  uint8_t* sK = smem_raw;              // NS stages
+  uint8_t* sQ = smem_raw;
+  uint8_t* sK = sQ + Q_BYTES;          // NS stages
   uint8_t* sV = sK + NS * KV_BYTES;    // NS stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * KV_BYTES);
-  uint64_t* q_ready = bars + 0;
+  uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;            // [NS]
   uint64_t* k_free = k_full + NS;         // [NS]
   uint64_t* v_full = k_free + NS;         // [NS]
   uint64_t* v_free = v_full + NS;         // [NS]
-  uint64_t* s_full = v_free + NS;         // [2]
-  uint64_t* p_full = s_full + 2;          // [2]
-  uint64_t* pv_done = p_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-  static_assert((1 + 4 * NS + 6) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
+  uint64_t* s_full = v_free + NS;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* pv_done = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  static_assert((1 + 4 * NS + 3) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
 
   const int warp = threadIdx.x >> 5;
   const int q_tile = blockIdx.x % p.q_tiles;
@@ -101,12 +108,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
   const int n_blocks = (p.Lk + BKV - 1) / BKV;
 
   if (warp == 4 && elect_one()) {
+    tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    mbar_init(q_ready, 128);
+    mbar_init(q_full, 1);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_free[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_free[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -116,13 +124,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 2 * BKV;
-  const uint32_t tmem_Q = tmem_base + 3 * BKV;
+  const uint32_t tmem_S = *tmem_slot;        // S_j (fp32, 64 columns); P_j (16-bit) is written back over columns [0,32)
+  const uint32_t tmem_O = tmem_S + BKV;
 
   if (warp == 4) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, p.q_col0 + head * HD, q_row0);
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j % NS;
         const int kv_row0 = kv_row0_seg + j * BKV;
@@ -139,38 +148,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, DT, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(BQ, HD, DT, 0, 1);
-      // S_j = Q K_j^T: A = the Q tile in TMEM (K=16 elements = 8 columns per instruction), B = K_j in smem
+      constexpr uint32_t ST16 = KV_BYTES >> 4;
+      const uint64_t dQ = make_desc_kmajor(smem_u32(sQ)), dK = make_desc_kmajor(smem_u32(sK));
+      const uint64_t dV = make_desc_mnmajor(smem_u32(sV), 8192);
+      // S_j = Q K_j^T, both operands in shared memory (48 clk per instruction instead of 32: irrelevant next to the
+      // 512 clk of exp2 per block)
       auto issue_s = [&](int j) {
-        const int st = j % NS, sb = j & 1;
+        const int st = j % NS;
         mbar_wait(&k_full[st], (j / NS) & 1, 21);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * KV_BYTES);
+        const uint64_t kd = dK + (uint64_t)(st * ST16);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_f16_ts(tmem_base + sb * BKV, tmem_Q + k * 8, make_desc_kmajor(k_addr + k * 32), idesc_s, k > 0);
-        umma_commit(&s_full[sb]);
+        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tmem_S, dQ + k * 2, kd + k * 2, idesc_s, k > 0);
+        umma_commit(s_full);
         umma_commit(&k_free[st]);
         if (j < 96) TRACE(1024 + j * 4 + 0);
       };
-      mbar_wait(q_ready, 0, 20);
-      tc_fence_after();
+      mbar_wait(q_full, 0, 20);
       issue_s(0);
       for (int j = 0; j < n_blocks; ++j) {
-        const int st = j % NS, sb = j & 1;
-        // S_{j+1} goes out before we block on the softmax of block j.  It overwrites buffer (j+1)&1, i.e. P_{j-1}:
-        // P_{j-1}.V_{j-1} was issued in the previous iteration and the tensor pipe executes in issue order.
-        if (j + 1 < n_blocks) issue_s(j + 1);
-        mbar_wait(&p_full[sb], (j >> 1) & 1, 22);
+        const int st = j % NS;
+        mbar_wait(p_full, j & 1, 22);
         mbar_wait(&v_full[st], (j / NS) & 1, 23);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + st * KV_BYTES);
+        const uint64_t vd = dV + (uint64_t)(st * ST16);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)   // A = P_j (16-bit, packed over the first 32 columns of S buffer sb)
-          umma_f16_ts(tmem_O, tmem_base + sb * BKV + k * 8, make_desc_mnmajor(v_addr + k * 2048, 8192), idesc_pv,
-                      (j > 0 || k > 0));
-        umma_commit(&pv_done[sb]);
+        for (int k = 0; k < BKV / 16; ++k)   // A = P_j in TMEM (16-bit, packed over the first 32 columns of S)
+          umma_f16_ts(tmem_O, tmem_S + k * 8, vd + k * 128, idesc_pv, (j > 0 || k > 0));
+        umma_commit(pv_done);
         umma_commit(&v_free[st]);
         if (j < 96) TRACE(1024 + j * 4 + 1);
+        // S_{j+1} overwrites S_j / P_j: issued after P_j.V_j, and the tensor pipe executes in issue order
+        if (j + 1 < n_blocks) issue_s(j + 1);
       }
     }
   } else {
@@ -191,82 +200,64 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
     }
     const float c_eff = GEN ? 1.f : c;
 
-    {  // park this thread's Q row (64 x 16-bit = 32 packed columns) in TMEM as the A operand of every S_j
-      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.q) +
-                                                        (int64_t)(seg * p.Lq + q_in_seg) * p.ldq + p.q_col0 + head * HD);
-      uint32_t qa[32];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 u = __ldg(src + i);
-        qa[4 * i] = u.x; qa[4 * i + 1] = u.y; qa[4 * i + 2] = u.z; qa[4 * i + 3] = u.w;
-      }
-      tmem_st_x32(tmem_Q + lane_off, qa);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(q_ready);
-    }
-
     for (int j = 0; j < n_blocks; ++j) {
-      const int st = j & 1;
       const int kv_valid = min(BKV, p.Lk - j * BKV);
+      const bool full = kv_valid == BKV;   // predicate-free path (every block when Lk % 64 == 0)
       const bool tr = threadIdx.x == 0 && j < 96;
       if (tr) TRACE(64 + j * 8 + 0);
-      mbar_wait(&s_full[st], (j >> 1) & 1, 30);
+      mbar_wait(s_full, j & 1, 30);
       tc_fence_after();
       if (tr) TRACE(64 + j * 8 + 1);
-      uint32_t s[BKV];
-      {
-        uint32_t a[32], b[32];
-        tmem_ld_x32(tmem_base + lane_off + st * BKV, a);
-        tmem_ld_x32(tmem_base + lane_off + st * BKV + 32, b);
+      // 32 scores of this row (half h of the block) in the units the running max uses.  The block is read twice from
+      // TMEM (max pass, exp pass) instead of being held in 64 registers: four CTAs per SM leave 85 registers per thread.
+      auto load_half = [&](int h, float (&t)[32]) {
+        uint32_t a[32];
+        tmem_ld_x32(tmem_S + lane_off + h * 32, a);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { s[i] = a[i]; s[32 + i] = b[i]; }
-      }
-      if constexpr (GEN) {
-        // t = s*c (+ bias*log2e) ; padded keys -> -inf
+        for (int i = 0; i < 32; ++i) t[i] = __uint_as_float(a[i]);
+        if constexpr (GEN) {
 #pragma unroll
-        for (int i = 0; i < BKV; ++i) s[i] = __float_as_uint(__uint_as_float(s[i]) * c);
-        if (bias_row != nullptr) {
-          const float* bp = bias_row + j * BKV;
+          for (int i = 0; i < 32; ++i) t[i] *= c;
+          if (bias_row != nullptr) {
+            const float* bp = bias_row + j * BKV + h * 32;
 #pragma unroll
-          for (int i = 0; i < BKV; ++i)
-            if (i < kv_valid) s[i] = __float_as_uint(fmaf(__ldg(bp + i), 1.4426950408889634f, __uint_as_float(s[i])));
+            for (int i = 0; i < 32; ++i)
+              if (h * 32 + i < kv_valid) t[i] = fmaf(__ldg(bp + i), 1.4426950408889634f, t[i]);
+          }
+          if (p.kpm != nullptr) {
+            const uint8_t* kp = p.kpm + (int64_t)seg * p.Lk + j * BKV + h * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (h * 32 + i < kv_valid && __ldg(kp + i) != 0) t[i] = -INFINITY;
+          }
         }
-        if (p.kpm != nullptr) {
-          const uint8_t* kp = p.kpm + (int64_t)seg * p.Lk + j * BKV;
-#pragma unroll
-          for (int i = 0; i < BKV; ++i)
-            if (i < kv_valid && __ldg(kp + i) != 0) s[i] = __float_as_uint(-INFINITY);
-        }
-      }
-      // full blocks (every block when Lk % 64 == 0) take the predicate-free path: the per-element ISETP/FSEL
-      // of the tail mask were 27 % of this kernel's issued instructions (profiles/r01_ncu_attn_fwd.txt)
-      const bool full = kv_valid == BKV;
-      if (tr) TRACE(64 + j * 8 + 2);
+      };
+      // ---- pass 1: block max ----
       float m_blk = -INFINITY;
-      if (full) {
-        // 8 independent max chains (a single 64-deep FMNMX dependency chain costs ~300 cycles per block)
-        float mx[8];
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float t[32];
+        load_half(h, t);
+        if (full) {
+          float mx[4] = {t[0], t[1], t[2], t[3]};   // independent chains
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx[i] = __uint_as_float(s[i]);
+          for (int i = 4; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], t[i]);
+          m_blk = fmaxf(m_blk, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+        } else {
 #pragma unroll
-        for (int i = 8; i < BKV; ++i) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(s[i]));
-        m_blk = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-      } else {
-#pragma unroll
-        for (int i = 0; i < BKV; ++i)
-          if (i < kv_valid) m_blk = fmaxf(m_blk, __uint_as_float(s[i]));
+          for (int i = 0; i < 32; ++i)
+            if (h * 32 + i < kv_valid) m_blk = fmaxf(m_blk, t[i]);
+        }
       }
+      if (tr) TRACE(64 + j * 8 + 2);
       // always true on the first block (m_used = -inf) unless every key so far is masked (m_blk = -inf)
       const bool need = m_blk > m_used + tau;
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? m_blk : m_used;
         const float alpha = ex2_approx((m_used - m_new) * c_eff);  // 0 on the first block, 1 for rows that keep their max
         if (j > 0) {
-          // every earlier P.V has landed in the accumulator (MMAs complete in issue order)
-          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1, 31);
-          tc_fence_after();
+          // s_full(j) was signalled by a commit issued after P.V of block j-1: every earlier P.V has landed in O
 #pragma unroll
           for (int cc = 0; cc < HD; cc += 32) {
             uint32_t t[32];
@@ -281,54 +272,52 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
         l_run *= alpha;
         m_used = m_new;
       }
-      // P_j goes over the S_j columns: s_full(j) (a commit) already implies that P.V of block j-2, the last
-      // reader of this buffer, has completed.
       if (tr) TRACE(64 + j * 8 + 3);
+      // ---- pass 2: p = exp2(t - m), row sum, P_j (16-bit) over the S_j columns ----
       const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_eff;  // all keys masked so far: exp2(-inf - 0) = 0
-      uint32_t pk[32];
       float l_part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float t[32];
+        load_half(h, t);
+        uint32_t pk[16];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float e[8];
-        if (full) {
+        for (int q = 0; q < 4; ++q) {
+          float e[8];
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(s[q * 8 + i]), c_eff, -mc));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float v = ex2_approx(fmaf(__uint_as_float(s[q * 8 + i]), c_eff, -mc));
-            e[i] = (q * 8 + i < kv_valid) ? v : 0.f;
-          }
-        }
-        uint4 u;
-        if constexpr (GEN) {
-          if (p.drop_thr != 0) {   // dropout on the probabilities fed to P.V; the row sum stays un-dropped
-            float d[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              d[i] = attn_drop_keep(drop_base, (uint32_t)q_in_seg, (uint32_t)(j * BKV + q * 8 + i), (uint32_t)p.Lk, p.drop_thr)
-                         ? e[i] * p.drop_inv_keep : 0.f;
-            u.x = pack2<DT>(d[0], d[1]); u.y = pack2<DT>(d[2], d[3]); u.z = pack2<DT>(d[4], d[5]); u.w = pack2<DT>(d[6], d[7]);
+            for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(t[q * 8 + i], c_eff, -mc));
           } else {
-            u.x = pack2<DT>(e[0], e[1]); u.y = pack2<DT>(e[2], e[3]); u.z = pack2<DT>(e[4], e[5]); u.w = pack2<DT>(e[6], e[7]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float v = ex2_approx(fmaf(t[q * 8 + i], c_eff, -mc));
+              e[i] = (h * 32 + q * 8 + i < kv_valid) ? v : 0.f;
+            }
           }
-        } else {
-          u.x = pack2<DT>(e[0], e[1]); u.y = pack2<DT>(e[2], e[3]); u.z = pack2<DT>(e[4], e[5]); u.w = pack2<DT>(e[6], e[7]);
+          // fp32 row sum of the unrounded, un-dropped probabilities
+          l_part[q] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+          if constexpr (GEN) {
+            if (p.drop_thr != 0) {   // dropout on the probabilities fed to P.V
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                e[i] = attn_drop_keep(drop_base, (uint32_t)q_in_seg, (uint32_t)(j * BKV + h * 32 + q * 8 + i), (uint32_t)p.Lk, p.drop_thr)
+                           ? e[i] * p.drop_inv_keep : 0.f;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pk[q * 4 + i] = pack2<DT>(e[2 * i], e[2 * i + 1]);
         }
-        // fp32 row sum of the unrounded probabilities (no 16-bit -> fp32 conversions: the conversion pipe
-        // shares its 16 lanes/clk with MUFU and is what bounds this loop)
-        l_part[q & 3] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-        pk[4 * q] = u.x; pk[4 * q + 1] = u.y; pk[4 * q + 2] = u.z; pk[4 * q + 3] = u.w;
+        // half 0 lands on S columns [0,16), half 1 on [16,32): both already consumed by this thread
+        tmem_st_x16(tmem_S + lane_off + h * 16, pk);
       }
-      if (tr) TRACE(64 + j * 8 + 4);
-      tmem_st_x32(tmem_base + lane_off + st * BKV, pk);
-      tmem_st_wait();
       l_run += (l_part[0] + l_part[1]) + (l_part[2] + l_part[3]);
+      if (tr) TRACE(64 + j * 8 + 4);
+      tmem_st_wait();
       tc_fence_before();         // our tcgen05.ld/st are ordered before the MMA warp's next tcgen05 ops
-      mbar_arrive(&p_full[st]);
+      mbar_arrive(p_full);
       if (tr) TRACE(64 + j * 8 + 5);
     }
-    mbar_wait(&pv_done[(n_blocks - 1) & 1], ((n_blocks - 1) >> 1) & 1, 33);
+    mbar_wait(pv_done, (n_blocks - 1) & 1, 33);
     tc_fence_after();
     const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;  // a fully masked row yields zeros (torch would give NaN)
     const int row = q_row0 + r;
@@ -357,18 +346,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, TCOLS);
+  if (warp == 5) tmem_dealloc(tmem_S, TCOLS);
 }
 
 // one instantiation (and one cached smem attribute) per (operand format, feature set)
 template <int DT, bool GEN>
-static int launch_fwd(const CUtensorMap& tmKV, const FwdParams& p, dim3 grid, cudaStream_t stream) {
+static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const FwdParams& p, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     SAM3B_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr_set = true;
   }
-  attn_fwd_kernel<DT, GEN><<<grid, 192, FWD_SMEM, stream>>>(tmKV, p);
+  attn_fwd_kernel<DT, GEN><<<grid, 192, FWD_SMEM, stream>>>(tmQ, tmKV, p);
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -382,8 +371,10 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t stream) {
   SAM3B_REQUIRE(a.q_col0 % 8 == 0 && a.k_col0 % 8 == 0 && a.v_col0 % 8 == 0 && a.o_col0 % 8 == 0, "attention: column offsets must be multiples of 8");
   SAM3B_REQUIRE(a.dtype == 0 || a.dtype == 1, "attention: dtype");
   SAM3B_REQUIRE(a.drop_p >= 0.f && a.drop_p < 1.f, "attention: dropout p=%f outside [0,1)", a.drop_p);
-  CUtensorMap tmKV;
-  int rc = make_tmap_2d(&tmKV, a.kv, (uint64_t)a.nseg * a.Lk, a.kv_cols, a.ldkv, BKV, HD);
+  CUtensorMap tmQ, tmKV;
+  int rc = make_tmap_2d(&tmQ, a.q, (uint64_t)a.nseg * a.Lq, a.q_cols, a.ldq, BQ, HD);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmKV, a.kv, (uint64_t)a.nseg * a.Lk, a.kv_cols, a.ldkv, BKV, HD);
   if (rc) return rc;
   FwdParams p{};
   p.Lq = a.Lq; p.Lk = a.Lk; p.q_tiles = (a.Lq + BQ - 1) / BQ;
@@ -396,8 +387,8 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t stream) {
   p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_thr = a.drop_p > 0.f ? dropout_threshold(a.drop_p) : 0u; p.drop_seed = a.drop_seed;
   dim3 grid(p.q_tiles * a.nseg, a.heads);
   const bool gen = a.bias != nullptr || a.kpm != nullptr || a.drop_p > 0.f;
-  if (gen) return a.dtype == 0 ? launch_fwd<0, true>(tmKV, p, grid, stream) : launch_fwd<1, true>(tmKV, p, grid, stream);
-  return a.dtype == 0 ? launch_fwd<0, false>(tmKV, p, grid, stream) : launch_fwd<1, false>(tmKV, p, grid, stream);
+  if (gen) return a.dtype == 0 ? launch_fwd<0, true>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, true>(tmQ, tmKV, p, grid, stream);
+  return a.dtype == 0 ? launch_fwd<0, false>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, false>(tmQ, tmKV, p, grid, stream);
 }
 
 #ifdef SAM3B_TRACE
