@@ -370,6 +370,53 @@ def run_native(args):
                 "step_trunk_frac_of_sustained": value / world * GF_TRUNK_TRAIN / 1e3 / peaks["sustained"],
                 "attn_gemm_roofline_frac": value / world * GF_ATTN_GEMM_TRAIN / 1e3 / peaks["sustained"]}
 
+    # -------- the other heavy kernels, same method (timed alone, CUDA events): context for the step breakdown --------
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    others = []
+    try:
+        C1 = torch.empty(M, N, device=dev, dtype=dt)
+        ms_plain = timed(lambda: L.gemm(A, W, C1, epilogue=L.EPI_STORE16, bias=bias))
+        others.append({"kernel": "gemm2_kernel<EPI_STORE16> M=%d N=%d K=%d" % (M, N, K), "ms": ms_plain, "bound": "tensor",
+                       "achieved": 2.0 * M * N * K / ms_plain / 1e9, "peak": peaks["burst"], "unit": "TFLOP/s"})
+        del C1
+        heads, D = 16, 1024
+        for name, Ls, segs in (("window 576", 576, B * 9), ("global 5184", 5184, B)):
+            T = Ls * segs
+            qkv = (torch.randn(T, 3 * D + 64, device=dev) * 0.5).to(dt)
+            O = torch.zeros(T, D + 64, device=dev, dtype=dt)
+            lse2 = torch.zeros(heads, T, device=dev)
+            dO = (torch.randn(T, D, device=dev) * 0.5).to(dt)
+            delta = torch.zeros(heads, T, device=dev)
+            dqkv = torch.zeros(T, 3 * D + 64, device=dev, dtype=dt)
+            tab = torch.zeros(Ls, 32, 2, device=dev)
+            tab[..., 0] = 1.0
+            fl = 4.0 * segs * heads * Ls * Ls * 64
+            ms_f = timed(lambda: L.attention_fwd(qkv, Ls, D, heads, O, lse2))
+            ms_b = timed(lambda: L.attention_bwd(qkv, Ls, D, heads, O, lse2, dO, delta, dqkv, tab, Ls))
+            # exp2 floor: one MUFU.EX2 warp instruction per 8 clk per SM sub-partition (tools/micro/mufu_rate.cu)
+            sm_hz = (clocks or {}).get("sm_mhz") or 1700.0
+            mufu_s = segs * heads * Ls * Ls / (148 * 16.0 * sm_hz * 1e6)
+            others.append({"kernel": "attn_fwd_kernel, %s, B=%d" % (name, B), "ms": ms_f, "bound": "mufu-ex2", "achieved": fl / ms_f / 1e9,
+                           "unit": "TFLOP/s", "floor_ms": mufu_s * 1e3, "frac_of_floor": mufu_s * 1e3 / ms_f})
+            others.append({"kernel": "attn_bwd_dkdv+dq kernels, %s, B=%d" % (name, B), "ms": ms_b, "bound": "mufu-ex2 (2 exp per score)",
+                           "achieved": 2.5 * fl / ms_b / 1e9, "unit": "TFLOP/s (5 algorithmic matmuls)", "floor_ms": 2 * mufu_s * 1e3,
+                           "frac_of_floor": 2 * mufu_s * 1e3 / ms_b})
+            del qkv, O, lse2, dO, delta, dqkv
+    except Exception as e:  # noqa: BLE001 - context only, never fatal for the bench line
+        others.append({"error": f"{type(e).__name__}: {e}"[:200]})
+    roofline["other_kernels"] = others
+
     # -------- CPU baseline beside it (rank 0, N=1 only) --------
     cpu_baseline = None
     if world == 1 and not args.no_cpu:

@@ -580,7 +580,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       tc_fence_before();
       __syncwarp();
+      #ifdef SAM3B_TEMPTY_RELEASE   // A/B switch for the measurement in profiles/README.md
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+#else
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(&tempty[acc], 0));
+#endif
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }

@@ -301,6 +301,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same, without release semantics: for hand-offs whose payload is not in memory (a drained TMEM accumulator, ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  A cluster-scope release first waits for every outstanding global
+// store of the thread: 8 % of the GELU GEMM's stall samples (profiles/r01_ncu_v3_gemm2_gelu.txt).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load issued by either CTA of a pair; completion bytes are credited to the mbarrier at
 // `mbar_cluster_addr` (the leader CTA's barrier).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t mbar_cluster_addr, int c0,
