@@ -38,7 +38,8 @@ namespace sam3b {
 // Debug timeline (tools/attn_trace.py): one chosen CTA stamps clock64() at its pipeline events.
 __device__ unsigned long long g_attn_trace[16384];
 #define TR_CTA 70
-#define TRACE(slot) do { if (blockIdx.x == TR_CTA && (slot) < 16384) g_attn_trace[(slot)] = clock64(); } while (0)
+// stamps items 2 and 3 of the traced CTA (steady state of the persistent loop): item 3 uses slots + 4096
+#define TRACE(slot) do { if (blockIdx.x == TR_CTA && (it == 2 || it == 3) && (slot) < 4096) g_attn_trace[(slot) + (it - 2) * 4096] = clock64(); } while (0)
 #else
 #define TRACE(slot) do { } while (0)
 #endif
@@ -404,18 +405,24 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
       }
       // park the next item's K / V before this item's epilogue so that its first MMAs overlap the epilogue
       const int next = item + gridDim.x;
+      const bool trt = threadIdx.x == 0 || threadIdx.x == 256;
+      if (trt) TRACE(8 + g * 8 + 0);
       if (next < n_items) {
         mbar_wait(kv_free, it & 1, 34);
         tc_fence_after();
+        if (trt) TRACE(8 + g * 8 + 1);
         park(next);
       }
+      if (trt) TRACE(8 + g * 8 + 2);
       mbar_wait(all_done, it & 1, 32);
       tc_fence_after();
+      if (trt) TRACE(8 + g * 8 + 3);
       const int row = t_row0 + r;
       const bool valid = (tile * BT + r) < p.Lk;
       const int ec = (wi >> 2) * 32 + g * 16;   // this warp's 16-column quarter of both accumulators
       store_grad_chunk16<DT, false>(p, p.dkv, p.lddkv, tm_dV + lane_off, row, row, p.dv_col0 + head * HD, ec, 1.f, valid);
       store_grad_chunk16<DT, true>(p, p.dkv, p.lddkv, tm_dK + lane_off, row, row, p.dk_col0 + head * HD, ec, p.scale, valid);
+      if (trt) TRACE(8 + g * 8 + 4);
       tc_fence_before();
       mbar_arrive(epi_done);
     }

@@ -96,8 +96,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
   const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * D);
   const uint2* dyr = reinterpret_cast<const uint2*>(dy + (int64_t)row * lddy);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  float4 xh[VPT], g[VPT];
+  // all three streams (x, dy, residual gradient) are requested before the first reduction: one memory-latency phase per row
+  const float4* rr = reinterpret_cast<const float4*>(dres + (int64_t)row * D);
+  float4 xh[VPT], g[VPT], rres[VPT];
   float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) rres[i] = rr[lane + i * 32];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const float4 xv = xr[lane + i * 32];
@@ -110,12 +114,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
     s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
   }
   const float m1 = warp_sum(s1) * (1.f / D), m2 = warp_sum(s2) * (1.f / D);
-  const float4* rr = reinterpret_cast<const float4*>(dres + (int64_t)row * D);
   float4* dxr = reinterpret_cast<float4*>(dx + (int64_t)row * D);
   const float sc = row_scale != nullptr ? __ldg(row_scale + row / rows_per_scale) : 1.f;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
-    const float4 r = rr[lane + i * 32];
+    const float4 r = rres[i];
     float4 o;
     o.x = r.x + rs * (g[i].x - m1 - xh[i].x * m2);
     o.y = r.y + rs * (g[i].y - m1 - xh[i].y * m2);

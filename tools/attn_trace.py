@@ -67,22 +67,34 @@ def main():
     lib.sam3b_debug_trace_read(buf, n)
     t = list(buf)
     nb = (Ls + 63) // 64
-    # slots (csrc/attn_bwd.cu): compute thread 0 / 256 (group 0 / 1): 64 + j*8 + {0 start, 1 S^T/dP^T ready, 2 in registers,
-    # 3 math+pack done, 4 P^T/dS^T buffer free, 5 stored + signalled}; MMA thread: 1024 + j*4 + {0 S^T/dP^T(j) issued, 1 dV/dK(j) issued}
-    t0 = min(x for x in t[64:64 + 8 * min(nb, 64)] if x) if any(t[64:64 + 8 * min(nb, 64)]) else 0
-    print(json.dumps({"case": f"dkdv_{Ls}_{segs}_{heads}", "blocks": nb, "note": "first work item of CTA 70; clocks relative to its first stamp"}))
+    # slots (csrc/attn_bwd.cu), items 2 and 3 of CTA 70 (item 3 at +4096): compute thread 0 / 256 (group 0 / 1): 64 + j*8 +
+    # {0 start, 1 S^T/dP^T ready, 2 in registers, 3 math+pack done, 4 P^T/dS^T buffer free, 5 stored + signalled};
+    # MMA threads: 1024 + j*4 + {0 S^T/dP^T(j) issued, 1 dV/dK(j) issued};
+    # item transition per group g: 8 + g*8 + {0 block loop left, 1 kv_free seen, 2 next K/V parked, 3 all_done seen, 4 epilogue stored}
+    def rows_of(base):
+        out = []
+        for j in range(min(nb, 64)):
+            e = t[base + 64 + j * 8:base + 64 + j * 8 + 8]
+            m = t[base + 1024 + j * 4:base + 1024 + j * 4 + 4]
+            out.append((e, m))
+        return out
+    it2, it3 = rows_of(0), rows_of(4096)
+    t0 = min(x for e, m in it2 for x in list(e[:6]) + list(m[:2]) if x)
+    print(json.dumps({"case": f"dkdv_{Ls}_{segs}_{heads}", "blocks": nb, "note": "items 2 and 3 of CTA 70; clocks relative to item 2's first stamp"}))
     rows = []
-    for j in range(min(nb, 64)):
-        e = t[64 + j * 8:64 + j * 8 + 8]
-        m = t[1024 + j * 4:1024 + j * 4 + 4]
-        rows.append({"j": j, "grp": j & 1, "c_start": e[0] - t0, "c_wait_sdp": e[1] - e[0], "c_ld": e[2] - e[1], "c_math": e[3] - e[2],
-                     "c_wait_acc": e[4] - e[3], "c_store": e[5] - e[4], "m_sdp_issued": m[0] - t0, "m_dvdk_issued": m[1] - t0})
-    show = rows if len(rows) <= 12 else rows[:4] + rows[len(rows) // 2:len(rows) // 2 + 3] + rows[-3:]
+    for label, its in (("item2", it2), ("item3", it3)):
+        for j, (e, m) in enumerate(its):
+            rows.append({"item": label, "j": j, "grp": "?", "c_start": e[0] - t0, "c_wait_sdp": e[1] - e[0], "c_ld": e[2] - e[1], "c_math": e[3] - e[2],
+                         "c_wait_acc": e[4] - e[3], "c_store": e[5] - e[4], "m_sdp_issued": m[0] - t0, "m_dvdk_issued": m[1] - t0})
+    show = rows if len(rows) <= 24 else rows[:3] + rows[nb - 3:nb + 3] + rows[-2:]
     for r in show:
         print(json.dumps(r))
-    if len(rows) > 4:
-        per = (rows[-1]["m_dvdk_issued"] - rows[1]["m_dvdk_issued"]) / (len(rows) - 2)
-        print(json.dumps({"steady_clk_per_block": per}))
+    for g in (0, 1):
+        x = t[8 + g * 8:8 + g * 8 + 5]
+        print(json.dumps({"transition_item2_group": g, "loop_left": x[0] - t0, "kv_free_seen": x[1] - t0, "parked": x[2] - t0, "all_done_seen": x[3] - t0,
+                          "epilogue_stored": x[4] - t0}))
+    if nb > 2:
+        print(json.dumps({"item_period_clk": (it3[0][0][0] or 0) - (it2[0][0][0] or 0), "alt_period_from_mma": it3[0][1][0] - it2[0][1][0]}))
 
 
 if __name__ == "__main__":
