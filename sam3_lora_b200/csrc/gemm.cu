@@ -55,33 +55,42 @@ struct GemmCfg {
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 8 * STG_BYTES + 1024;
 };
 
-// Exact-erf GELU (nn.GELU default, timm Mlp): gelu(h) = h * Phi(h), Phi = standard normal CDF, with
-// Phi(-|h|) = 0.5 * erfc(|h|/sqrt 2) from Abramowitz-Stegun 7.1.26 (|abs error| <= 7.5e-8 on Phi):
-//   q = (b1 t + b2 t^2 + b3 t^3 + b4 t^4 + b5 t^5) * exp(-h^2/2),   t = 1 / (1 + p |h| / sqrt 2),  b_i = a_i / 2
-//   Phi(h) = h >= 0 ? 1 - q : q
-// 2 MUFU (rcp, ex2) + 12 FMA-pipe ops per element; exp(-h^2/2) is also the Gaussian term of GELU'.
-// The libdevice erff / __frcp_rn / exp2f forms cost 30-45 instructions per element, which made the
-// fc1 and fc2-dgrad epilogues slower than their MMAs (profiles/r01_ncu_gemm2_kernelILi3.txt).
-__device__ __forceinline__ void phi_neg_abs(float h, float& q, float& gauss) {
-  const float t = rcp_approx(fmaf(0.23164189f, fabsf(h), 1.f));   // 0.3275911 / sqrt(2)
-  gauss = ex2_approx(h * h * -0.72134752f);                        // exp(-h^2/2)
-  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
-  poly = fmaf(poly, t, 0.7107068705f);
-  poly = fmaf(poly, t, -0.142248368f);
-  poly = fmaf(poly, t, 0.127414796f);
-  q = poly * t * gauss;
-}
+// Exact-erf GELU (nn.GELU default, timm Mlp): gelu(h) = h * Phi(h), Phi = standard normal CDF.
+// Forward, one MUFU + 10 FMA/ALU ops per element:
+//   q = Phi(-|h|) = exp2(P(a)),  a = min(|h|, 6),  P = degree-7 fit of log2 Phi(-a)   (Phi(-6) = 1e-9)
+//   gelu(h) = max(h, 0) - |h| * q
+// Backward, one MUFU + 15 ops:
+//   g = exp(-h^2/2),  S(a) = Phi(-a)/g - a/sqrt(2 pi)  (degree-8 fit, error weighted by g)
+//   gelu'(h) = h < 0 ? g*S : 1 - g*S
+// Constants and their float32 error check come from tools/fit_gelu.py: |gelu error| <= 3e-7, |gelu' error| <= 1.1e-6
+// (the A&S 7.1.26 rational form used before had the same accuracy at 2 MUFU + 15 ops; libdevice erff costs 30-45).
+// The epilogue, not the MMA, paces the fc1 / fc2-dgrad GEMMs (profiles/r01_ncu_v3_gemm2_gelu.txt), so ops count.
 __device__ __forceinline__ float gelu_erf(float h) {
-  float q, g;
-  phi_neg_abs(h, q, g);
-  const float r = h * q;
-  return h >= 0.f ? h - r : r;
+  const float a = fminf(fabsf(h), 6.f);
+  float p = fmaf(-1.752960928e-06f, a, 6.019484742e-05f);
+  p = fmaf(p, a, -9.220063879e-04f);
+  p = fmaf(p, a, 8.487955181e-03f);
+  p = fmaf(p, a, -5.395627800e-02f);
+  p = fmaf(p, a, -4.584195313e-01f);
+  p = fmaf(p, a, -1.151296121e+00f);
+  p = fmaf(p, a, -9.999863347e-01f);
+  return fmaf(-fabsf(h), ex2_approx(p), fmaxf(h, 0.f));
 }
 __device__ __forceinline__ float dgelu_erf(float h) {
-  float q, g;
-  phi_neg_abs(h, q, g);
-  const float phi = h >= 0.f ? 1.f - q : q;
-  return fmaf(h * 0.39894228f, g, phi);
+  const float ah = fabsf(h);
+  const float a = fminf(ah, 6.f);
+  const float ap = ah * 0.84932180028801904f;   // sqrt(log2(e) / 2): g = exp2(-ap^2)
+  const float g = ex2_approx(-(ap * ap));
+  float s = fmaf(3.790287705e-05f, a, -6.153799106e-04f);
+  s = fmaf(s, a, 4.399772528e-03f);
+  s = fmaf(s, a, -1.882489903e-02f);
+  s = fmaf(s, a, 5.614903928e-02f);
+  s = fmaf(s, a, -1.299720504e-01f);
+  s = fmaf(s, a, 2.492791102e-01f);
+  s = fmaf(s, a, -7.978181042e-01f);
+  s = fmaf(s, a, 4.999989938e-01f);
+  const float gs = g * s;
+  return h < 0.f ? gs : 1.f - gs;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -468,11 +477,18 @@ struct Gemm2Cfg {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB (this CTA's half of the N tile)
   static constexpr int STAGES = 6;
   static constexpr int TCOLS = 512;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 256 + 8 * STG_BYTES + 1024;
+  // Epilogue warps: 8 (2 per scheduler).  Round-1 A/B on B200: 16 warps (4 per scheduler, <= 96 registers) and a GELU
+  // with a third fewer instructions both left the GELU / GELU' GEMMs at the same time relative to the plain-store GEMM
+  // (+25 % / +37 %), i.e. the epilogue is neither latency- nor issue-bound; the extra time tracks the extra 393 MB of
+  // HBM traffic per launch under the 1000 W power cap (SM clock 1.5-1.68 GHz of 1.965 during these runs).
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 256 + EPI_WARPS * STG_BYTES + 1024;
 };
 
 template <int EPI, int DT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
@@ -485,7 +501,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* full = bars;                 // used in the leader CTA only
   uint64_t* empty = bars + STAGES;       // in both CTAs (multicast commit)
   uint64_t* tfull = bars + 2 * STAGES;   // in both CTAs (multicast commit)
-  uint64_t* tempty = tfull + 2;          // used in the leader CTA only, 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint64_t* tempty = tfull + 2;          // used in the leader CTA only, one arrival per epilogue warp of both CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 256 + ((threadIdx.x >> 5) >= 4 ? ((threadIdx.x >> 5) - 4) * STG_BYTES : 0);
 
@@ -505,7 +521,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * Cfg::EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -563,7 +579,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp >= 4) {
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
     const int ew = warp & 3;
-    const int c_lo = ((warp - 4) >> 2) * (BN / 2);
+    const int c_lo = ((warp - 4) >> 2) * Cfg::COLS_PER_WARP;
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = cluster_id; w < total_work; w += n_clusters) {
       const int n_blk = w % n_tiles, m_pair = w / n_tiles;
@@ -572,7 +588,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int row0 = m_pair * 256 + (int)rank * 128 + ew * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = c_lo; c < c_lo + BN / 2; c += 32) {
+      for (int c = c_lo; c < c_lo + Cfg::COLS_PER_WARP; c += 32) {
         uint32_t r[32];
         tmem_ld_x32(t_row + c, r);
         tmem_ld_wait();
@@ -612,7 +628,7 @@ static int launch_pair(const GemmArgs& a, const GemmParams& p, cudaStream_t stre
   int clusters = (a.max_ctas > 0 ? a.max_ctas : num_sms()) / 2;
   if (clusters > total) clusters = total;
   if (clusters < 1) clusters = 1;
-  kern<<<2 * clusters, 384, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
   SAM3B_LAUNCHED();
   return 0;
 }
