@@ -45,7 +45,7 @@ extern "C" {
 #define SAM3B_EPI_GELU 3         /* C16 = h = acc+bias ; C2_16 = gelu_erf(h) */
 #define SAM3B_EPI_DGELU 4        /* C16 = acc * gelu_erf'(aux16) */
 #define SAM3B_EPI_ATOMIC_F32 5   /* C32 += alpha*acc (split-K, red.global.add) */
-#define SAM3B_EPI_STORE32 6      /* C32 = alpha*acc (+bias) */
+#define SAM3B_EPI_STORE32 6      /* C32 = [row_scale[row/rows_per_scale] *] (alpha*acc (+bias)) */
 #define SAM3B_EPI_ADDMASK16 7    /* C16 += dropout_mask/(1-p) * alpha*acc [* gelu_erf'(aux16)] */
 
 const char* sam3b_last_error(void);
@@ -88,6 +88,9 @@ int sam3b_layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const fl
                         const float* gamma, const float* dres, int32_t rows, int32_t D, float* dx, void* dx16,
                         int64_t lddx16, int32_t dtype, void* stream);
 int sam3b_cast_rows_16(const float* x, int32_t rows, int32_t D, void* y16, int64_t ldy, int32_t dtype, void* stream);
+/* same with a device-resident factor: y16 = (16-bit)(x * *scale)  (gradient scaling, see sam3b_grad_scale) */
+int sam3b_cast_rows_16_scaled(const float* x, int32_t rows, int32_t D, void* y16, int64_t ldy, int32_t dtype, const float* scale,
+                              void* stream);
 
 /* ---- attention (head_dim 64; tokens in window-major order so a window/image is a row run) --- */
 /* apply_rotary_enc + F.scaled_dot_product_attention, vitdet.py:68-90,485,502 (RoPE itself is the
@@ -202,6 +205,42 @@ int sam3b_focal_loss_fwd(const float* x, const float* y, int64_t n, float alpha,
 /* dx[i] = dL/dx[i] * gscale * (g ? g[i] : 1) */
 int sam3b_focal_loss_bwd(const float* x, const float* y, int64_t n, float alpha, float gamma, const float* g, float gscale,
                          float* dx, void* stream);
+
+/* ---- neck / pixel decoder / mask head helpers (row a8: sam3/model/necks.py:100-125, maskformer_segmentation.py:23-51,
+ * 203-219).  The convolutions run on sam3b_gemm; these are the HBM-bound kernels around it.  Activations: channels-last
+ * (NHWC) 16-bit; element-type codes below: 0 = 16-bit (per `dtype`), 1 = fp32. */
+/* scale[0] = 2^floor(log2(target/max|g|)) (1 if g == 0), scale[1] = 1/scale[0], scale[2] = scratch (device floats) */
+int sam3b_grad_scale(const float* g, int64_t n, float target, float* scale, void* stream);
+/* out[i] = (tout)(in[i] * *scale) (scale may be NULL); accumulate: out[i] += (fp32 out only); n % 4 == 0 */
+int sam3b_scale_cast(const void* in, int32_t tin, void* out, int32_t tout, int64_t n, int32_t dtype, const float* scale,
+                     int32_t accumulate, void* stream);
+/* in [batch][R][C] -> out [batch][C][R] (NCHW <-> NHWC; replaces the .permute()/.contiguous() pairs around the reference's convs) */
+int sam3b_transpose_cast(const void* in, int32_t tin, void* out, int32_t tout, int32_t batch, int32_t R, int32_t C, int32_t dtype,
+                         const float* scale, void* stream);
+/* 3x3 / padding 1 patch matrix: out16[(b,y,x)][(ky*3+kx)*C + c] = x16[b][y+ky-1][x+kx-1][c] (nn.Conv2d(.,.,3,padding=1), necks.py:84-92) */
+int sam3b_im2col3x3(const void* x16, int32_t B, int32_t H, int32_t W, int32_t C, void* out16, int64_t ldo, void* stream);
+/* nn.ConvTranspose2d(k=2,s=2) output placement (necks.py:44-62): in16 [B*H*W][4C] columns (di,dj,c) -> out16 [B][2H][2W][C], optional GELU */
+int sam3b_pixel_shuffle2(const void* in16, int32_t B, int32_t H, int32_t W, int32_t C, int32_t gelu, void* out16, int32_t dtype,
+                         void* stream);
+int sam3b_pixel_unshuffle2(const void* dy16, const void* h16, int32_t B, int32_t H, int32_t W, int32_t C, void* out16, int32_t dtype,
+                           void* stream);
+/* nn.MaxPool2d(2,2) (necks.py:66-69); the backward accumulates *scale * dy at the arg-max into the fp32 NHWC gradient */
+int sam3b_maxpool2_fwd(const void* x16, int32_t B, int32_t H, int32_t W, int32_t C, void* y16, int32_t dtype, void* stream);
+int sam3b_maxpool2_bwd(const void* x16, const void* dy16, int32_t B, int32_t H, int32_t W, int32_t C, const float* scale, float* dx32,
+                       int32_t dtype, void* stream);
+/* curr + F.interpolate(prev, size=curr.shape[-2:], mode="nearest") (maskformer_segmentation.py:208-210), integer factors */
+int sam3b_upsample_add(const void* prev16, int32_t h, int32_t w, const void* cur16, int32_t B, int32_t H, int32_t W, int32_t C,
+                       void* out16, int32_t dtype, void* stream);
+int sam3b_upsample_add_bwd(const void* dout16, int32_t B, int32_t H, int32_t W, int32_t C, int32_t h, int32_t w, void* dprev16,
+                           int32_t dtype, void* stream);
+/* F.relu(GroupNorm(G, C)(x)) on NHWC fp32 x [B][HW][C] (maskformer_segmentation.py:216-217).  work: 3*B*G doubles of scratch;
+ * stat: [B][G][2] fp32 (mean, rstd) */
+int sam3b_groupnorm_stats(const float* x, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, double* work, float* stat,
+                          void* stream);
+int sam3b_groupnorm_relu_fwd(const float* x, const float* stat, const float* gamma, const float* beta, int32_t B, int32_t HW,
+                             int32_t C, int32_t G, void* y, int32_t out_f32, int32_t dtype, void* stream);
+int sam3b_groupnorm_relu_bwd(const void* dy16, const float* x, const float* stat, const float* gamma, const float* beta, int32_t B,
+                             int32_t HW, int32_t C, int32_t G, double* work, void* dx16, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,7 @@ SIGNATURES: dict[str, tuple] = {
     "sam3b_layernorm_fwd": (C.c_int, [vp, vp, vp, f32, i32, i32, vp, i64, i32, vp, vp, vp]),
     "sam3b_layernorm_bwd": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, i32, i32, vp, vp, i64, i32, vp]),
     "sam3b_cast_rows_16": (C.c_int, [vp, i32, i32, vp, i64, i32, vp]),
+    "sam3b_cast_rows_16_scaled": (C.c_int, [vp, i32, i32, vp, i64, i32, vp, vp]),
     "sam3b_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), vp]),
     "sam3b_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), vp]),
     "sam3b_patch_gather": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, i64, i32, i32, vp]),
@@ -51,6 +52,19 @@ SIGNATURES: dict[str, tuple] = {
     "sam3b_focal_loss_fwd": (C.c_int, [vp, vp, i64, f32, f32, vp, vp, vp]),
     "sam3b_focal_loss_bwd": (C.c_int, [vp, vp, i64, f32, f32, vp, f32, vp, vp]),
     "sam3b_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]),
+    "sam3b_grad_scale": (C.c_int, [vp, i64, f32, vp, vp]),
+    "sam3b_scale_cast": (C.c_int, [vp, i32, vp, i32, i64, i32, vp, i32, vp]),
+    "sam3b_transpose_cast": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "sam3b_im2col3x3": (C.c_int, [vp, i32, i32, i32, i32, vp, i64, vp]),
+    "sam3b_pixel_shuffle2": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "sam3b_pixel_unshuffle2": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, i32, vp]),
+    "sam3b_maxpool2_fwd": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, vp]),
+    "sam3b_maxpool2_bwd": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "sam3b_upsample_add": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
+    "sam3b_upsample_add_bwd": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "sam3b_groupnorm_stats": (C.c_int, [vp, i32, i32, i32, i32, f32, vp, vp, vp]),
+    "sam3b_groupnorm_relu_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
+    "sam3b_groupnorm_relu_bwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]),
 }
 
 

@@ -159,10 +159,26 @@ def layernorm_bwd(dy16, x, mean, rstd, gamma, dres, dx, dx16=None):
                                      torch_dtype_code(dy16.dtype), current_stream()))
 
 
-def cast_rows_16(x, y16):
+def cast_rows_16(x, y16, scale=None):
+    """y16[:, :D] = (16-bit)(x * *scale); scale: optional 1-element fp32 device tensor."""
     rows, D = x.shape
-    check(load().sam3b_cast_rows_16(ptr(x), rows, D, ptr(y16), y16.stride(0), torch_dtype_code(y16.dtype),
-                                    current_stream()))
+    check(load().sam3b_cast_rows_16_scaled(ptr(x), rows, D, ptr(y16), y16.stride(0), torch_dtype_code(y16.dtype), ptr(scale),
+                                           current_stream()))
+
+
+GRAD_SCALE_TARGET = 256.0
+ALL_ROWS = 1 << 30   # rows_per_scale that maps every GEMM row to row_scale[0]
+
+
+def grad_scale(g, target: float = GRAD_SCALE_TARGET):
+    """Device-resident fp32 [s, 1/s, scratch, -] with s = 2^floor(log2(target / max|g|)) (1 for g == 0).  Every backward
+    chain here is linear in the incoming gradient, so it runs on s*g (fp16 operands neither overflow nor flush a
+    mean-reduced loss gradient to zero) and the last kernel multiplies by 1/s; nothing is read back to the host."""
+    import torch  # noqa: PLC0415
+
+    scale = torch.empty(4, device=g.device, dtype=torch.float32)
+    check(load().sam3b_grad_scale(ptr(g), g.numel(), float(target), ptr(scale), current_stream()))
+    return scale
 
 
 def _attn_desc(qkv, seg_len, D, heads, O, lse2):

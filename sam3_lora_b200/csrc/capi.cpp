@@ -3,6 +3,7 @@
 
 #include "common.h"
 #include "attn.cuh"
+#include "conv.cuh"
 #include "elementwise.cuh"
 #include "engine.h"
 #include "gemm.cuh"
@@ -51,6 +52,10 @@ int sam3b_layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const fl
 }
 int sam3b_cast_rows_16(const float* x, int32_t rows, int32_t D, void* y16, int64_t ldy, int32_t dtype, void* stream) {
   return cast_rows_16(x, rows, D, y16, ldy, dtype, static_cast<cudaStream_t>(stream));
+}
+int sam3b_cast_rows_16_scaled(const float* x, int32_t rows, int32_t D, void* y16, int64_t ldy, int32_t dtype, const float* scale,
+                              void* stream) {
+  return cast_rows_16(x, rows, D, y16, ldy, dtype, static_cast<cudaStream_t>(stream), scale);
 }
 
 static AttnArgs to_attn_args(const sam3b_attn_desc* d) {
@@ -196,6 +201,56 @@ int sam3b_focal_loss_bwd(const float* x, const float* y, int64_t n, float alpha,
                          float* dx, void* stream) {
   return focal_loss_bwd(x, y, n, alpha, gamma, g, gscale, dx, static_cast<cudaStream_t>(stream));
 }
+
+#define SAM3B_ST static_cast<cudaStream_t>(stream)
+int sam3b_grad_scale(const float* g, int64_t n, float target, float* scale, void* stream) { return grad_scale(g, n, target, scale, SAM3B_ST); }
+int sam3b_scale_cast(const void* in, int32_t tin, void* out, int32_t tout, int64_t n, int32_t dtype, const float* scale,
+                     int32_t accumulate, void* stream) {
+  return scale_cast(in, tin, out, tout, n, dtype, scale, accumulate, SAM3B_ST);
+}
+int sam3b_transpose_cast(const void* in, int32_t tin, void* out, int32_t tout, int32_t batch, int32_t R, int32_t C, int32_t dtype,
+                         const float* scale, void* stream) {
+  return transpose_cast(in, tin, out, tout, batch, R, C, dtype, scale, SAM3B_ST);
+}
+int sam3b_im2col3x3(const void* x16, int32_t B, int32_t H, int32_t W, int32_t C, void* out16, int64_t ldo, void* stream) {
+  return im2col3x3(x16, B, H, W, C, out16, ldo, SAM3B_ST);
+}
+int sam3b_pixel_shuffle2(const void* in16, int32_t B, int32_t H, int32_t W, int32_t C, int32_t gelu, void* out16, int32_t dtype,
+                         void* stream) {
+  return pixel_shuffle2(in16, B, H, W, C, gelu, out16, dtype, SAM3B_ST);
+}
+int sam3b_pixel_unshuffle2(const void* dy16, const void* h16, int32_t B, int32_t H, int32_t W, int32_t C, void* out16, int32_t dtype,
+                           void* stream) {
+  return pixel_unshuffle2(dy16, h16, B, H, W, C, out16, dtype, SAM3B_ST);
+}
+int sam3b_maxpool2_fwd(const void* x16, int32_t B, int32_t H, int32_t W, int32_t C, void* y16, int32_t dtype, void* stream) {
+  return maxpool2_fwd(x16, B, H, W, C, y16, dtype, SAM3B_ST);
+}
+int sam3b_maxpool2_bwd(const void* x16, const void* dy16, int32_t B, int32_t H, int32_t W, int32_t C, const float* scale, float* dx32,
+                       int32_t dtype, void* stream) {
+  return maxpool2_bwd(x16, dy16, B, H, W, C, scale, dx32, dtype, SAM3B_ST);
+}
+int sam3b_upsample_add(const void* prev16, int32_t h, int32_t w, const void* cur16, int32_t B, int32_t H, int32_t W, int32_t C,
+                       void* out16, int32_t dtype, void* stream) {
+  return upsample_add(prev16, h, w, cur16, B, H, W, C, out16, dtype, SAM3B_ST);
+}
+int sam3b_upsample_add_bwd(const void* dout16, int32_t B, int32_t H, int32_t W, int32_t C, int32_t h, int32_t w, void* dprev16,
+                           int32_t dtype, void* stream) {
+  return upsample_add_bwd(dout16, B, H, W, C, h, w, dprev16, dtype, SAM3B_ST);
+}
+int sam3b_groupnorm_stats(const float* x, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, double* work, float* stat,
+                          void* stream) {
+  return groupnorm_stats(x, B, HW, C, G, eps, work, stat, SAM3B_ST);
+}
+int sam3b_groupnorm_relu_fwd(const float* x, const float* stat, const float* gamma, const float* beta, int32_t B, int32_t HW,
+                             int32_t C, int32_t G, void* y, int32_t out_f32, int32_t dtype, void* stream) {
+  return groupnorm_relu_fwd(x, stat, gamma, beta, B, HW, C, G, y, out_f32, dtype, SAM3B_ST);
+}
+int sam3b_groupnorm_relu_bwd(const void* dy16, const float* x, const float* stat, const float* gamma, const float* beta, int32_t B,
+                             int32_t HW, int32_t C, int32_t G, double* work, void* dx16, int32_t dtype, void* stream) {
+  return groupnorm_relu_bwd(dy16, x, stat, gamma, beta, B, HW, C, G, work, dx16, dtype, SAM3B_ST);
+}
+#undef SAM3B_ST
 
 #ifdef SAM3B_TRACE
 int sam3b_debug_trace_read(unsigned long long* host, int n) { return attn_trace_read(host, n); }

@@ -132,11 +132,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
 
 template <int DT>
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ x, int rows, int D,
-                                                        uint16_t* __restrict__ y, int64_t ldy) {
+                                                        uint16_t* __restrict__ y, int64_t ldy, const float* __restrict__ scale) {
   const int64_t n4 = (int64_t)rows * (D / 4);
+  const float sc = scale != nullptr ? __ldg(scale) : 1.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int row = (int)(i / (D / 4)), c4 = (int)(i % (D / 4));
-    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
     reinterpret_cast<uint2*>(y + (int64_t)row * ldy)[c4] = pack4<DT>(v.x, v.y, v.z, v.w);
   }
 }
@@ -218,8 +220,10 @@ __global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const float* __rest
 template <int DT>
 __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __restrict__ g, int G, int ws, int D,
                                                              float* __restrict__ dx, uint16_t* __restrict__ dx16,
-                                                             int64_t ld16, const float* __restrict__ img_scale) {
+                                                             int64_t ld16, const float* __restrict__ img_scale,
+                                                             const float* __restrict__ gscale) {
   __shared__ float tile[32][33];
+  const float gs = gscale != nullptr ? __ldg(gscale) : 1.f;
   const int T = G * G, nwx = G / ws;
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __rest
     if (s < T) {
       const int pi = s / G, pj = s % G;
       const int tok = ((pi / ws) * nwx + pj / ws) * (ws * ws) + (pi % ws) * ws + (pj % ws);
-      const float v = tile[tx][i];
+      const float v = tile[tx][i] * gs;
       const int64_t r = (int64_t)b * T + tok;
       dx[r * D + d0 + tx] = v;
       if (dx16 != nullptr) {
@@ -284,19 +288,21 @@ struct UnpackArgs {
   LoraSite s;
   const float* dA_pack; const float* dB_pack;
   float* dA[3]; float* dB[3];
+  const float* out_scale;
 };
 __global__ void __launch_bounds__(256) lora_unpack_kernel(const UnpackArgs a) {
   const LoraSite& s = a.s;
+  const float sc = a.out_scale != nullptr ? __ldg(a.out_scale) : 1.f;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int ad = 0; ad < s.n; ++ad) {
     for (int64_t i = tid; i < (int64_t)s.in * s.r; i += stride) {
       const int k = (int)(i / s.r), j = (int)(i % s.r);
-      a.dA[ad][i] = a.dA_pack[(int64_t)k * s.rpad + ad * s.r + j];
+      a.dA[ad][i] = sc * a.dA_pack[(int64_t)k * s.rpad + ad * s.r + j];
     }
     for (int64_t i = tid; i < (int64_t)s.r * s.out_len[ad]; i += stride) {
       const int j = (int)(i / s.out_len[ad]), n = (int)(i % s.out_len[ad]);
-      a.dB[ad][i] = a.dB_pack[(int64_t)(ad * s.r + j) * s.out_total + s.out_off[ad] + n];
+      a.dB[ad][i] = sc * a.dB_pack[(int64_t)(ad * s.r + j) * s.out_total + s.out_off[ad] + n];
     }
   }
 }
@@ -493,12 +499,12 @@ int dropout_rows16(const void* x16, int64_t ldx, int rows, int cols, void* out16
   return 0;
 }
 
-int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s) {
+int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s, const float* scale) {
   SAM3B_REQUIRE(D % 4 == 0 && ldy % 4 == 0, "cast: D and ldy must be multiples of 4");
   const int64_t n4 = (int64_t)rows * (D / 4);
   const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)num_sms() * 16);
-  if (dtype == 0) cast_rows_kernel<0><<<blocks, 256, 0, s>>>(x, rows, D, (uint16_t*)y16, ldy);
-  else cast_rows_kernel<1><<<blocks, 256, 0, s>>>(x, rows, D, (uint16_t*)y16, ldy);
+  if (dtype == 0) cast_rows_kernel<0><<<blocks, 256, 0, s>>>(x, rows, D, (uint16_t*)y16, ldy, scale);
+  else cast_rows_kernel<1><<<blocks, 256, 0, s>>>(x, rows, D, (uint16_t*)y16, ldy, scale);
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -540,11 +546,11 @@ int tokens_to_nchw(const float* x, int B, int G, int ws, int D, float* out, cuda
 }
 
 int nchw_to_tokens(const float* g, int B, int G, int ws, int D, float* dx, void* dx16, int64_t ld16, int dtype,
-                   cudaStream_t s, const float* img_scale) {
+                   cudaStream_t s, const float* img_scale, const float* gscale) {
   SAM3B_REQUIRE(D % 32 == 0 && G % ws == 0, "nchw_to_tokens: D %% 32, G %% ws");
   dim3 grid((G * G + 31) / 32, D / 32, B);
-  if (dtype == 0) nchw_to_tokens_kernel<0><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16, img_scale);
-  else nchw_to_tokens_kernel<1><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16, img_scale);
+  if (dtype == 0) nchw_to_tokens_kernel<0><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16, img_scale, gscale);
+  else nchw_to_tokens_kernel<1><<<grid, 256, 0, s>>>(g, G, ws, D, dx, (uint16_t*)dx16, ld16, img_scale, gscale);
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -562,9 +568,9 @@ int lora_pack(const LoraSite& site, void* down_T, void* w_ext, int64_t ldw, void
 }
 
 int lora_unpack_grads(const LoraSite& site, const float* dA_pack, const float* dB_pack, float* const dA[3],
-                      float* const dB[3], cudaStream_t s) {
+                      float* const dB[3], cudaStream_t s, const float* out_scale) {
   UnpackArgs a{};
-  a.s = site; a.dA_pack = dA_pack; a.dB_pack = dB_pack;
+  a.s = site; a.dA_pack = dA_pack; a.dB_pack = dB_pack; a.out_scale = out_scale;
   for (int i = 0; i < 3; ++i) { a.dA[i] = dA[i]; a.dB[i] = dB[i]; }
   const int64_t work = (int64_t)site.r * std::max(site.in, site.out_total);
   const int blocks = (int)std::min<int64_t>((work + 255) / 256, 512);

@@ -34,7 +34,8 @@ int dropout_rows16(const void* x16, int64_t ldx, int rows, int cols, void* out16
                    int dtype, cudaStream_t s);
 
 // y16[row][0..D) = (16-bit) x[row][0..D)
-int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s);
+// scale (device scalar, optional): y16 = (16-bit)(x * *scale)
+int cast_rows_16(const float* x, int rows, int D, void* y16, int64_t ldy, int dtype, cudaStream_t s, const float* scale = nullptr);
 
 // delta[h][row] = sum_c dO[row][h*64+c] * O[row][h*64+c]   (head-major)
 // delta[h][seg*Lq_stat + i] for row = seg*Lq + i (Lq_stat = Lq rounded up to 64; pass Lq = rows for one flat segment)
@@ -50,8 +51,9 @@ int patch_gather(const float* img, int B, int C, int Himg, int Wimg, int P, int 
 // Window-major token stream [B][T][D] fp32 <-> NCHW feature map [B][D][G][G] (vitdet.py:847-857).
 int tokens_to_nchw(const float* x, int B, int G, int ws, int D, float* out, cudaStream_t s);
 // and back (gradient path): also emits the 16-bit copy used as the first dgrad operand.
+// gscale (device scalar, optional) multiplies both outputs (gradient scaling of the trunk backward).
 int nchw_to_tokens(const float* g, int B, int G, int ws, int D, float* dx, void* dx16, int64_t ld16, int dtype,
-                   cudaStream_t s, const float* img_scale = nullptr);
+                   cudaStream_t s, const float* img_scale = nullptr, const float* gscale = nullptr);
 
 // ---- LoRA packing -------------------------------------------------------------------------
 // One adapted Linear (in -> out_total) with n adapters of rank r that each own the output
@@ -71,8 +73,9 @@ struct LoraSite {
 int lora_pack(const LoraSite& site, void* down_T, void* w_ext, int64_t ldw, void* up_pack, void* wt_ext,
               int64_t ldwt, int dtype, cudaStream_t s);
 // dA_a[k][j] = dA_pack[k][a*r+j] ; dB_a[j][n] = dB_pack[a*r+j][off_a+n]   (fp32)
+// out_scale (device scalar, optional) multiplies every element written.
 int lora_unpack_grads(const LoraSite& site, const float* dA_pack, const float* dB_pack, float* const dA[3],
-                      float* const dB[3], cudaStream_t s);
+                      float* const dB[3], cudaStream_t s, const float* out_scale = nullptr);
 
 // Fused AdamW over a flat fp32 buffer (torch.optim.AdamW semantics, train_sam3_lora_native.py:736-740).
 int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -20,6 +20,7 @@
 
 #include "attn.cuh"
 #include "common.h"
+#include "conv.cuh"
 #include "gemm.cuh"
 #include "rng.cuh"
 
@@ -162,6 +163,7 @@ void VitEngine::layout_work(Bump& b, int batch, bool training) {
     const int max_feat = std::max(3 * D_, Dm_);
     dA_pack_ = b.take<float>((int64_t)max_feat * std::max(Rmax_, 1));
     dB_pack_ = b.take<float>((int64_t)max_feat * std::max(Rmax_, 1));
+    gscale_ = b.take<float>(4);
   }
 }
 
@@ -362,7 +364,7 @@ int VitEngine::site_wgrad(const Site& st, const uint16_t* x_act, int64_t ldx, co
     dA[a] = grad_flat + e.a_off;
     dB[a] = grad_flat + e.b_off;
   }
-  return lora_unpack_grads(make_site(st, nullptr), dA_pack_, dB_pack_, dA, dB, s);
+  return lora_unpack_grads(make_site(st, nullptr), dA_pack_, dB_pack_, dA, dB, s, gscale_ + 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -476,7 +478,11 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
   const float* ds = fwd_drop_scales_;
   const int Bn = last_batch_;
   auto drop = [&](int blk, int branch) -> const float* { return ds ? ds + (int64_t)(2 * blk + branch) * Bn : nullptr; };
-  if ((rc = nchw_to_tokens(gout_nchw, last_batch_, G_, cfg_.window_size, D_, dx, dx16_, ld_dx16, dt, s, drop(cfg_.depth - 1, 1)))) return rc;
+  // The whole backward is linear in gout, so it runs on s * gout with s a power of two chosen on the device from
+  // max|gout| (fp16 operands would otherwise flush a mean-reduced loss gradient, ~1e-9 per element, to zero); the
+  // LoRA gradients are multiplied by 1/s when they are unpacked into grad_flat.
+  if ((rc = grad_scale(gout_nchw, (int64_t)last_batch_ * D_ * T_, 256.f, gscale_, s))) return rc;
+  if ((rc = nchw_to_tokens(gout_nchw, last_batch_, G_, cfg_.window_size, D_, dx, dx16_, ld_dx16, dt, s, drop(cfg_.depth - 1, 1), gscale_))) return rc;
 
   // dst16[:, out .. out+R) = s * dy[:, :out] . B^T      (skinny GEMM; B operand = up_pack [R][out])
   auto site_up_grad = [&](const Site& st, uint16_t* dy, int64_t ld) -> int {

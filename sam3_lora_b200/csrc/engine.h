@@ -105,6 +105,7 @@ class VitEngine {
   std::vector<float*> x_;  // residual stream, x_[i] = input of block i, x_[depth] = output
   std::vector<BlockAct> acts_;
   float *dxa_ = nullptr, *dxb_ = nullptr, *delta_ = nullptr, *dA_pack_ = nullptr, *dB_pack_ = nullptr;
+  float* gscale_ = nullptr;   // device [s, 1/s, scratch]: power-of-two scale of the incoming gradient (grad_scale, conv.cuh)
   uint16_t *dx16_ = nullptr, *dh16_ = nullptr, *dxn16_ = nullptr, *dO16_ = nullptr, *dqkv16_ = nullptr;
   int Rmax_ = 0;
   float drop_p_ = 0.f, fwd_drop_p_ = 0.f;

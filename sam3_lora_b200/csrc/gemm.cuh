@@ -13,7 +13,7 @@ enum GemmEpilogue : int {
   EPI_GELU = 3,          // C16 = h = acc + bias ; C2_16 = gelu_erf(h)
   EPI_DGELU = 4,         // C16 = acc * gelu_erf'(aux16)
   EPI_ATOMIC_F32 = 5,    // C32 (+)= alpha*acc with red.global.add (split-K), optional transpose
-  EPI_STORE32 = 6,       // C32 = alpha*acc (+bias)
+  EPI_STORE32 = 6,       // C32 = [row_scale[row/rows_per_scale] *] (alpha*acc (+bias))
   EPI_ADDMASK16 = 7,     // C16 += keep(row,col)/(1-p) * alpha*acc [* gelu_erf'(aux16)]   (adapter dgrad under dropout)
   EPI_COUNT
 };

@@ -66,14 +66,17 @@ class _AttnCoreFn(torch.autograd.Function):
         Ep = heads * 64
         dev = gO.device
         dO16 = torch.empty(nseg * Lq, Ep, device=dev, dtype=q16.dtype)
-        L.cast_rows_16(gO.float().contiguous(), dO16)
+        g32 = gO.float().contiguous()
+        sc = L.grad_scale(g32)                    # backward on s*gO (linear in gO), outputs times 1/s; see _lib.grad_scale
+        L.cast_rows_16(g32, dO16, sc[0:1])
         delta = torch.zeros_like(lse2)
         dq16 = torch.empty(nseg * Lq, Ep, device=dev, dtype=q16.dtype)
         dkv16 = torch.empty(nseg * Lk, 2 * Ep, device=dev, dtype=q16.dtype)
         d = L.mha_desc(q16, kv16, nseg, Lq, Lk, heads, scale, O16, lse2, bias=bias if has_bias else None,
                        kpm=kpm if has_kpm else None, drop_p=drop_p, drop_seed=seed)
         L.mha_bwd(d, dO16, delta, dq16, dkv16)
-        return (dq16.float().to(qdt), dkv16[:, :Ep].float().to(qdt), dkv16[:, Ep:].float().to(qdt),
+        inv = sc[1:2]
+        return ((dq16.float() * inv).to(qdt), (dkv16[:, :Ep].float() * inv).to(qdt), (dkv16[:, Ep:].float() * inv).to(qdt),
                 None, None, None, None, None, None, None, None, None)
 
 

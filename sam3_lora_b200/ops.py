@@ -117,20 +117,22 @@ class _LoRALinearFn(torch.autograd.Function):
         dt = xd16.dtype
         g2 = gy.reshape(-1, out_f).float().contiguous()
         M = g2.shape[0]
+        sc = L.grad_scale(g2)                      # the chain below runs on s*gy; outputs are multiplied by 1/s (on the device)
+        s_in, s_out = sc[0:1], sc[1:2]
         dy16 = torch.empty(M, out_f + R, device=gy.device, dtype=dt)
-        L.cast_rows_16(g2, dy16)
+        L.cast_rows_16(g2, dy16, s_in)
         if R > 0:
             L.gemm(dy16[:, :out_f], up_pack, dy16[:, out_f:], epilogue=L.EPI_STORE16, alpha=scaling, bn=64)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, in_f, device=gy.device, dtype=torch.float32)
             if dropout_p > 0.0:
-                L.gemm(dy16[:, :out_f], wt_ext[:, :out_f], dx, epilogue=L.EPI_STORE32)
+                L.gemm(dy16[:, :out_f], wt_ext[:, :out_f], dx, epilogue=L.EPI_STORE32, row_scale=s_out, rows_per_scale=L.ALL_ROWS)
                 dxl = torch.empty(M, in_f, device=gy.device, dtype=torch.float32)
-                L.gemm(dy16[:, out_f:], wt_ext[:, out_f:], dxl, epilogue=L.EPI_STORE32)
+                L.gemm(dy16[:, out_f:], wt_ext[:, out_f:], dxl, epilogue=L.EPI_STORE32, row_scale=s_out, rows_per_scale=L.ALL_ROWS)
                 dx += dxl * mask.float()
             else:
-                L.gemm(dy16, wt_ext, dx, epilogue=L.EPI_STORE32)
+                L.gemm(dy16, wt_ext, dx, epilogue=L.EPI_STORE32, row_scale=s_out, rows_per_scale=L.ALL_ROWS)
             dx = dx.reshape(*lead, in_f).to(xdtype)
         if R == 0:
             return dx, None, None, None, None, None, None
@@ -142,8 +144,8 @@ class _LoRALinearFn(torch.autograd.Function):
                splitk=sk, c_trans=True)
         L.gemm(xd16[:, :in_f], dy16[:, out_f:], dA_pack, epilogue=L.EPI_ATOMIC_F32, a_mn=True, b_mn=True, M=in_f, N=R, K=M,
                splitk=sk)
-        dA = dA_pack[:, :r].contiguous().to(pdtype)
-        dB = dB_pack[:r].contiguous().to(pdtype)
+        dA = (dA_pack[:, :r] * s_out).to(pdtype)
+        dB = (dB_pack[:r] * s_out).to(pdtype)
         return dx, None, None, dA, dB, None, None
 
 

@@ -26,6 +26,23 @@ def test_lora_linear_matches_reference_golden():
     assert rel_l2(B.grad.cpu(), t["dB"].cpu()) < 2e-3
 
 
+def test_lora_linear_tiny_and_huge_cotangents():
+    """Backward runs on a device-chosen power-of-two multiple of the cotangent (fp16 operands): 1e-10 and 1e7 scale alike."""
+    from sam3_lora_b200.ops import lora_linear
+
+    z = np.load(GOLDEN / "lora_linear.npz")
+    t = {k: torch.from_numpy(z[k]).cuda() for k in z.files if k != "scaling"}
+    s = float(z["scaling"])
+    for k in (1.0e-10, 1.0e7):
+        x = t["x"].clone().requires_grad_(True)
+        A = t["A"].clone().requires_grad_(True)
+        B = t["B"].clone().requires_grad_(True)
+        (lora_linear(x, t["W"], t["b"], A, B, s) * (t["gy"] * k)).sum().backward()
+        assert rel_l2(x.grad.cpu() / k, t["dx"].cpu()) < 2e-3
+        assert rel_l2(A.grad.cpu() / k, t["dA"].cpu()) < 2e-3
+        assert rel_l2(B.grad.cpu() / k, t["dB"].cpu()) < 2e-3
+
+
 def test_lora_linear_module_detr_shape_and_small_batch():
     """d=256 Linear as in the DETR / seg-head projections, 3-D input, tiny row count (M < one MMA tile)."""
     from sam3_lora_b200.lora_layers import LoRALinear

@@ -94,6 +94,24 @@ def test_small_vit_matches_reference_golden():
         assert e < GRAD_TOL, (k, e)
 
 
+def test_tiny_output_gradient_survives_fp16_operands():
+    """A mean-reduced loss over 1008^2 masks hands the trunk cotangents of ~1e-9 per element, below fp16's smallest
+    subnormal (6e-8).  The backward runs on a power-of-two multiple chosen on the device (grad_scale) and the LoRA
+    gradients come back un-scaled: the result must be the golden gradient times the same factor, to the usual tolerance."""
+    g = load_small_golden()
+    eng = _engine_for(g["cfg"], g["spec"], g["params"])
+    k = 3.0e-9
+    _, grads = _run(eng, g["cfg"], g["params"], g["img"], g["gout"] * k)
+    errs = {n: rel_l2(grads[n] / k, ref) for n, ref in g["grads"].items()}
+    _report("small_golden_fp16_tiny_gout", {"grad_rel_l2_max": max(errs.values())})
+    for n, e in errs.items():
+        assert e < GRAD_TOL, (n, e)
+    # and a huge one (would overflow fp16 un-scaled)
+    _, grads = _run(eng, g["cfg"], g["params"], g["img"], g["gout"] * 1.0e6)
+    for n, ref in g["grads"].items():
+        assert rel_l2(grads[n] / 1.0e6, ref) < GRAD_TOL, n
+
+
 def test_small_vit_bf16_operands_run_and_are_close():
     g = load_small_golden()
     eng = _engine_for(g["cfg"], g["spec"], g["params"], dtype=torch.bfloat16)
