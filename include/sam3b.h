@@ -206,6 +206,34 @@ int sam3b_focal_loss_fwd(const float* x, const float* y, int64_t n, float alpha,
 int sam3b_focal_loss_bwd(const float* x, const float* y, int64_t n, float alpha, float gamma, const float* g, float gscale,
                          float* dx, void* stream);
 
+/* ---- fused mask losses: bilinear up-sampling (align_corners=False) of the matched mask logits to the target size + sigmoid
+ * focal + dice in one pass over the targets (sam3/train/loss/loss_fns.py:105-123, 126-176, 689-707).  src [N][h][w] fp32, tgt
+ * [N][H][W] uint8 (tgt_u8 != 0) or fp32; partial: N*ceil(H/8)*4 floats scratch; sums [N][4] kept for the backward;
+ * out[0] = loss_mask, out[1] = loss_dice (already / num_boxes). */
+int sam3b_mask_loss_fwd(const float* src, int32_t N, int32_t h, int32_t w, const void* tgt, int32_t tgt_u8, int32_t H, int32_t W,
+                        float alpha, float gamma, float num_boxes, float* partial, float* sums, float* out, void* stream);
+/* dsrc = g[0] * d loss_mask/d src + g[1] * d loss_dice/d src; g: two device floats (no host read-back) */
+int sam3b_mask_loss_bwd(const float* src, int32_t N, int32_t h, int32_t w, const void* tgt, int32_t tgt_u8, int32_t H, int32_t W,
+                        float alpha, float gamma, float num_boxes, const float* sums, const float* g, float* dsrc, void* stream);
+
+/* ---- GPU-resident Hungarian matcher: BinaryHungarianMatcherV2.forward + _do_matching (sam3/train/matcher.py:15-29, 431-668)
+ * without the .cpu().numpy() copy and the per-image scipy.optimize.linear_sum_assignment call. */
+typedef struct sam3b_matcher_desc {
+  int32_t B, Q, Tmax, repeats;
+  const float* logits;          /* [B][Q] */
+  const float* pred_boxes;      /* [B][Q][4] cxcywh */
+  const float* tgt_boxes;       /* [B][Tmax][4] cxcywh (boxes_padded) */
+  const int32_t* num_boxes;     /* [B] */
+  const uint8_t* out_valid;     /* [B][Q] or NULL */
+  const uint8_t* tgt_valid;     /* [B][Tmax] or NULL */
+  float w_class, w_bbox, w_giou;
+  int32_t focal, stable;
+  float alpha, gamma;
+} sam3b_matcher_desc;
+/* cost [B][Q][Tmax] fp32 (output);  query_of_col [B][max(1,Tmax*repeats)] and col_of_query [B][Q] (int32, -1 = unmatched);
+ * column c of image b is target c % num_boxes[b] (np.tile of the cost matrix when repeats > 1) */
+int sam3b_matcher(const sam3b_matcher_desc* d, float* cost, int32_t* query_of_col, int32_t* col_of_query, void* stream);
+
 /* ---- neck / pixel decoder / mask head helpers (row a8: sam3/model/necks.py:100-125, maskformer_segmentation.py:23-51,
  * 203-219).  The convolutions run on sam3b_gemm; these are the HBM-bound kernels around it.  Activations: channels-last
  * (NHWC) 16-bit; element-type codes below: 0 = 16-bit (per `dtype`), 1 = fp32. */

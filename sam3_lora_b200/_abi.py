@@ -35,6 +35,16 @@ class LoraSite(C.Structure):
     ]
 
 
+class MatcherDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("Q", i32), ("Tmax", i32), ("repeats", i32),
+        ("logits", vp), ("pred_boxes", vp), ("tgt_boxes", vp), ("num_boxes", vp), ("out_valid", vp), ("tgt_valid", vp),
+        ("w_class", f32), ("w_bbox", f32), ("w_giou", f32),
+        ("focal", i32), ("stable", i32),
+        ("alpha", f32), ("gamma", f32),
+    ]
+
+
 # name -> (restype, argtypes)
 SIGNATURES: dict[str, tuple] = {
     "sam3b_layernorm_fwd": (C.c_int, [vp, vp, vp, f32, i32, i32, vp, i64, i32, vp, vp, vp]),
@@ -51,6 +61,9 @@ SIGNATURES: dict[str, tuple] = {
     "sam3b_dropout_rows16": (C.c_int, [vp, i64, i32, i32, vp, i64, f32, C.c_uint32, i32, vp]),
     "sam3b_focal_loss_fwd": (C.c_int, [vp, vp, i64, f32, f32, vp, vp, vp]),
     "sam3b_focal_loss_bwd": (C.c_int, [vp, vp, i64, f32, f32, vp, f32, vp, vp]),
+    "sam3b_mask_loss_fwd": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp]),
+    "sam3b_mask_loss_bwd": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp]),
+    "sam3b_matcher": (C.c_int, [C.POINTER(MatcherDesc), vp, vp, vp, vp]),
     "sam3b_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]),
     "sam3b_grad_scale": (C.c_int, [vp, i64, f32, vp, vp]),
     "sam3b_scale_cast": (C.c_int, [vp, i32, vp, i32, i64, i32, vp, i32, vp]),

@@ -8,6 +8,7 @@
 #include "engine.h"
 #include "gemm.cuh"
 #include "loss.cuh"
+#include "matcher.cuh"
 
 #ifdef SAM3B_TRACE
 namespace sam3b { int attn_trace_read(unsigned long long*, int); int attn_trace_clear(); int attn_trace_read_fwd(unsigned long long*, int); }
@@ -200,6 +201,26 @@ int sam3b_focal_loss_fwd(const float* x, const float* y, int64_t n, float alpha,
 int sam3b_focal_loss_bwd(const float* x, const float* y, int64_t n, float alpha, float gamma, const float* g, float gscale,
                          float* dx, void* stream) {
   return focal_loss_bwd(x, y, n, alpha, gamma, g, gscale, dx, static_cast<cudaStream_t>(stream));
+}
+
+int sam3b_mask_loss_fwd(const float* src, int32_t N, int32_t h, int32_t w, const void* tgt, int32_t tgt_u8, int32_t H, int32_t W,
+                        float alpha, float gamma, float num_boxes, float* partial, float* sums, float* out, void* stream) {
+  return mask_loss_fwd(src, N, h, w, tgt, tgt_u8, H, W, alpha, gamma, num_boxes, partial, sums, out, static_cast<cudaStream_t>(stream));
+}
+int sam3b_mask_loss_bwd(const float* src, int32_t N, int32_t h, int32_t w, const void* tgt, int32_t tgt_u8, int32_t H, int32_t W,
+                        float alpha, float gamma, float num_boxes, const float* sums, const float* g, float* dsrc, void* stream) {
+  return mask_loss_bwd(src, N, h, w, tgt, tgt_u8, H, W, alpha, gamma, num_boxes, sums, g, dsrc, static_cast<cudaStream_t>(stream));
+}
+
+int sam3b_matcher(const sam3b_matcher_desc* d, float* cost, int32_t* query_of_col, int32_t* col_of_query, void* stream) {
+  if (!d) return fail(-1, "sam3b_matcher: null descriptor");
+  MatcherArgs a;
+  a.B = d->B; a.Q = d->Q; a.Tmax = d->Tmax; a.repeats = d->repeats;
+  a.logits = d->logits; a.pred_boxes = d->pred_boxes; a.tgt_boxes = d->tgt_boxes; a.num_boxes = d->num_boxes;
+  a.out_valid = d->out_valid; a.tgt_valid = d->tgt_valid;
+  a.w_class = d->w_class; a.w_bbox = d->w_bbox; a.w_giou = d->w_giou;
+  a.focal = d->focal; a.stable = d->stable; a.alpha = d->alpha; a.gamma = d->gamma;
+  return matcher_run(a, cost, query_of_col, col_of_query, static_cast<cudaStream_t>(stream));
 }
 
 #define SAM3B_ST static_cast<cudaStream_t>(stream)
