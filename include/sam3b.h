@@ -247,6 +247,13 @@ int sam3b_transpose_cast(const void* in, int32_t tin, void* out, int32_t tout, i
                          const float* scale, void* stream);
 /* 3x3 / padding 1 patch matrix: out16[(b,y,x)][(ky*3+kx)*C + c] = x16[b][y+ky-1][x+kx-1][c] (nn.Conv2d(.,.,3,padding=1), necks.py:84-92) */
 int sam3b_im2col3x3(const void* x16, int32_t B, int32_t H, int32_t W, int32_t C, void* out16, int64_t ldo, void* stream);
+/* Implicit-GEMM nn.Conv2d(C, Cout, 3, padding=1) on channels-last 16-bit x16 [B][H][W][C] (necks.py:84-92,
+ * maskformer_segmentation.py:187): no patch matrix, each filter tap's operand tile is one zero-filled 4-D TMA box.
+ * w9 [Cout][9*C] with k = (ky*3+kx)*C + c; out [B*H*W][ldc] fp32 (out_f32) or 16-bit; bias [Cout] or NULL.
+ * Needs C % 64 == 0, W % 8 == 0, Cout % 8 == 0 (sam3b_conv3x3_supported); otherwise use sam3b_im2col3x3 + sam3b_gemm. */
+int sam3b_conv3x3_supported(int32_t H, int32_t W, int32_t C, int32_t Cout);
+int sam3b_conv3x3(const void* x16, int32_t B, int32_t H, int32_t W, int32_t C, const void* w9, int32_t Cout, const float* bias,
+                  void* out, int64_t ldc, int32_t out_f32, int32_t dtype, void* stream);
 /* nn.ConvTranspose2d(k=2,s=2) output placement (necks.py:44-62): in16 [B*H*W][4C] columns (di,dj,c) -> out16 [B][2H][2W][C], optional GELU */
 int sam3b_pixel_shuffle2(const void* in16, int32_t B, int32_t H, int32_t W, int32_t C, int32_t gelu, void* out16, int32_t dtype,
                          void* stream);

@@ -69,6 +69,8 @@ SIGNATURES: dict[str, tuple] = {
     "sam3b_scale_cast": (C.c_int, [vp, i32, vp, i32, i64, i32, vp, i32, vp]),
     "sam3b_transpose_cast": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
     "sam3b_im2col3x3": (C.c_int, [vp, i32, i32, i32, i32, vp, i64, vp]),
+    "sam3b_conv3x3_supported": (C.c_int, [i32, i32, i32, i32]),
+    "sam3b_conv3x3": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, vp, vp, i64, i32, i32, vp]),
     "sam3b_pixel_shuffle2": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "sam3b_pixel_unshuffle2": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, i32, vp]),
     "sam3b_maxpool2_fwd": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, vp]),

@@ -168,6 +168,24 @@ def groupnorm_relu_bwd(dy16, x32, stat, gamma, beta, B, HW, Cc, G) -> torch.Tens
     return dx
 
 
+IMPLICIT_CONV = True   # tests flip this to compare the TMA implicit-GEMM convolution with the im2col + GEMM path
+
+
+def conv3x3(x16: torch.Tensor, w9: torch.Tensor, bias=None, out_f32: bool = False) -> torch.Tensor:
+    """nn.Conv2d(C, Cout, 3, padding=1) on channels-last 16-bit x16 [B,H,W,C] -> [B*H*W, Cout] (16-bit or fp32).
+    w9 [Cout, 9C] with k = (ky, kx, c).  Implicit GEMM (4-D TMA boxes, no patch matrix) when the shape allows it."""
+    B, H, W, Cc = x16.shape
+    co = w9.shape[0]
+    lib = L.load()
+    if IMPLICIT_CONV and lib.sam3b_conv3x3_supported(H, W, Cc, co):
+        out = torch.empty(B * H * W, co, device=x16.device, dtype=torch.float32 if out_f32 else x16.dtype)
+        L.check(lib.sam3b_conv3x3(L.ptr(x16), B, H, W, Cc, L.ptr(w9), co, L.ptr(bias), L.ptr(out), out.stride(0), int(out_f32),
+                                  _dtc(x16), _st()))
+        return out
+    col = im2col3x3(x16)
+    return _gemm32(col, w9, bias) if out_f32 else _gemm16(col, w9, bias)
+
+
 def _gemm16(a16, w16, bias=None):
     out = torch.empty(a16.shape[0], w16.shape[0], device=a16.device, dtype=a16.dtype)
     return L.gemm(a16, w16, out, epilogue=L.EPI_STORE16, bias=bias)
@@ -297,7 +315,7 @@ class _NeckFn(torch.autograd.Function):
             if w1.shape[0] != d:
                 c1 = c1[:, :d].contiguous()
             w9, _, b9 = pack_conv3x3(seq.conv_3x3)
-            out = _gemm32(im2col3x3(c1.view(B, h, w, d)), w9, b9)
+            out = conv3x3(c1.view(B, h, w, d), w9, b9, out_f32=True)
             outs.append(nhwc32_as_nchw(out.view(B, h, w, seq.conv_3x3.out_channels)))
             saved.append(h0)
         ctx.branches = branches
@@ -323,7 +341,7 @@ class _NeckFn(torch.autograd.Function):
             s_in, s_out = sc[0:1], sc[1:2]
             dy16 = to_nhwc16(g, s_in)
             _, wg, _ = pack_conv3x3(seq.conv_3x3)
-            dc1 = _gemm16(im2col3x3(dy16), wg)                        # [Mb, d_model]
+            dc1 = conv3x3(dy16, wg)                                   # [Mb, d_model]
             w1, w1t, _ = pack_conv1x1(seq.conv_1x1)
             if w1.shape[0] != dc1.shape[1]:
                 dc1 = torch.nn.functional.pad(dc1, (0, w1.shape[0] - dc1.shape[1]))
@@ -370,7 +388,7 @@ class _PixelDecoderFn(torch.autograd.Function):
             _, H, W, Cc = cur.shape
             s16 = upsample_add(prev, cur)
             w9, _, b9 = pack_conv3x3(convs[k])
-            y32 = _gemm32(im2col3x3(s16), w9, b9)                                           # [B*H*W, C] fp32
+            y32 = conv3x3(s16, w9, b9, out_f32=True)                                        # [B*H*W, C] fp32
             G = norms[k].num_groups
             stat = groupnorm_stats(y32, B, H * W, Cc, G, norms[k].eps)
             last = li == len(fpn) - 1
@@ -401,7 +419,7 @@ class _PixelDecoderFn(torch.autograd.Function):
             dconv = groupnorm_relu_bwd(dy16.view(B * H * W, Cc), ys[li], stats[li], norms[k].weight.detach().float().contiguous(),
                                        norms[k].bias.detach().float().contiguous(), B, H * W, Cc, G)
             _, wg, _ = pack_conv3x3(convs[k])
-            ds16 = _gemm16(im2col3x3(dconv.view(B, H, W, Cc)), wg)                           # d(curr + up(prev)), scaled
+            ds16 = conv3x3(dconv.view(B, H, W, Cc), wg)                                      # d(curr + up(prev)), scaled
             dcur = torch.empty(B, H, W, Cc, device=ds16.device, dtype=torch.float32)
             scale_cast(ds16, dcur, s_out)
             grads_fpn.append(nhwc32_as_nchw(dcur))

@@ -236,6 +236,14 @@ int sam3b_transpose_cast(const void* in, int32_t tin, void* out, int32_t tout, i
 int sam3b_im2col3x3(const void* x16, int32_t B, int32_t H, int32_t W, int32_t C, void* out16, int64_t ldo, void* stream) {
   return im2col3x3(x16, B, H, W, C, out16, ldo, SAM3B_ST);
 }
+int sam3b_conv3x3_supported(int32_t H, int32_t W, int32_t C, int32_t Cout) { return conv3x3_supported(H, W, C, Cout) ? 1 : 0; }
+int sam3b_conv3x3(const void* x16, int32_t B, int32_t H, int32_t W, int32_t C, const void* w9, int32_t Cout, const float* bias,
+                  void* out, int64_t ldc, int32_t out_f32, int32_t dtype, void* stream) {
+  ConvArgs a;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.Cout = Cout;
+  a.x16 = x16; a.w9 = w9; a.bias = bias; a.out = out; a.ldc = ldc; a.out_f32 = out_f32; a.dtype = dtype;
+  return conv3x3_launch(a, SAM3B_ST);
+}
 int sam3b_pixel_shuffle2(const void* in16, int32_t B, int32_t H, int32_t W, int32_t C, int32_t gelu, void* out16, int32_t dtype,
                          void* stream) {
   return pixel_shuffle2(in16, B, H, W, C, gelu, out16, dtype, SAM3B_ST);

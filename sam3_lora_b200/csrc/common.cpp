@@ -54,6 +54,27 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
   return 0;
 }
 
+int make_tmap_nhwc(CUtensorMap* out, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_c,
+                   uint32_t box_w, uint32_t box_h) {
+  auto fn = encode_fn();
+  if (!fn) return fail(-3, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-1, "TMA base pointer %p not 16-byte aligned", ptr);
+  if ((C * 2) % 16 != 0) return fail(-1, "TMA pixel pitch %llu B not a multiple of 16", (unsigned long long)(C * 2));
+  if (box_c * 2 != 128) return fail(-1, "TMA inner box %u B must equal the 128-byte swizzle span", box_c * 2);
+  if (box_w > 256 || box_h > 256) return fail(-1, "TMA box %ux%u > 256", box_w, box_h);
+  cuuint64_t gdim[4] = {C, W, H, B};
+  cuuint64_t gstride[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(-3, "cuTensorMapEncodeTiled (NHWC) failed with %d (B=%llu H=%llu W=%llu C=%llu)", (int)r, (unsigned long long)B,
+                (unsigned long long)H, (unsigned long long)W, (unsigned long long)C);
+  return 0;
+}
+
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }

@@ -38,6 +38,12 @@ const char* last_error_message();
 int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, int elem_bytes = 2);
 
+// 4-D map over a channels-last 16-bit tensor [B][H][W][C]: dimensions (C, W, H, B), box (box_c, box_w, box_h, 1),
+// SWIZZLE_128B (box_c * 2 bytes == 128).  Coordinates may be negative / past the end: those elements read as zero,
+// which is exactly the zero padding of a convolution.
+int make_tmap_nhwc(CUtensorMap* out, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_c,
+                   uint32_t box_w, uint32_t box_h);
+
 int num_sms();
 void count_launch();
 long long launch_count();

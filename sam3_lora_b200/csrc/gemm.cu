@@ -19,6 +19,7 @@
 // together share the A row-panel in L2).
 #include "gemm.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.h"
@@ -603,6 +604,195 @@ static int launch_pair(const GemmArgs& a, const GemmParams& p, cudaStream_t stre
 template <int EPI>
 static int launch_pair_dt(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
   return a.dtype == 0 ? launch_pair<EPI, 0>(a, p, stream) : launch_pair<EPI, 1>(a, p, stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// Implicit-GEMM 3x3 convolution (see gemm.cuh).  Same warp roles and mbarrier ring as gemm_kernel<256>; an output
+// tile is a 16 x 8 pixel patch of one image (128 GEMM rows), so the A operand of filter tap (ky, kx), channels
+// [c0, c0+64) is the 4-D TMA box {c0, x0+kx-1, y0+ky-1, b} of extent {64, 8, 16, 1}: in shared memory that is 128 rows
+// of 128 bytes with the 128B swizzle, i.e. exactly the K-major tile the MMA descriptor expects.  Borders cost nothing:
+// out-of-range coordinates are zero-filled by the TMA unit.  K loop = 9 taps x C/64 blocks.
+// ---------------------------------------------------------------------------------------
+struct ConvParams {
+  int H, W, C, Cout, tiles_x, tiles_y, n_tiles, total_work, kb_total, kb_per_tap;
+  const float* bias;
+  void* out; int64_t ldc;
+};
+constexpr int CONV_BH = 16, CONV_BW = 8;
+
+template <bool OUT32, int DT>
+__global__ void __launch_bounds__(384, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+  using Cfg = GemmCfg<256>;
+  constexpr int STAGES = Cfg::STAGES, BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TCOLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const int n_blk = w % p.n_tiles, t = w / p.n_tiles;
+        const int b = t / tiles_per_img, ti = t % tiles_per_img;
+        const int y0 = (ti / p.tiles_x) * CONV_BH, x0 = (ti % p.tiles_x) * CONV_BW;
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          const int tap = kb / p.kb_per_tap, c0 = (kb % p.kb_per_tap) * 64;
+          mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
+          mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmX, &full[stage], c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmW, &full[stage], kb * 64, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BN, DT, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(&full[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(d_tmem, make_desc_kmajor(a_addr + k * 32), make_desc_kmajor(b_addr + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // lane = tile row ew*32 + lane = pixel (y0 + row / 8, x0 + row % 8); each lane owns whole 64/128-byte output segments
+    const int ew = warp & 3;
+    const int c_lo = ((warp - 4) >> 2) * (BN / 2);
+    const int row = ew * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const int n_blk = w % p.n_tiles, t = w / p.n_tiles;
+      const int b = t / tiles_per_img, ti = t % tiles_per_img;
+      const int y = (ti / p.tiles_x) * CONV_BH + row / CONV_BW, x = (ti % p.tiles_x) * CONV_BW + row % CONV_BW;
+      const bool ok = y < p.H;
+      const int64_t m = ((int64_t)b * p.H + y) * p.W + x;
+      mbar_wait(&tfull[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = c_lo; c < c_lo + BN / 2; c += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c, r);
+        tmem_ld_wait();
+        const int col = n_blk * BN + c;
+        if (!ok || col >= p.Cout) continue;
+        const int nvalid = min(32, p.Cout - col);   // multiple of 8 (host-checked)
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q * 4 < nvalid) { const float4 bb = __ldg(b4 + q); v[q * 4] += bb.x; v[q * 4 + 1] += bb.y; v[q * 4 + 2] += bb.z; v[q * 4 + 3] += bb.w; }
+        }
+        if constexpr (OUT32) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldc + col);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q * 4 < nvalid) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + m * p.ldc + col);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q * 8 < nvalid)
+              o[q] = make_uint4(pack2<DT>(v[q * 8], v[q * 8 + 1]), pack2<DT>(v[q * 8 + 2], v[q * 8 + 3]),
+                                pack2<DT>(v[q * 8 + 4], v[q * 8 + 5]), pack2<DT>(v[q * 8 + 6], v[q * 8 + 7]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TCOLS);
+}
+
+bool conv3x3_supported(int H, int W, int C, int Cout) { return H > 0 && W > 0 && W % CONV_BW == 0 && C > 0 && C % 64 == 0 && Cout > 0 && Cout % 8 == 0; }
+
+template <bool OUT32, int DT>
+static int launch_conv(const ConvArgs& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<256>;
+  CUtensorMap tmX, tmW;
+  int rc;
+  if ((rc = make_tmap_nhwc(&tmX, a.x16, a.B, a.H, a.W, a.C, 64, CONV_BW, CONV_BH))) return rc;
+  if ((rc = make_tmap_2d(&tmW, a.w9, a.Cout, 9 * (uint64_t)a.C, 9 * (uint64_t)a.C, 256, 64))) return rc;
+  ConvParams p{};
+  p.H = a.H; p.W = a.W; p.C = a.C; p.Cout = a.Cout;
+  p.tiles_x = a.W / CONV_BW; p.tiles_y = (a.H + CONV_BH - 1) / CONV_BH; p.n_tiles = (a.Cout + 255) / 256;
+  p.total_work = a.B * p.tiles_x * p.tiles_y * p.n_tiles;
+  p.kb_per_tap = a.C / 64; p.kb_total = 9 * p.kb_per_tap;
+  p.bias = a.bias; p.out = a.out; p.ldc = a.ldc;
+  auto kern = conv3x3_kernel<OUT32, DT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SAM3B_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  const int ctas = std::min(num_sms(), p.total_work);
+  kern<<<ctas, 384, Cfg::SMEM, stream>>>(tmX, tmW, p);
+  SAM3B_LAUNCHED();
+  return 0;
+}
+
+int conv3x3_launch(const ConvArgs& a, cudaStream_t stream) {
+  SAM3B_REQUIRE(a.B > 0 && a.x16 && a.w9 && a.out, "conv3x3: null tensor / empty batch");
+  SAM3B_REQUIRE(conv3x3_supported(a.H, a.W, a.C, a.Cout), "conv3x3: needs C %% 64 == 0, W %% 8 == 0, Cout %% 8 == 0 (H=%d W=%d C=%d Cout=%d)", a.H, a.W, a.C, a.Cout);
+  SAM3B_REQUIRE(a.dtype == 0 || a.dtype == 1, "conv3x3: dtype %d (0 fp16, 1 bf16)", a.dtype);
+  SAM3B_REQUIRE(a.ldc >= a.Cout && a.ldc % (a.out_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0, "conv3x3: output leading dimension / alignment");
+  if (a.bias) SAM3B_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "conv3x3: bias not 16-byte aligned");
+  if (a.out_f32) return a.dtype == 0 ? launch_conv<true, 0>(a, stream) : launch_conv<true, 1>(a, stream);
+  return a.dtype == 0 ? launch_conv<false, 0>(a, stream) : launch_conv<false, 1>(a, stream);
 }
 
 // ---------------------------------------------------------------------------------------

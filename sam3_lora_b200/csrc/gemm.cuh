@@ -43,4 +43,21 @@ struct GemmArgs {
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 
+// Implicit-GEMM 3x3 convolution, stride 1, zero padding 1, on channels-last 16-bit activations (nn.Conv2d(C, Cout, 3,
+// padding=1): necks.py:84-92, maskformer_segmentation.py:187).  No im2col buffer: the A tile of filter tap (ky, kx) is ONE
+// 4-D TMA box of the input shifted by (ky-1, kx-1), with out-of-range pixels zero-filled by the TMA unit.
+//   x16 [B][H][W][C]   w9 [Cout][9*C] with k = (ky*3 + kx)*C + c   out [B*H*W][ldc] 16-bit or fp32 (+ bias [Cout])
+// Needs C % 64 == 0, W % 8 == 0, Cout % 8 == 0 (callers fall back to im2col3x3 + gemm_launch otherwise).
+struct ConvArgs {
+  int B = 0, H = 0, W = 0, C = 0, Cout = 0;
+  const void* x16 = nullptr;
+  const void* w9 = nullptr;
+  const float* bias = nullptr;
+  void* out = nullptr; int64_t ldc = 0;
+  int out_f32 = 0;
+  int dtype = 0;
+};
+bool conv3x3_supported(int H, int W, int C, int Cout);
+int conv3x3_launch(const ConvArgs& a, cudaStream_t stream);
+
 }  // namespace sam3b

@@ -116,6 +116,37 @@ def test_im2col_shuffle_pool_upsample_against_torch():
     assert rel_l2(adj.float(), ref) < 1e-3
 
 
+@pytest.mark.parametrize("B,H,W,Cc,co", [(2, 20, 24, 64, 40), (1, 16, 8, 128, 256), (3, 37, 40, 256, 256), (2, 72, 72, 256, 264)])
+def test_implicit_gemm_conv3x3_against_torch_and_im2col(B, H, W, Cc, co):
+    """TMA implicit-GEMM conv (zero-filled 4-D boxes) vs F.conv2d on the same 16-bit-rounded operands, fp32 and 16-bit
+    outputs, image heights that are not a multiple of the 16-row tile, Cout above one 256-wide N tile, and vs im2col + GEMM."""
+    from sam3_lora_b200 import conv_ops as CO
+
+    torch.backends.cudnn.allow_tf32 = False          # the PyTorch side of the comparison must be real fp32
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(B, H, W, Cc, device=DEV, generator=g).half()
+    wgt = (torch.randn(co, Cc, 3, 3, device=DEV, generator=g) * (9 * Cc) ** -0.5)
+    bias = torch.randn(co, device=DEV, generator=g)
+    w9 = wgt.permute(0, 2, 3, 1).reshape(co, 9 * Cc).half().contiguous()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w9.float().view(co, 3, 3, Cc).permute(0, 3, 1, 2), bias, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, co)
+    assert CO.L.load().sam3b_conv3x3_supported(H, W, Cc, co)
+    y32 = CO.conv3x3(x, w9, bias, out_f32=True)
+    assert rel_l2(y32, ref) < 1e-5                   # identical operands; fp32 accumulation order differs over K = 9C
+    y16 = CO.conv3x3(x, w9, bias)
+    assert y16.dtype == torch.float16 and rel_l2(y16.float(), ref) < 6e-4
+    CO.IMPLICIT_CONV = False
+    try:
+        y_im2col = CO.conv3x3(x, w9, bias, out_f32=True)
+    finally:
+        CO.IMPLICIT_CONV = True
+    assert rel_l2(y32, y_im2col) < 1e-5
+    xb = x.bfloat16()
+    yb = CO.conv3x3(xb, w9.bfloat16(), None, out_f32=True)
+    refb = F.conv2d(xb.permute(0, 3, 1, 2).float(), w9.bfloat16().float().view(co, 3, 3, Cc).permute(0, 3, 1, 2), None, padding=1)
+    assert rel_l2(yb, refb.permute(0, 2, 3, 1).reshape(B * H * W, co)) < 1e-5
+
+
 @pytest.mark.parametrize("Cc,HW", [(32, 4 * 36), (256, 20 * 27)])
 def test_groupnorm_relu_forward_backward(Cc, HW):
     from sam3_lora_b200 import conv_ops as CO
