@@ -31,6 +31,7 @@
 #include "common.h"
 #include "ptx.cuh"
 #include "rng.cuh"
+#include "stage.cuh"
 
 namespace sam3b {
 
@@ -96,6 +97,73 @@ template <int DT>
 __device__ __forceinline__ void pack16(const float (&v)[32], uint32_t (&o)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) o[i] = pack2<DT>(v[2 * i], v[2 * i + 1]);
+}
+
+// ---- coalesced item transitions (stage.cuh) ------------------------------------------------------------------------
+// A compute warp owns the 32 rows of its TMEM lane quarter.  Row-per-lane global accesses (the first version of park /
+// epilogue) touch 32 different lines per instruction: per item that was ~2k LSU wavefronts for parking K/V and ~4k for
+// the rope-table loads + dK/dV stores, i.e. 1.3-2.0k and 4.1-5.3k clk of an 18.4k-clk window item
+// (profiles/r01_attn_bwd_timeline.md).  Through the warp's 2 KB staging tile four lanes share a row, so an instruction
+// covers 8 rows x 64 B: a quarter of the wavefronts.
+
+// 32 rows x 32 16-bit elements (64 B per row) of global memory -> 16 packed TMEM columns of each lane (A-operand layout)
+template <typename RowFn>
+__device__ __forceinline__ void park_rows(uint8_t* stg, int lane, uint32_t taddr, RowFn rowaddr) {
+  stage_fill_rows(stg, lane, rowaddr);
+  __syncwarp();
+  uint32_t v[16];
+  stage_get_row(stg, lane, v);
+  __syncwarp();
+  tmem_st_x16(taddr, v);
+}
+// second half of an asynchronous park: the rows were requested with stage_fill_rows_async into stg
+__device__ __forceinline__ void park_staged(uint8_t* stg, int lane, uint32_t taddr) {
+  uint32_t v[16];
+  stage_get_row(stg, lane, v);
+  __syncwarp();
+  tmem_st_x16(taddr, v);
+}
+
+// Inverse-RoPE table rows of the warp's 32 rows, columns [cc, cc+32) of the head: 16 (cos, sin) pairs = 128 B per row,
+// requested asynchronously as two 64-byte halves into tiles srope and srope + STG_BYTES.
+__device__ __forceinline__ void rope_fill_async(const BwdParams& p, uint8_t* srope, int lane, int64_t row0, int cc) {
+  stage_fill_rows_async(srope, lane, [&](int rl) { return reinterpret_cast<const uint8_t*>(p.rope + (int64_t)((row0 + rl) % p.rope_period) * 32 + (cc >> 1)); });
+  stage_fill_rows_async(srope + STG_BYTES, lane, [&](int rl) { return reinterpret_cast<const uint8_t*>(p.rope + (int64_t)((row0 + rl) % p.rope_period) * 32 + (cc >> 1) + 8); });
+}
+
+// out[row0 + lane][col .. col + 32) = (optionally inverse-rotated) acc * mul in 16-bit, for the warp's 32 rows.
+// ROPE: the table halves were staged by the caller in tiles srope and srope + STG_BYTES (rope_fill_async, waited).
+template <int DT, bool ROPE>
+__device__ __forceinline__ void store_grad_rows(const BwdParams& p, uint8_t* stg, const uint8_t* srope, int lane, uint32_t taddr, void* out, int64_t ld,
+                                                int64_t row0, int col, float mul, int rows_valid) {
+  uint32_t t[32];
+  tmem_ld_x32(taddr, t);
+  tmem_ld_wait();
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(t[i]) * mul;
+  if constexpr (ROPE) {
+    if (p.rope != nullptr) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t w[16];
+        stage_get_row(srope + h * STG_BYTES, lane, w);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float cs = __uint_as_float(w[2 * q]), sn = __uint_as_float(w[2 * q + 1]);
+          const float a = v[16 * h + 2 * q], b = v[16 * h + 2 * q + 1];
+          v[16 * h + 2 * q] = a * cs + b * sn;
+          v[16 * h + 2 * q + 1] = -a * sn + b * cs;
+        }
+      }
+    }
+  }
+  uint32_t w[16];
+  pack16<DT>(v, w);
+  stage_put_row(stg, lane, w);
+  __syncwarp();
+  stage_flush(stg, lane, reinterpret_cast<uint8_t*>(reinterpret_cast<uint16_t*>(out) + row0 * ld + col), ld * 2, rows_valid, 64);
+  __syncwarp();
 }
 
 // out[row][col0 + cc .. col0 + cc + 32) = (optionally inverse-rotated) acc * mul, 16-bit
@@ -177,7 +245,8 @@ __device__ __forceinline__ void store_grad_chunk16(const BwdParams& p, void* out
 // =========================================================================================
 // TMEM columns: S^T x2 [0,128)  dP^T x2 [128,256)  dV [256,320)  dK [320,384)  K [384,416)  V [416,448)
 //               P^T [448,480)  dS^T [480,512)   (K, V, P^T, dS^T: 16-bit A operands, two elements per column)
-constexpr int DKDV_SMEM = 2 * NSI * I_BYTES + NSI * 2 * BI * 4 + 256;  // Q ring | dO ring | [lse2 | delta] ring | barriers
+constexpr int DKDV_MAIN = 2 * NSI * I_BYTES + NSI * 2 * BI * 4 + 256;  // Q ring | dO ring | [lse2 | delta] ring | barriers
+constexpr int DKDV_SMEM = DKDV_MAIN + 16 * STG_BYTES + 8 * 2 * STG_BYTES;   // + a row tile per compute warp, + 2 rope tiles per dK warp (199 KB)
 
 template <int DT, bool GEN>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -310,12 +379,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
     const uint32_t lane_off = static_cast<uint32_t>((wi & 3) * 32) << 16;
     const float c = p.scale_log2;
 
-    // K (group 0) / V (group 1) rows of an item -> TMEM; each thread parks 32 of its row's 64 elements
+    uint8_t* stg = smem_raw + DKDV_MAIN + warp * STG_BYTES;
+    uint8_t* srope = smem_raw + DKDV_MAIN + 16 * STG_BYTES + wi * 2 * STG_BYTES;   // used by group 1 (dK) only
+    const int lane = threadIdx.x & 31, lq = wi & 3;
+
+    // K (group 0) / V (group 1) rows of an item -> TMEM; each warp parks 32 rows x 32 of the 64 elements
     auto park = [&](int item) {
       const int tile = item % p.tiles, seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
-      const int64_t grow = (int64_t)seg * p.Lk + min(tile * BT + r, p.Lk - 1);
-      park_row_half((g == 0 ? tm_K : tm_V) + lane_off + (wi >> 2) * 16, p.kv, grow, p.ldkv,
-                    (g == 0 ? p.k_col0 : p.v_col0) + head * HD + (wi >> 2) * 32);
+      const int col = (g == 0 ? p.k_col0 : p.v_col0) + head * HD + (wi >> 2) * 32;
+      park_rows(stg, lane, (g == 0 ? tm_K : tm_V) + lane_off + (wi >> 2) * 16, [&](int rl) {
+        const int64_t grow = (int64_t)seg * p.Lk + min(tile * BT + lq * 32 + rl, p.Lk - 1);
+        return reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.kv) + grow * p.ldkv + col);
+      });
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(kv_ready);
@@ -403,25 +478,44 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
         mbar_arrive(&pds_full[g]);
         if (tr) TRACE(64 + j * 8 + 5);
       }
-      // park the next item's K / V before this item's epilogue so that its first MMAs overlap the epilogue
+      // Item transition.  All global loads go out first (next item's K / V rows, this item's inverse-RoPE rows), then the
+      // barrier waits, then the staged copies: the load latency hides behind the tail of the item's MMAs.
       const int next = item + gridDim.x;
       const bool trt = threadIdx.x == 0 || threadIdx.x == 256;
       if (trt) TRACE(8 + g * 8 + 0);
+      const int ch = (wi >> 2) * 32;
+      const int64_t row0 = (int64_t)t_row0 + lq * 32;
+      const bool do_rope = g == 1 && p.rope != nullptr;
+      if (next < n_items) {
+        const int ntile = next % p.tiles, nseg_ = (next / p.tiles) % p.nseg, nhead = next / (p.tiles * p.nseg);
+        const int ncol = (g == 0 ? p.k_col0 : p.v_col0) + nhead * HD + ch;
+        stage_fill_rows_async(stg, lane, [&](int rl) {
+          const int64_t grow = (int64_t)nseg_ * p.Lk + min(ntile * BT + lq * 32 + rl, p.Lk - 1);
+          return reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.kv) + grow * p.ldkv + ncol);
+        });
+      }
+      if (do_rope) rope_fill_async(p, srope, lane, row0, ch);
       if (next < n_items) {
         mbar_wait(kv_free, it & 1, 34);
         tc_fence_after();
         if (trt) TRACE(8 + g * 8 + 1);
-        park(next);
+        stage_async_wait();
+        __syncwarp();
+        park_staged(stg, lane, (g == 0 ? tm_K : tm_V) + lane_off + (wi >> 2) * 16);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(kv_ready);
       }
       if (trt) TRACE(8 + g * 8 + 2);
       mbar_wait(all_done, it & 1, 32);
       tc_fence_after();
+      stage_async_wait();
+      __syncwarp();
       if (trt) TRACE(8 + g * 8 + 3);
-      const int row = t_row0 + r;
-      const bool valid = (tile * BT + r) < p.Lk;
-      const int ec = (wi >> 2) * 32 + g * 16;   // this warp's 16-column quarter of both accumulators
-      store_grad_chunk16<DT, false>(p, p.dkv, p.lddkv, tm_dV + lane_off, row, row, p.dv_col0 + head * HD, ec, 1.f, valid);
-      store_grad_chunk16<DT, true>(p, p.dkv, p.lddkv, tm_dK + lane_off, row, row, p.dk_col0 + head * HD, ec, p.scale, valid);
+      // group 0 drains dV, group 1 drains dK (+ inverse rotation): each warp its 32 rows x one 32-column half
+      const int rows_valid = max(0, min(32, p.Lk - (tile * BT + lq * 32)));
+      if (g == 0) store_grad_rows<DT, false>(p, stg, srope, lane, tm_dV + lane_off + ch, p.dkv, p.lddkv, row0, p.dv_col0 + head * HD + ch, 1.f, rows_valid);
+      else store_grad_rows<DT, true>(p, stg, srope, lane, tm_dK + lane_off + ch, p.dkv, p.lddkv, row0, p.dk_col0 + head * HD + ch, p.scale, rows_valid);
       if (trt) TRACE(8 + g * 8 + 4);
       tc_fence_before();
       mbar_arrive(epi_done);
@@ -436,7 +530,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
 // dQ
 // =========================================================================================
 // TMEM columns: S x2 [0,128)  dP x2 [128,256)  dQ [256,320)  Q [320,352)  dO [352,384)  dS x2 [384,448)
-constexpr int DQ_SMEM = 2 * NSI * I_BYTES + 256;   // K ring | V ring | barriers
+constexpr int DQ_MAIN = 2 * NSI * I_BYTES + 256;   // K ring | V ring | barriers
+constexpr int DQ_SMEM = DQ_MAIN + 16 * STG_BYTES + 8 * 2 * STG_BYTES;   // + a row tile per compute warp, + 2 rope tiles per dQ warp
+static_assert(DKDV_SMEM <= 227 * 1024 && DQ_SMEM <= 227 * 1024, "attention backward exceeds the 227 KB of shared memory per CTA");
 
 template <int DT, bool GEN>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -550,12 +646,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
     const uint32_t lane_off = static_cast<uint32_t>((wi & 3) * 32) << 16;
     const float c = p.scale_log2;
 
-    // Q (group 0) / dO (group 1) rows of an item -> TMEM
+    uint8_t* stg = smem_raw + DQ_MAIN + warp * STG_BYTES;
+    uint8_t* srope = smem_raw + DQ_MAIN + 16 * STG_BYTES + wi * 2 * STG_BYTES;     // used by group 0 (dQ) only
+    const int lane = threadIdx.x & 31, lq = wi & 3;
+
+    // Q (group 0) / dO (group 1) rows of an item -> TMEM (coalesced through the warp's staging tile)
     auto park = [&](int item) {
       const int tile = item % p.tiles, seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
-      const int64_t grow = (int64_t)seg * p.Lq + min(tile * BT + r, p.Lq - 1);
-      if (g == 0) park_row_half(tm_Q + lane_off + (wi >> 2) * 16, p.q, grow, p.ldq, p.q_col0 + head * HD + (wi >> 2) * 32);
-      else        park_row_half(tm_dO + lane_off + (wi >> 2) * 16, p.dO, grow, p.lddo, p.do_col0 + head * HD + (wi >> 2) * 32);
+      const uint16_t* base = reinterpret_cast<const uint16_t*>(g == 0 ? p.q : p.dO);
+      const int64_t ldb = g == 0 ? p.ldq : p.lddo;
+      const int col = (g == 0 ? p.q_col0 : p.do_col0) + head * HD + (wi >> 2) * 32;
+      park_rows(stg, lane, (g == 0 ? tm_Q : tm_dO) + lane_off + (wi >> 2) * 16, [&](int rl) {
+        const int64_t grow = (int64_t)seg * p.Lq + min(tile * BT + lq * 32 + rl, p.Lq - 1);
+        return reinterpret_cast<const uint8_t*>(base + grow * ldb + col);
+      });
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(qdo_ready);
@@ -567,7 +671,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
       const int tile = item % p.tiles, seg = (item / p.tiles) % p.nseg, head = item / (p.tiles * p.nseg);
       const int B0 = it * n_blocks;
       const int t_row0 = seg * p.Lq + tile * BT;   // this item's 128 queries
-      const int row = t_row0 + r;
       const int q_in_seg = min(tile * BT + r, p.Lq - 1);
       const int64_t sidx = (int64_t)head * p.stat_stride + (int64_t)seg * p.Lq_stat + q_in_seg;   // head-major statistics
       const float lse = __ldg(p.lse2 + sidx);
@@ -625,16 +728,40 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
         tc_fence_before();
         mbar_arrive(&ds_full[g]);
       }
+      // item transition: loads first (next item's Q / dO rows, this item's inverse-RoPE rows), then waits, then copies
       const int next = item + gridDim.x;
+      const int ch = (wi >> 2) * 32;
+      const int64_t row0 = (int64_t)t_row0 + lq * 32;
+      const bool do_rope = g == 0 && p.rope != nullptr;
+      if (next < n_items) {
+        const int ntile = next % p.tiles, nseg_ = (next / p.tiles) % p.nseg, nhead = next / (p.tiles * p.nseg);
+        const uint16_t* base = reinterpret_cast<const uint16_t*>(g == 0 ? p.q : p.dO);
+        const int64_t ldb = g == 0 ? p.ldq : p.lddo;
+        const int ncol = (g == 0 ? p.q_col0 : p.do_col0) + nhead * HD + ch;
+        stage_fill_rows_async(stg, lane, [&](int rl) {
+          const int64_t grow = (int64_t)nseg_ * p.Lq + min(ntile * BT + lq * 32 + rl, p.Lq - 1);
+          return reinterpret_cast<const uint8_t*>(base + grow * ldb + ncol);
+        });
+      }
+      if (do_rope) rope_fill_async(p, srope, lane, row0, ch);
       if (next < n_items) {
         mbar_wait(qdo_free, it & 1, 34);
         tc_fence_after();
-        park(next);
+        stage_async_wait();
+        __syncwarp();
+        park_staged(stg, lane, (g == 0 ? tm_Q : tm_dO) + lane_off + (wi >> 2) * 16);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(qdo_ready);
       }
       mbar_wait(all_done, it & 1, 32);
       tc_fence_after();
-      const bool valid = (tile * BT + r) < p.Lq;
-      store_grad_chunk16<DT, true>(p, p.dq, p.lddq, tm_dQ + lane_off, row, row, p.dq_col0 + head * HD, (wi >> 2) * 32 + g * 16, p.scale, valid);
+      stage_async_wait();
+      __syncwarp();
+      if (g == 0) {   // 8 warps x (32 rows x 32 columns): whole 64-byte row segments per lane group
+        const int rows_valid = max(0, min(32, p.Lq - (tile * BT + lq * 32)));
+        store_grad_rows<DT, true>(p, stg, srope, lane, tm_dQ + lane_off + ch, p.dq, p.lddq, row0, p.dq_col0 + head * HD + ch, p.scale, rows_valid);
+      }
       tc_fence_before();
       mbar_arrive(epi_done);
     }

@@ -25,6 +25,7 @@
 #include "common.h"
 #include "ptx.cuh"
 #include "gelu.cuh"
+#include "stage.cuh"
 #include "rng.cuh"
 
 namespace sam3b {
@@ -44,7 +45,6 @@ struct GemmParams {
   uint32_t mn_lbo, mn_sbo;
 };
 
-constexpr int STG_BYTES = 2048;   // epilogue staging tile per epilogue warp (see "Coalesced epilogue I/O" below)
 
 template <int BN>
 struct GemmCfg {
@@ -66,42 +66,6 @@ struct GemmCfg {
 // one instruction covers 8 rows x 64 contiguous bytes (16 full sectors).  The 16-byte chunks are XOR-swizzled by
 // (row >> 1) & 3, which is conflict-free for both access patterns.
 // ---------------------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t stg_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
-
-__device__ __forceinline__ void stage_put_row(uint8_t* stg, int lane, const uint32_t (&w)[16]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-    *reinterpret_cast<uint4*>(stg + stg_off(lane, c)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-}
-__device__ __forceinline__ void stage_get_row(const uint8_t* stg, int lane, uint32_t (&w)[16]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(lane, c));
-    w[4 * c] = u.x; w[4 * c + 1] = u.y; w[4 * c + 2] = u.z; w[4 * c + 3] = u.w;
-  }
-}
-// staging -> global.  g = address of (first row of the warp, first byte of the segment); rows_valid / bytes_valid clip.
-__device__ __forceinline__ void stage_flush(const uint8_t* stg, int lane, uint8_t* g, int64_t ld_bytes, int rows_valid, int bytes_valid) {
-  const int c = lane & 3;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int row = it * 8 + (lane >> 2);
-    const uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(row, c));
-    if (row < rows_valid && c * 16 < bytes_valid) *reinterpret_cast<uint4*>(g + (int64_t)row * ld_bytes + c * 16) = u;
-  }
-}
-// global -> staging (same access shape)
-__device__ __forceinline__ void stage_fill(uint8_t* stg, int lane, const uint8_t* g, int64_t ld_bytes, int rows_valid, int bytes_valid) {
-  const int c = lane & 3;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int row = it * 8 + (lane >> 2);
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (row < rows_valid && c * 16 < bytes_valid) u = *reinterpret_cast<const uint4*>(g + (int64_t)row * ld_bytes + c * 16);
-    *reinterpret_cast<uint4*>(stg + stg_off(row, c)) = u;
-  }
-}
 
 // this lane's 32 values -> 16-bit -> rows [row0, row0+32) x columns [col, col+32) of `base` (leading dimension ld elements)
 template <int DT>
