@@ -413,6 +413,15 @@ def run_native(args):
                            "achieved": 2.5 * fl / ms_b / 1e9, "unit": "TFLOP/s (5 algorithmic matmuls)", "floor_ms": 2 * mufu_s * 1e3,
                            "frac_of_floor": 2 * mufu_s * 1e3 / ms_b})
             del qkv, O, lse2, dO, delta, dqkv
+        # row a8's dominant kernel: the im2col-free 3x3 convolution at the 288x288 level (256 -> 256 channels)
+        from sam3_lora_b200 import conv_ops as CO  # noqa: PLC0415
+        xc = (torch.randn(B, 288, 288, 256, device=dev) * 0.5).to(dt)
+        w9 = (torch.randn(256, 9 * 256, device=dev) * 0.02).to(dt)
+        ms_c = timed(lambda: CO.conv3x3(xc, w9, None, out_f32=False))
+        flc = 2.0 * B * 288 * 288 * 9 * 256 * 256
+        others.append({"kernel": "conv3x3_kernel (implicit GEMM, 4-D TMA boxes) B=%d 288x288 256->256" % B, "ms": ms_c, "bound": "tensor",
+                       "achieved": flc / ms_c / 1e9, "peak": peaks["burst"], "unit": "TFLOP/s"})
+        del xc, w9
     except Exception as e:  # noqa: BLE001 - context only, never fatal for the bench line
         others.append({"error": f"{type(e).__name__}: {e}"[:200]})
     roofline["other_kernels"] = others
@@ -420,7 +429,7 @@ def run_native(args):
     # -------- CPU baseline beside it (rank 0, N=1 only) --------
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
-        times, cores = cpu_unit_seconds(2, 1)
+        times, cores = cpu_unit_seconds(6, 1)     # ~15 s of CPU work on the box's host cores (bounded sample)
         _, cpu_baseline = cpu_line(times, cores, args.steps, args.warmup)
 
     line = {
