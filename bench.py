@@ -278,6 +278,9 @@ def run_native(args):
     value = B * world / (ms_step / 1000.0)
 
     # -------- end-to-end step through the public API (e2e) --------
+    # ViT(cuda_graphs=True) is the public switch for graph replay of the trunk forward / backward (one eager warm-up step,
+    # then two replays per step); --e2e-eager measures the same leg with ~1290 eager launches per step.
+    model.cuda_graphs = not args.e2e_eager and not args.no_graph
     params = model.lora_parameters()
     if world > 1:
         model.grad_hook = lambda g: dist.all_reduce(g)
@@ -466,6 +469,7 @@ def main():
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (use with `ncu --profile-from-start off`)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--e2e-eager", action="store_true", help="run the end-to-end leg without ViT(cuda_graphs=True)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

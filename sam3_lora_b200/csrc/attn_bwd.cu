@@ -518,7 +518,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
       else store_grad_rows<DT, true>(p, stg, srope, lane, tm_dK + lane_off + ch, p.dkv, p.lddkv, row0, p.dk_col0 + head * HD + ch, p.scale, rows_valid);
       if (trt) TRACE(8 + g * 8 + 4);
       tc_fence_before();
-      mbar_arrive(epi_done);
+      mbar_arrive_relaxed(epi_done);   // payload = drained TMEM accumulators, not the global stores above
     }
   }
   tc_fence_before();
@@ -763,7 +763,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
         store_grad_rows<DT, true>(p, stg, srope, lane, tm_dQ + lane_off + ch, p.dq, p.lddq, row0, p.dq_col0 + head * HD + ch, p.scale, rows_valid);
       }
       tc_fence_before();
-      mbar_arrive(epi_done);
+      mbar_arrive_relaxed(epi_done);   // payload = drained TMEM accumulators, not the global stores above
     }
   }
   tc_fence_before();

@@ -384,7 +384,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) mbar_arrive_relaxed(&tempty[acc]);   // TMEM hand-off: no need to wait for the stores above
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -711,7 +711,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) mbar_arrive_relaxed(&tempty[acc]);   // TMEM hand-off: no need to wait for the stores above
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }

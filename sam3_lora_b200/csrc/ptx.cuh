@@ -71,6 +71,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive without release semantics, for hand-offs whose payload is NOT in memory (a drained TMEM accumulator, ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  The default .release arrive first waits until the thread's
+// outstanding global stores are performed: after an epilogue's STGs that is 1.8-2.5k clk per work item in the attention
+// backward (profiles/r01_attn_bwd_timeline.md).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

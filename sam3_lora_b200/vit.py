@@ -81,8 +81,21 @@ class Block(nn.Module):
         self.mlp = Mlp(dim, mlp_hidden)
 
 
+class _GraphState:
+    """Static buffers + captured graphs of one (engine binding, batch, adapter buffer) combination."""
+
+    def __init__(self, key, B, spec, device, has_drop):
+        self.key = key
+        self.img = torch.empty(B, spec.in_chans, spec.img_size, spec.img_size, device=device, dtype=torch.float32)
+        self.out = torch.empty(B, spec.embed_dim, spec.grid, spec.grid, device=device, dtype=torch.float32)
+        self.gout = torch.empty_like(self.out)
+        self.drop = torch.ones(spec.depth, 2, B, device=device, dtype=torch.float32) if has_drop else None
+        self.g_fwd = self.g_bwd = None
+        self.warm = False        # one eager step has run (first-use attribute calls, allocator warm-up)
+
+
 class _TrunkFn(torch.autograd.Function):
-    """autograd node for the whole trunk: forward/backward are one C-ABI call each."""
+    """autograd node for the whole trunk: forward/backward are one C-ABI call each (or one CUDA-graph replay each)."""
 
     @staticmethod
     def forward(ctx, images, vit: "ViT", need_grad: bool, *lora_params):
@@ -93,18 +106,41 @@ class _TrunkFn(torch.autograd.Function):
             eng.load_base(vit._base_tensors())
         flat = vit._sync_flat()
         spec = vit.spec
+        drop = vit._drop_scales_for(B, images.device)
+        p_drop = vit._lora_dropout_p if (vit.training and need_grad) else 0.0
+        ctx.vit = vit
+        ctx.n = len(lora_params)
+        ctx.graph = None
+        if vit.cuda_graphs and need_grad and p_drop == 0.0 and flat is not None:
+            key = (str(images.device), B, eng.work_buf.data_ptr(), eng.weight_buf.data_ptr(), flat.data_ptr(), drop is not None)
+            st = vit._graph_state
+            if st is None or st.key != key:
+                st = vit._graph_state = _GraphState(key, B, spec, images.device, drop is not None)
+            st.img.copy_(images.detach())
+            if drop is not None:
+                st.drop.copy_(drop)
+            eng.set_drop_path(st.drop)
+            eng.set_lora_dropout(0.0, 0)
+            if not st.warm:
+                eng.forward(st.img, flat, st.out, save_for_backward=True)
+            elif st.g_fwd is None:
+                st.g_fwd = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(st.g_fwd):
+                    eng.forward(st.img, flat, st.out, save_for_backward=True)
+                st.g_fwd.replay()
+            else:
+                st.g_fwd.replay()
+            ctx.graph = st
+            return st.out.clone()
         out = torch.empty(B, spec.embed_dim, spec.grid, spec.grid, device=images.device, dtype=torch.float32)
         img = images.detach().float().contiguous()
-        ctx.drop = vit._drop_scales_for(B, images.device)   # keeps the tensor alive until backward
+        ctx.drop = drop   # keeps the tensor alive until backward
         eng.set_drop_path(ctx.drop)
-        p_drop = vit._lora_dropout_p if (vit.training and need_grad) else 0.0
         seed = vit.lora_dropout_seed_override
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
         eng.set_lora_dropout(p_drop, seed)
         eng.forward(img, flat, out, save_for_backward=need_grad)
-        ctx.vit = vit
-        ctx.n = len(lora_params)
         return out
 
     @staticmethod
@@ -112,7 +148,22 @@ class _TrunkFn(torch.autograd.Function):
         vit: "ViT" = ctx.vit
         eng = vit._engine
         gflat = vit._flat_grad_buffer()
-        eng.backward(gout.float().contiguous(), gflat)
+        st = ctx.graph
+        if st is not None:
+            st.gout.copy_(gout)
+            if not st.warm:
+                eng.backward(st.gout, gflat)
+                st.warm = True
+            elif st.g_bwd is None or st.g_bwd[1] != gflat.data_ptr():
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    eng.backward(st.gout, gflat)
+                st.g_bwd = (g, gflat.data_ptr())
+                g.replay()
+            else:
+                st.g_bwd[0].replay()
+        else:
+            eng.backward(gout.float().contiguous(), gflat)
         vit._after_backward(gflat)
         grads = [gflat[a:a + n].view(shape) for (a, n, shape) in vit._flat_index]
         return (None, None, None, *grads)
@@ -123,8 +174,13 @@ class ViT(nn.Module):
 
     def __init__(self, img_size=1008, patch_size=14, in_chans=3, embed_dim=1024, depth=32, num_heads=16,
                  mlp_ratio=4.625, window_size=24, global_att_blocks=(7, 15, 23, 31), pretrain_img_size=336,
-                 ln_eps=1e-5, rope_theta=10000.0, drop_path_rate=0.1, operand_dtype=torch.float16, max_batch=8):
+                 ln_eps=1e-5, rope_theta=10000.0, drop_path_rate=0.1, operand_dtype=torch.float16, max_batch=8,
+                 cuda_graphs: bool = False):
         super().__init__()
+        # cuda_graphs=True: after one eager warm-up step the ~1280 launches of the trunk forward and of its backward are
+        # each replayed from a CUDA graph (training mode, adapter dropout 0; inputs are copied into static buffers).
+        self.cuda_graphs = bool(cuda_graphs)
+        self._graph_state = None
         # stochastic depth decay rule of the reference: linspace(0, rate, depth) (vitdet.py:746), 0.1 in SAM3
         # (model_builder.py:80); active in train() mode only.
         self.drop_path_rates = [drop_path_rate * i / (depth - 1) for i in range(depth)] if depth > 1 else [float(drop_path_rate)]
