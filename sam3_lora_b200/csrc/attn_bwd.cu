@@ -81,18 +81,6 @@ __device__ __forceinline__ bool attn_drop_keep(uint32_t base, uint32_t q, uint32
   return lowbias32(base ^ (q * Lk + k)) >= thr;
 }
 
-// 32 consecutive 16-bit elements of one global row -> 16 packed TMEM columns of this thread's lane (A-operand layout)
-__device__ __forceinline__ void park_row_half(uint32_t taddr, const void* base, int64_t row, int64_t ld, int col) {
-  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + row * ld + col);
-  uint32_t v[16];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 u = __ldg(src + i);
-    v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
-  }
-  tmem_st_x16(taddr, v);
-}
-
 template <int DT>
 __device__ __forceinline__ void pack16(const float (&v)[32], uint32_t (&o)[16]) {
 #pragma unroll

@@ -307,6 +307,55 @@ __global__ void __launch_bounds__(256) lora_unpack_kernel(const UnpackArgs a) {
   }
 }
 
+template <int DT>
+__global__ void __launch_bounds__(256) lora_pack_all_kernel(const LoraSiteDesc* __restrict__ descs, const float* __restrict__ flat) {
+  const LoraSiteDesc& s = descs[blockIdx.y];
+  uint16_t* down_T = static_cast<uint16_t*>(s.down_T);
+  uint16_t* w_ext = static_cast<uint16_t*>(s.w_ext);
+  uint16_t* up_pack = static_cast<uint16_t*>(s.up_pack);
+  uint16_t* wt_ext = static_cast<uint16_t*>(s.wt_ext);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < (int64_t)s.rpad * s.in; i += stride) {
+    const int jj = (int)(i / s.in), k = (int)(i % s.in);
+    const int ad = jj / s.r, j = jj % s.r;
+    const float v = (ad < s.n) ? flat[s.a_off[ad] + (int64_t)k * s.r + j] : 0.f;
+    const uint16_t h = to16<DT>(v);
+    down_T[(int64_t)jj * s.in + k] = h;
+    wt_ext[(int64_t)k * s.ldwt + s.out_total + jj] = h;
+  }
+  for (int64_t i = tid; i < (int64_t)s.rpad * s.out_total; i += stride) {
+    const int jj = (int)(i / s.out_total), n = (int)(i % s.out_total);
+    const int ad = jj / s.r, j = jj % s.r;
+    float v = 0.f;
+    if (ad < s.n && n >= s.out_off[ad] && n < s.out_off[ad] + s.out_len[ad])
+      v = flat[s.b_off[ad] + (int64_t)j * s.out_len[ad] + (n - s.out_off[ad])];
+    const uint16_t h = to16<DT>(v);
+    w_ext[(int64_t)n * s.ldw + s.in + jj] = h;
+    up_pack[(int64_t)jj * s.out_total + n] = h;
+  }
+}
+
+__global__ void __launch_bounds__(256) lora_unpack_all_kernel(const LoraSiteDesc* __restrict__ descs, float* __restrict__ grad,
+                                                              const float* __restrict__ out_scale) {
+  const LoraSiteDesc& s = descs[blockIdx.y];
+  const float sc = out_scale != nullptr ? __ldg(out_scale) : 1.f;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int ad = 0; ad < s.n; ++ad) {
+    float* dA = grad + s.a_off[ad];
+    float* dB = grad + s.b_off[ad];
+    for (int64_t i = tid; i < (int64_t)s.in * s.r; i += stride) {
+      const int k = (int)(i / s.r), j = (int)(i % s.r);
+      dA[i] = sc * s.dA_pack[(int64_t)k * s.rpad + ad * s.r + j];
+    }
+    for (int64_t i = tid; i < (int64_t)s.r * s.out_len[ad]; i += stride) {
+      const int j = (int)(i / s.out_len[ad]), n = (int)(i % s.out_len[ad]);
+      dB[i] = sc * s.dB_pack[(int64_t)(ad * s.r + j) * s.out_total + s.out_off[ad] + n];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                                     float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
@@ -418,13 +467,23 @@ __global__ void __launch_bounds__(256) dropout_rows16_kernel(const uint16_t* __r
 
 template <typename F>
 int dispatch_vpt(int D, F&& f) {
+  // one warp per row, VPT float4 per lane: any width that is a multiple of 128 up to 2048 (SAM3: 1024; ViT-B 768, ViT-H 1280)
   switch (D) {
     case 128: return f(std::integral_constant<int, 1>{});
     case 256: return f(std::integral_constant<int, 2>{});
+    case 384: return f(std::integral_constant<int, 3>{});
     case 512: return f(std::integral_constant<int, 4>{});
+    case 640: return f(std::integral_constant<int, 5>{});
+    case 768: return f(std::integral_constant<int, 6>{});
+    case 896: return f(std::integral_constant<int, 7>{});
     case 1024: return f(std::integral_constant<int, 8>{});
+    case 1152: return f(std::integral_constant<int, 9>{});
+    case 1280: return f(std::integral_constant<int, 10>{});
+    case 1408: return f(std::integral_constant<int, 11>{});
+    case 1536: return f(std::integral_constant<int, 12>{});
+    case 1792: return f(std::integral_constant<int, 14>{});
     case 2048: return f(std::integral_constant<int, 16>{});
-    default: return fail(-1, "layernorm: D=%d not supported (128,256,512,1024,2048)", D);
+    default: return fail(-1, "layernorm: D=%d not supported (multiples of 128 up to 1536, 1792, 2048)", D);
   }
 }
 
@@ -575,6 +634,26 @@ int lora_unpack_grads(const LoraSite& site, const float* dA_pack, const float* d
   const int64_t work = (int64_t)site.r * std::max(site.in, site.out_total);
   const int blocks = (int)std::min<int64_t>((work + 255) / 256, 512);
   lora_unpack_kernel<<<blocks, 256, 0, s>>>(a);
+  SAM3B_LAUNCHED();
+  return 0;
+}
+
+int lora_pack_all(const LoraSiteDesc* dev_descs, int n_sites, int max_work, const float* flat, int dtype, cudaStream_t s) {
+  if (n_sites <= 0) return 0;
+  SAM3B_REQUIRE(dev_descs && flat && n_sites <= 65535, "lora_pack_all: bad arguments");
+  const dim3 grid(std::max(1, std::min((max_work + 255) / 256, 64)), n_sites);
+  if (dtype == 0) lora_pack_all_kernel<0><<<grid, 256, 0, s>>>(dev_descs, flat);
+  else lora_pack_all_kernel<1><<<grid, 256, 0, s>>>(dev_descs, flat);
+  SAM3B_LAUNCHED();
+  return 0;
+}
+
+int lora_unpack_all(const LoraSiteDesc* dev_descs, int n_sites, int max_work, float* grad_flat, const float* out_scale,
+                    cudaStream_t s) {
+  if (n_sites <= 0) return 0;
+  SAM3B_REQUIRE(dev_descs && grad_flat && n_sites <= 65535, "lora_unpack_all: bad arguments");
+  const dim3 grid(std::max(1, std::min((max_work + 255) / 256, 64)), n_sites);
+  lora_unpack_all_kernel<<<grid, 256, 0, s>>>(dev_descs, grad_flat, out_scale);
   SAM3B_LAUNCHED();
   return 0;
 }

@@ -77,6 +77,21 @@ int lora_pack(const LoraSite& site, void* down_T, void* w_ext, int64_t ldw, void
 int lora_unpack_grads(const LoraSite& site, const float* dA_pack, const float* dB_pack, float* const dA[3],
                       float* const dB[3], cudaStream_t s, const float* out_scale = nullptr);
 
+// Batched forms for the trunk engine: one launch for ALL adapted Linears of the trunk instead of one per site (128 pack +
+// 128 unpack launches and 256 memsets per step at depth 32).  Descriptors live in device memory (built once per bind);
+// adapter parameters / gradients are addressed as offsets into the flat LoRA buffers.
+struct LoraSiteDesc {
+  int in, out_total, n, r, rpad;
+  int out_off[3], out_len[3];
+  int64_t a_off[3], b_off[3];      // element offsets of A_a [in][r] / B_a [r][out_len] in the flat buffer
+  void *down_T, *w_ext, *up_pack, *wt_ext;
+  int64_t ldw, ldwt;
+  float *dA_pack, *dB_pack;        // this site's split-K accumulators ([in][rpad], [rpad][out_total]); null in inference layouts
+};
+int lora_pack_all(const LoraSiteDesc* dev_descs, int n_sites, int max_work, const float* flat, int dtype, cudaStream_t s);
+int lora_unpack_all(const LoraSiteDesc* dev_descs, int n_sites, int max_work, float* grad_flat, const float* out_scale,
+                    cudaStream_t s);
+
 // Fused AdamW over a flat fp32 buffer (torch.optim.AdamW semantics, train_sam3_lora_native.py:736-740).
 int adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                float weight_decay, int step, float grad_scale, cudaStream_t s);

@@ -160,11 +160,29 @@ void VitEngine::layout_work(Bump& b, int batch, bool training) {
     dO16_ = b.take<uint16_t>(M * D_);
     dqkv16_ = b.take<uint16_t>(M * (3 * D_ + Rmax_));
     xd16_ = b.take<uint16_t>(M * std::max(Dm_, D_));
-    const int max_feat = std::max(3 * D_, Dm_);
-    dA_pack_ = b.take<float>((int64_t)max_feat * std::max(Rmax_, 1));
-    dB_pack_ = b.take<float>((int64_t)max_feat * std::max(Rmax_, 1));
     gscale_ = b.take<float>(4);
+    // per-site split-K accumulators, contiguous
+    int64_t total = 0;
+    for (auto& w : blocks_)
+      for (Site* st : {&w.qkv, &w.proj, &w.fc1, &w.fc2})
+        if (st->R > 0) total += (int64_t)st->in * st->R + (int64_t)st->R * st->out;
+    wgrad_pack_ = b.take<float>(std::max<int64_t>(total, 1));
+    wgrad_pack_bytes_ = total * 4;
+    float* cur = wgrad_pack_;
+    for (auto& w : blocks_)
+      for (Site* st : {&w.qkv, &w.proj, &w.fc1, &w.fc2}) {
+        st->dA_pack = st->dB_pack = nullptr;
+        if (st->R > 0) {
+          st->dA_pack = cur; cur += (int64_t)st->in * st->R;
+          st->dB_pack = cur; cur += (int64_t)st->R * st->out;
+        }
+      }
+  } else {
+    wgrad_pack_ = nullptr; wgrad_pack_bytes_ = 0;
+    for (auto& w : blocks_)
+      for (Site* st : {&w.qkv, &w.proj, &w.fc1, &w.fc2}) st->dA_pack = st->dB_pack = nullptr;
   }
+  site_desc_dev_ = b.take<LoraSiteDesc>(4 * (int64_t)blocks_.size());
 }
 
 int64_t VitEngine::workspace_bytes(int batch, bool training) {
@@ -197,6 +215,7 @@ int VitEngine::bind(void* weight_buf, int64_t weight_bytes, void* work_buf, int6
   bound_training_ = training;
   Bump b(work_base_);
   layout_work(b, batch, training);
+  build_site_descs();
   last_saved_ = false;
   return 0;
 }
@@ -288,6 +307,29 @@ int VitEngine::pack_site(const Site& st, const float* lora_flat, cudaStream_t s)
   return lora_pack(make_site(st, lora_flat), st.down_T, st.w_ext, st.ldw, st.up_pack, st.wt_ext, st.ldwt, cfg_.dtype, s);
 }
 
+// Host copy of the device-resident descriptors of every adapted Linear (uploaded by the next forward).
+void VitEngine::build_site_descs() {
+  site_desc_host_.clear();
+  site_max_work_ = 0;
+  for (auto& w : blocks_)
+    for (const Site* st : {&w.qkv, &w.proj, &w.fc1, &w.fc2}) {
+      if (st->R == 0) continue;
+      LoraSiteDesc d{};
+      d.in = st->in; d.out_total = st->out; d.n = st->n_ad; d.r = cfg_.lora_rank; d.rpad = st->R;
+      for (int a = 0; a < st->n_ad; ++a) {
+        const LoraEntry& e = entries_[st->entry[a]];
+        d.out_off[a] = st->off[a]; d.out_len[a] = st->len[a];
+        d.a_off[a] = e.a_off; d.b_off[a] = e.b_off;
+      }
+      d.down_T = st->down_T; d.w_ext = st->w_ext; d.up_pack = st->up_pack; d.wt_ext = st->wt_ext;
+      d.ldw = st->ldw; d.ldwt = st->ldwt;
+      d.dA_pack = st->dA_pack; d.dB_pack = st->dB_pack;
+      site_desc_host_.push_back(d);
+      site_max_work_ = std::max(site_max_work_, st->R * std::max(st->in, st->out));
+    }
+  site_desc_dirty_ = true;
+}
+
 int VitEngine::set_lora_dropout(float p, uint32_t seed) {
   SAM3B_REQUIRE(p >= 0.f && p < 1.f, "vit set_lora_dropout: p=%f outside [0,1)", p);
   drop_p_ = p;
@@ -330,8 +372,7 @@ int VitEngine::site_wgrad(const Site& st, const uint16_t* x_act, int64_t ldx, co
     xa = xd16_;
     ldxa = st.in;
   }
-  SAM3B_CHECK_CUDA(cudaMemsetAsync(dA_pack_, 0, (size_t)st.in * st.R * 4, s));
-  SAM3B_CHECK_CUDA(cudaMemsetAsync(dB_pack_, 0, (size_t)st.R * st.out * 4, s));
+  SAM3B_REQUIRE(st.dA_pack && st.dB_pack, "vit backward: no weight-gradient workspace (bind with training = 1)");
   const int kb_total = (M + 63) / 64;
   auto splitk_for = [&](int feat) {
     const int m_tiles = (feat + 127) / 128;
@@ -345,7 +386,7 @@ int VitEngine::site_wgrad(const Site& st, const uint16_t* x_act, int64_t ldx, co
     a.A = dy_act; a.lda = lddy; a.a_mn = 1;
     a.B = x_act + st.in; a.ldb = ldx; a.b_mn = 1;
     a.dtype = cfg_.dtype; a.epilogue = EPI_ATOMIC_F32;
-    a.C = dB_pack_; a.ldc = st.out; a.c_trans = 1; a.splitk = splitk_for(st.out);
+    a.C = st.dB_pack; a.ldc = st.out; a.c_trans = 1; a.splitk = splitk_for(st.out);
     if ((rc = gemm_launch(a, s))) return rc;
   }
   {  // dA_pack [in][R] = x^T . dT''
@@ -354,17 +395,11 @@ int VitEngine::site_wgrad(const Site& st, const uint16_t* x_act, int64_t ldx, co
     a.A = xa; a.lda = ldxa; a.a_mn = 1;
     a.B = dy_act + st.out; a.ldb = lddy; a.b_mn = 1;
     a.dtype = cfg_.dtype; a.epilogue = EPI_ATOMIC_F32;
-    a.C = dA_pack_; a.ldc = st.R; a.splitk = splitk_for(st.in);
+    a.C = st.dA_pack; a.ldc = st.R; a.splitk = splitk_for(st.in);
     if ((rc = gemm_launch(a, s))) return rc;
   }
-  float* dA[3] = {nullptr, nullptr, nullptr};
-  float* dB[3] = {nullptr, nullptr, nullptr};
-  for (int a = 0; a < st.n_ad; ++a) {
-    const LoraEntry& e = entries_[st.entry[a]];
-    dA[a] = grad_flat + e.a_off;
-    dB[a] = grad_flat + e.b_off;
-  }
-  return lora_unpack_grads(make_site(st, nullptr), dA_pack_, dB_pack_, dA, dB, s, gscale_ + 1);
+  (void)grad_flat;   // un-packed for all sites at once at the end of backward() (lora_unpack_all)
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -393,12 +428,20 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
   }
   if ((rc = layernorm_fwd_f32(x_[0], ln_pre_g_, ln_pre_b_, cfg_.ln_eps, M, D_, x_[0], s))) return rc;
 
+  // adapter operands of ALL sites in one launch (the descriptors are uploaded once per bind, outside any graph capture)
+  if (!site_desc_host_.empty()) {
+    if (site_desc_dirty_) {
+      SAM3B_CHECK_CUDA(cudaMemcpyAsync(site_desc_dev_, site_desc_host_.data(), site_desc_host_.size() * sizeof(LoraSiteDesc),
+                                       cudaMemcpyHostToDevice, s));
+      site_desc_dirty_ = false;
+    }
+    if ((rc = lora_pack_all(site_desc_dev_, (int)site_desc_host_.size(), site_max_work_, lora_flat, dt, s))) return rc;
+  }
+
   for (int i = 0; i < cfg_.depth; ++i) {
     BlockW& w = blocks_[i];
     BlockAct& a = acts_[i];
     const int64_t ld_xn1 = D_ + w.qkv.R, ld_O = D_ + w.proj.R, ld_xn2 = D_ + w.fc1.R, ld_g = Dm_ + w.fc2.R;
-    for (const Site* st : {&w.qkv, &w.proj, &w.fc1, &w.fc2})
-      if ((rc = pack_site(*st, lora_flat, s))) return rc;
     // ---- attention half: x_mid = x + proj(attn(rope(qkv(LN1(x)))))
     if ((rc = layernorm_fwd(x_[i], w.g1, w.b1, cfg_.ln_eps, M, D_, a.xn1, ld_xn1, dt, a.mean1, a.rstd1, s))) return rc;
     if ((rc = site_down(w.qkv, a.xn1, ld_xn1, M, i, 0, s))) return rc;
@@ -482,6 +525,7 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
   // max|gout| (fp16 operands would otherwise flush a mean-reduced loss gradient, ~1e-9 per element, to zero); the
   // LoRA gradients are multiplied by 1/s when they are unpacked into grad_flat.
   if ((rc = grad_scale(gout_nchw, (int64_t)last_batch_ * D_ * T_, 256.f, gscale_, s))) return rc;
+  if (wgrad_pack_bytes_ > 0) SAM3B_CHECK_CUDA(cudaMemsetAsync(wgrad_pack_, 0, (size_t)wgrad_pack_bytes_, s));   // all split-K accumulators at once
   if ((rc = nchw_to_tokens(gout_nchw, last_batch_, G_, cfg_.window_size, D_, dx, dx16_, ld_dx16, dt, s, drop(cfg_.depth - 1, 1), gscale_))) return rc;
 
   // dst16[:, out .. out+R) = s * dy[:, :out] . B^T      (skinny GEMM; B operand = up_pack [R][out])
@@ -554,6 +598,9 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
     if ((rc = layernorm_bwd(dxn16_, D_, x_[i], a.mean1, a.rstd1, w.g1, dx, M, D_, dx_alt, dx16_, ld_dx16, dt, s, drop(i - 1, 1), T_))) return rc;
     std::swap(dx, dx_alt);
   }
+  // every site's packed weight gradients -> the flat gradient buffer, times 1/s, in one launch
+  if (!site_desc_host_.empty() &&
+      (rc = lora_unpack_all(site_desc_dev_, (int)site_desc_host_.size(), site_max_work_, grad_flat, gscale_ + 1, s))) return rc;
   last_saved_ = false;
   return 0;
 }

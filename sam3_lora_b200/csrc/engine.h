@@ -66,6 +66,7 @@ class VitEngine {
     uint16_t *w_ext = nullptr, *wt_ext = nullptr, *down_T = nullptr, *up_pack = nullptr;
     int64_t ldw = 0, ldwt = 0;
     const float* bias = nullptr;
+    float *dA_pack = nullptr, *dB_pack = nullptr;   // split-K weight-gradient accumulators of this site (training layouts)
   };
   struct BlockW {
     const float *g1, *b1, *g2, *b2;
@@ -104,7 +105,16 @@ class VitEngine {
   uint16_t* patches_ = nullptr;
   std::vector<float*> x_;  // residual stream, x_[i] = input of block i, x_[depth] = output
   std::vector<BlockAct> acts_;
-  float *dxa_ = nullptr, *dxb_ = nullptr, *delta_ = nullptr, *dA_pack_ = nullptr, *dB_pack_ = nullptr;
+  float *dxa_ = nullptr, *dxb_ = nullptr, *delta_ = nullptr;
+  // all sites' split-K accumulators are one region (zeroed by ONE memset per backward); descriptors of every adapted
+  // Linear live in device memory so that packing / unpacking is one launch each per step (elementwise.cuh)
+  float* wgrad_pack_ = nullptr;
+  int64_t wgrad_pack_bytes_ = 0;
+  LoraSiteDesc* site_desc_dev_ = nullptr;
+  std::vector<LoraSiteDesc> site_desc_host_;
+  int site_max_work_ = 0;
+  bool site_desc_dirty_ = true;
+  void build_site_descs();
   float* gscale_ = nullptr;   // device [s, 1/s, scratch]: power-of-two scale of the incoming gradient (grad_scale, conv.cuh)
   uint16_t *dx16_ = nullptr, *dh16_ = nullptr, *dxn16_ = nullptr, *dO16_ = nullptr, *dqkv16_ = nullptr;
   int Rmax_ = 0;

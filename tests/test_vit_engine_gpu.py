@@ -172,6 +172,25 @@ def test_other_ranks_match_oracle(rank, alpha):
     assert max(errs.values()) < GRAD_TOL, errs
 
 
+def test_vit_b_width_rank4_matches_oracle():
+    """BASELINE.json configs[0] shape (minimal_lora_config.yaml: 768-wide / 12-head trunk, rank 4) at reduced depth and
+    resolution: non-power-of-two width, 12 heads, MLP 3072."""
+    cfg = O.ViTConfig(img_size=224, patch_size=14, embed_dim=768, depth=2, num_heads=12, mlp_hidden=3072, window_size=8,
+                      global_att_blocks=(1,), pretrain_img_size=112)
+    spec = O.LoRASpec(rank=4, alpha=8.0)
+    params = O.make_params(cfg, spec, seed=23)
+    gen = torch.Generator().manual_seed(24)
+    img = torch.randn(2, 3, 224, 224, generator=gen)
+    gout = torch.randn(2, 768, 16, 16, generator=gen) * 0.1
+    eng = _engine_for(cfg, spec, params)
+    out, grads = _run(eng, cfg, params, img, gout)
+    ref_out, ref_grads = O.train_step_reference(img, params, cfg, spec, gout)
+    errs = {k: rel_l2(grads[k], ref_grads[k]) for k in ref_grads}
+    _report("vit_b_width_rank4_fp16", {"out_rel_l2": rel_l2(out, ref_out), "grad_rel_l2_max": max(errs.values())})
+    assert rel_l2(out, ref_out) < FWD_TOL
+    assert max(errs.values()) < GRAD_TOL, errs
+
+
 def test_full_width_blocks_match_oracle():
     """SAM3's real geometry (1008 px, 72x72 tokens, D=1024, 16 heads, 4736 MLP, 24x24 windows, r=16),
     depth cut to 3 with block 2 global so the CPU oracle finishes in seconds."""
