@@ -230,7 +230,7 @@ def run_native(args):
         torch.cuda.synchronize()
         n_before = L.launch_count()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             fwd_bwd()
         launches_per_fwd_bwd = L.launch_count() - n_before
 

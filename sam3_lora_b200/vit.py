@@ -125,7 +125,7 @@ class _TrunkFn(torch.autograd.Function):
                 eng.forward(st.img, flat, st.out, save_for_backward=True)
             elif st.g_fwd is None:
                 st.g_fwd = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(st.g_fwd):
+                with torch.cuda.graph(st.g_fwd, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may touch CUDA
                     eng.forward(st.img, flat, st.out, save_for_backward=True)
                 st.g_fwd.replay()
             else:
@@ -156,7 +156,7 @@ class _TrunkFn(torch.autograd.Function):
                 st.warm = True
             elif st.g_bwd is None or st.g_bwd[1] != gflat.data_ptr():
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     eng.backward(st.gout, gflat)
                 st.g_bwd = (g, gflat.data_ptr())
                 g.replay()
