@@ -82,6 +82,9 @@ VitEngine::VitEngine(const VitConfig& cfg) : cfg_(cfg) {
     single(b.fc1, LT_FC1);
     single(b.fc2, LT_FC2);
     for (Site* s : {&b.qkv, &b.proj, &b.fc1, &b.fc2}) {
+      // K-extension width: total adapter rank rounded up to a whole 64-wide k-block.  Rounding to the MMA K step (16) would
+      // skip 3 of the last k-block's 4 MMAs, but makes the operand row pitch (in + R) * 2 B a non-multiple of 128 B: every TMA
+      // box row then straddles two lines; measured 0.5 % SLOWER per step (round-1 A/B), so 64 stays.
       s->R = s->n_ad > 0 ? round_up(s->n_ad * r, 64) : 0;
       s->ldw = s->in + s->R;
       s->ldwt = s->out + s->R;
