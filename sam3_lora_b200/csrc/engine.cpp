@@ -121,8 +121,12 @@ void VitEngine::layout_weights(Bump& b) {
   }
 }
 
+// rows of the head-major attention statistics (lse2, delta): every segment of L queries is padded to a multiple of 64
+static int64_t g_stat_rows(int64_t M, int L) { return (M / L) * (int64_t)((L + 63) / 64 * 64); }
+
 void VitEngine::layout_work(Bump& b, int batch, bool training) {
   const int64_t M = (int64_t)batch * T_;
+  const int64_t stat_rows = std::max(g_stat_rows(M, cfg_.window_size * cfg_.window_size), g_stat_rows(M, T_));
   const int depth = cfg_.depth;
   const int nsave = training ? depth : 1;
   patches_ = b.take<uint16_t>(M * Kpe_pad_);
@@ -140,7 +144,7 @@ void VitEngine::layout_work(Bump& b, int batch, bool training) {
     const BlockW& w = blocks_[std::min(i, depth - 1)];
     BlockAct& a = saved[i];
     a.x_mid = b.take<float>(M * D_);
-    a.lse2 = b.take<float>(M * H_);
+    a.lse2 = b.take<float>(stat_rows * H_);
     a.mean1 = b.take<float>(M); a.rstd1 = b.take<float>(M);
     a.mean2 = b.take<float>(M); a.rstd2 = b.take<float>(M);
     // widths use Rmax_ so that a single saved slot (inference) fits every block
@@ -156,7 +160,7 @@ void VitEngine::layout_work(Bump& b, int batch, bool training) {
   if (training) {
     dxa_ = b.take<float>(M * D_);
     dxb_ = b.take<float>(M * D_);
-    delta_ = b.take<float>(M * H_);
+    delta_ = b.take<float>(stat_rows * H_);
     dx16_ = b.take<uint16_t>(M * (D_ + Rmax_));
     dh16_ = b.take<uint16_t>(M * (Dm_ + Rmax_));
     dxn16_ = b.take<uint16_t>(M * D_);
@@ -579,8 +583,22 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
     // ---- attention half.  dx16_ holds dy for proj.
     if ((rc = site_up_grad(w.proj, dx16_, ld_dx16))) return rc;
     if ((rc = site_wgrad(w.proj, a.O, ld_O, dx16_, ld_dx16, M, grad_flat, i, 1, s))) return rc;
-    if ((rc = site_dgrad(w.proj, dx16_, ld_dx16, EPI_STORE16, dO16_, D_, nullptr, 0, i, 1))) return rc;
-    if ((rc = attn_delta(dO16_, D_, a.O, ld_O, M, H_, dt, delta_, s))) return rc;
+    if (fwd_drop_p_ > 0.f && w.proj.R > 0) {
+      // adapter dropout splits this dgrad into two GEMMs: delta needs the final dO, so it stays a separate pass
+      if ((rc = site_dgrad(w.proj, dx16_, ld_dx16, EPI_STORE16, dO16_, D_, nullptr, 0, i, 1))) return rc;
+      if ((rc = attn_delta(dO16_, D_, a.O, ld_O, M, H_, dt, delta_, s))) return rc;
+    } else {
+      // dO = dy . [W^T | A]^T and delta = rowsum(dO * O) per head in the same epilogue (O read once, no extra launch)
+      const int L = w.global ? T_ : ws2;
+      SAM3B_CHECK_CUDA(cudaMemsetAsync(delta_, 0, (size_t)g_stat_rows(M, L) * H_ * sizeof(float), s));
+      GemmArgs g;
+      g.M = M; g.N = w.proj.in; g.K = w.proj.out + w.proj.R;
+      g.A = dx16_; g.lda = ld_dx16; g.B = w.proj.wt_ext; g.ldb = w.proj.ldwt;
+      g.dtype = dt; g.epilogue = EPI_STORE16_DELTA; g.C = dO16_; g.ldc = D_;
+      g.aux = a.O; g.ldaux = ld_O;
+      g.delta = delta_; g.delta_Lq = L; g.delta_Lq_stat = (L + 63) / 64 * 64; g.delta_stride = (int64_t)(M / L) * g.delta_Lq_stat;
+      if ((rc = gemm_launch(g, s))) return rc;
+    }
     {
       const int L = w.global ? T_ : ws2;
       AttnArgs b;

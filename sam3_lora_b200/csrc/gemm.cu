@@ -43,6 +43,7 @@ struct GemmParams {
   float alpha;
   int c_trans;
   uint32_t mn_lbo, mn_sbo;
+  float* delta; int delta_Lq, delta_Lq_stat; int64_t delta_stride;
 };
 
 
@@ -207,6 +208,25 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
       v[2 * i] *= dgelu_erf(hh.x);
       v[2 * i + 1] *= dgelu_erf(hh.y);
     }
+    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
+  } else if constexpr (EPI == EPI_STORE16_DELTA) {
+    // O (the forward attention output, 16-bit) through the staging tile, like h in the DGELU epilogue
+    stage_fill(stg, lane, reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row0 * p.ldaux + col),
+               p.ldaux * 2, rows_valid, nvalid * 2);
+    __syncwarp();
+    uint32_t ow[16];
+    stage_get_row(stg, lane, ow);
+    __syncwarp();
+    float dsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 g = unpack2<DT>(pack2<DT>(v[2 * i], v[2 * i + 1]));   // the 16-bit dO the attention kernels will read
+      const float2 o = unpack2<DT>(ow[i]);
+      dsum = fmaf(g.x, o.x, dsum);
+      dsum = fmaf(g.y, o.y, dsum);
+    }
+    // two 32-column chunks per 64-wide head: two commutative adds per (row, head) -> bitwise deterministic
+    if (row_ok) atomicAdd(p.delta + (int64_t)(col >> 6) * p.delta_stride + (int64_t)(row / p.delta_Lq) * p.delta_Lq_stat + row % p.delta_Lq, dsum);
     store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_ADDMASK16) {
     if (row_ok) {
@@ -830,11 +850,12 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.rope = reinterpret_cast<const float2*>(a.rope); p.rope_period = a.rope_period > 0 ? a.rope_period : 1;
   p.rope_cols = a.rope_cols;
   p.alpha = a.alpha; p.c_trans = a.c_trans;
+  p.delta = a.delta; p.delta_Lq = a.delta_Lq > 0 ? a.delta_Lq : 1; p.delta_Lq_stat = a.delta_Lq_stat; p.delta_stride = a.delta_stride;
   p.mn_lbo = a.dbg_lbo > 0 ? a.dbg_lbo : 8192;
   p.mn_sbo = a.dbg_sbo > 0 ? a.dbg_sbo : 1024;
 
   const bool is16 = (a.epilogue == EPI_STORE16 || a.epilogue == EPI_QKV_ROPE || a.epilogue == EPI_GELU ||
-                     a.epilogue == EPI_DGELU || a.epilogue == EPI_ADDMASK16);
+                     a.epilogue == EPI_DGELU || a.epilogue == EPI_ADDMASK16 || a.epilogue == EPI_STORE16_DELTA);
   if (a.epilogue != EPI_ATOMIC_F32) {
     SAM3B_REQUIRE(a.ldc % (is16 ? 8 : 4) == 0, "gemm: ldc=%lld breaks 16-byte store alignment", (long long)a.ldc);
     SAM3B_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "gemm: C not 16-byte aligned");
@@ -845,6 +866,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   if (a.epilogue == EPI_RESIDUAL_F32) SAM3B_REQUIRE(a.residual != nullptr && a.ldres % 4 == 0, "gemm: residual epilogue needs residual with ld %% 4 == 0");
   if (a.epilogue == EPI_GELU) SAM3B_REQUIRE(a.C2 != nullptr && a.ldc2 % 8 == 0, "gemm: gelu epilogue needs C2");
   if (a.epilogue == EPI_DGELU) SAM3B_REQUIRE(a.aux != nullptr && a.ldaux % 8 == 0, "gemm: dgelu epilogue needs aux");
+  if (a.epilogue == EPI_STORE16_DELTA)
+    SAM3B_REQUIRE(a.aux != nullptr && a.ldaux % 8 == 0 && a.delta != nullptr && a.N % 64 == 0 && a.delta_Lq > 0 && a.bias == nullptr,
+                  "gemm: delta epilogue needs aux (O), a zeroed delta buffer, N %% 64 == 0 and no bias");
   if (a.bias) SAM3B_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias not 16-byte aligned");
 
   if (a.a_mn) {
@@ -870,6 +894,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
       case EPI_RESIDUAL_F32: return launch_pair_dt<EPI_RESIDUAL_F32>(a, p, stream);
       case EPI_GELU: return launch_pair_dt<EPI_GELU>(a, p, stream);
       case EPI_DGELU: return launch_pair_dt<EPI_DGELU>(a, p, stream);
+      case EPI_STORE16_DELTA: return launch_pair_dt<EPI_STORE16_DELTA>(a, p, stream);
       case EPI_STORE32: return launch_pair_dt<EPI_STORE32>(a, p, stream);
       case EPI_ADDMASK16: return launch_pair_dt<EPI_ADDMASK16>(a, p, stream);
       default: break;
@@ -881,6 +906,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     case EPI_RESIDUAL_F32: return launch_dt<256, EPI_RESIDUAL_F32, false, false>(a, p, stream);
     case EPI_GELU: return launch_dt<256, EPI_GELU, false, false>(a, p, stream);
     case EPI_DGELU: return launch_dt<256, EPI_DGELU, false, false>(a, p, stream);
+    case EPI_STORE16_DELTA: return launch_dt<256, EPI_STORE16_DELTA, false, false>(a, p, stream);
     case EPI_STORE32: return launch_dt<256, EPI_STORE32, false, false>(a, p, stream);
     case EPI_ADDMASK16: return launch_dt<256, EPI_ADDMASK16, false, false>(a, p, stream);
     default: return fail(-1, "gemm: epilogue %d not instantiated for BN=256", a.epilogue);

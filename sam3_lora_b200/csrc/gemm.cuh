@@ -15,6 +15,8 @@ enum GemmEpilogue : int {
   EPI_ATOMIC_F32 = 5,    // C32 (+)= alpha*acc with red.global.add (split-K), optional transpose
   EPI_STORE32 = 6,       // C32 = [row_scale[row/rows_per_scale] *] (alpha*acc (+bias))
   EPI_ADDMASK16 = 7,     // C16 += keep(row,col)/(1-p) * alpha*acc [* gelu_erf'(aux16)]   (adapter dgrad under dropout)
+  EPI_STORE16_DELTA = 8, // C16 = acc ; delta[col/64][row'] += sum_c C16[row][c] * aux16[row][c]  (proj dgrad: dO and the
+                         // flash-attention backward's delta = rowsum(dO * O) per head in one pass; engine-internal)
   EPI_COUNT
 };
 
@@ -37,6 +39,8 @@ struct GemmArgs {
   int c_trans = 0;      // EPI_ATOMIC_F32 only: write C[col*ldc + row]
   int bn = 0;           // 0 = choose; else 64 or 256
   int dbg_lbo = 0, dbg_sbo = 0;  // bring-up overrides for the MN-major descriptors (bytes); 0 = default
+  float* delta = nullptr; int delta_Lq = 0, delta_Lq_stat = 0; int64_t delta_stride = 0;  // EPI_STORE16_DELTA: head-major
+                        // statistics layout of the attention kernels: delta[h * stride + (row / Lq) * Lq_stat + row % Lq], zeroed by the caller
   int max_ctas = 0;     // 0 = number of SMs
   int cta_pair = 0;     // 0 = default policy, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) 256x256 tiles
 };
