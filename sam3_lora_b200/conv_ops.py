@@ -434,6 +434,10 @@ class _PixelDecoderFn(torch.autograd.Function):
 def pixel_decoder_forward(feats: Sequence[torch.Tensor], convs, norms, shared_conv: bool) -> torch.Tensor:
     if len(feats) == 1:   # a single level: the reference's loop body never runs and it returns backbone_feats[-1]
         return feats[-1]
+    # the reference relies on broadcasting when the backbone maps have batch 1 and the encoder map one entry per query
+    # (maskformer_segmentation.py:118-120, 209): make the batch explicit (autograd sums the expanded gradient back)
+    bmax = max(f.shape[0] for f in feats)
+    feats = [f.expand(bmax, -1, -1, -1) if (f.shape[0] == 1 and bmax > 1) else f for f in feats]
     return _PixelDecoderFn.apply(list(convs), list(norms), bool(shared_conv), *feats)
 
 

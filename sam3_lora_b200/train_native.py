@@ -7,12 +7,13 @@ argument; reads `lora.*`, `training.{learning_rate,weight_decay,data_dir,batch_s
 (:46-232); AdamW over the adapters (:736-740); saves `best_lora_weights.pt` / `last_lora_weights.pt`
 with `save_lora_weights` and appends JSON lines to `val_stats.json` (:995-1016).
 
-Scope note: this round builds the image-encoder trunk (rows a1-a6).  The DETR
-encoder/decoder, segmentation head, Hungarian matcher and SAM3 losses are "next" rows, so the
-objective here is a stand-in: a 1x1-conv mask head on the trunk features trained with BCE + dice against
-the union of the image's instance masks at 72x72 (the HF-path trainer of the reference also trains
-with a plain mask BCE, train_sam3_lora.py:319-355).  Everything trunk-side — LoRA injection, fused
-kernels, flat-gradient all-reduce, checkpoint format — is the production path.
+Scope note: the objective here is a stand-in — a 1x1-conv mask head on the trunk features trained with
+BCE + dice against the union of the image's instance masks at 72x72 (the HF-path trainer of the reference also trains with
+a plain mask BCE, train_sam3_lora.py:319-355) — because the full `Sam3Image` wiring (text encoder, geometry encoder, DETR
+encoder/decoder around the trunk) is the reference's and is not rebuilt in this repo.  The pieces of that wiring that ARE
+on the hot path exist as drop-in modules and are exercised end to end by tests/test_chain_gpu.py: `necks.py`,
+`maskformer_segmentation.py`, `mha.py`, `matcher.py` (GPU Hungarian matcher), `losses.py` (fused focal / dice / up-sample).
+Everything trunk-side — LoRA injection, fused kernels, flat-gradient all-reduce, checkpoint format — is the production path.
 """
 from __future__ import annotations
 

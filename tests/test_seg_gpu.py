@@ -340,6 +340,32 @@ def test_neck_and_mask_head_at_sam3_widths_against_oracle():
     assert max(errs) < 5e-3, errs
 
 
+def test_pixel_decoder_broadcasts_batch_one_backbone_maps():
+    """UniversalSegmentationHead with a single image and several prompts: backbone maps have batch 1, the encoder map has
+    one entry per prompt, and the reference adds them by broadcasting (maskformer_segmentation.py:118-120, 209)."""
+    from oracle import seg_oracle as SO
+    from sam3_lora_b200.maskformer_segmentation import PixelDecoder
+
+    d = 32
+    ps = SO.make_seg_params(d, 2, seed=41)
+    pd = PixelDecoder(d, 2)
+    pd.load_state_dict({k[len("pixel_decoder."):]: v for k, v in ps.items() if k.startswith("pixel_decoder.")})
+    pd = _frozen(pd).to(DEV)
+    g = torch.Generator().manual_seed(42)
+    feats = [torch.randn(1, d, 32, 32, generator=g), torch.randn(1, d, 16, 16, generator=g), torch.randn(3, d, 8, 8, generator=g)]
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    fg = [f.to(DEV).requires_grad_(True) for f in feats]
+    ref = SO.pixel_decoder(fr, ps, prefix="pixel_decoder.", operand_dtype=torch.float16)
+    out = pd(fg)
+    assert out.shape == ref.shape == (3, d, 32, 32)
+    assert rel_l2(out.detach().cpu(), ref.detach()) < 5e-4
+    cot = torch.randn(ref.shape, generator=g)
+    (ref * cot).sum().backward()
+    (out * cot.to(DEV)).sum().backward()
+    for a, b in zip(fg, fr):
+        assert a.grad.shape == b.grad.shape and rel_l2(a.grad.cpu(), b.grad) < 5e-3
+
+
 def test_cpu_tensors_are_rejected():
     from sam3_lora_b200 import _lib
     from sam3_lora_b200.necks import Sam3DualViTDetNeck
