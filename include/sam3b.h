@@ -234,6 +234,19 @@ typedef struct sam3b_matcher_desc {
  * column c of image b is target c % num_boxes[b] (np.tile of the cost matrix when repeats > 1) */
 int sam3b_matcher(const sam3b_matcher_desc* d, float* cost, int32_t* query_of_col, int32_t* col_of_query, void* stream);
 
+/* ---- input pipeline (next-row f4): the reference's host-side sample preparation (train_sam3_lora_native.py:101-108, 146-167)
+ * on the GPU, bit-exactly: PILImage.resize(BILINEAR) + ToTensor + Normalize, and RLE decode + nearest resize + > 0.5. */
+/* HOST function: Pillow's coefficient tables for one axis (bounds [out][2], coeffs [out][ksize] int32); returns ksize
+ * (call with NULL tables to query it), negative on error. */
+int sam3b_resample_coeffs(int32_t in_size, int32_t out_size, int32_t* bounds, int32_t* coeffs);
+/* src [h][w][3] uint8 (device) -> dst [3][out][out] fp32; tmp: h*out*3 bytes of scratch; tables in device memory */
+int sam3b_image_resize_normalize(const uint8_t* src, int32_t h, int32_t w, int32_t out, const int32_t* bounds_x, const int32_t* coeffs_x,
+                                 int32_t ks_x, const int32_t* bounds_y, const int32_t* coeffs_y, int32_t ks_y, uint8_t* tmp, float* dst,
+                                 float mean, float std, void* stream);
+/* N RLE masks (cumulative run lengths, column-major, first run = zeros) -> dst [N][out][out] uint8 in {0, 1} */
+int sam3b_rle_masks_nearest(const uint32_t* cum, const int32_t* offs, const int32_t* hw, int32_t N, int32_t out, uint8_t* dst,
+                            void* stream);
+
 /* ---- neck / pixel decoder / mask head helpers (row a8: sam3/model/necks.py:100-125, maskformer_segmentation.py:23-51,
  * 203-219).  The convolutions run on sam3b_gemm; these are the HBM-bound kernels around it.  Activations: channels-last
  * (NHWC) 16-bit; element-type codes below: 0 = 16-bit (per `dtype`), 1 = fp32. */

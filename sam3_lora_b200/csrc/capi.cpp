@@ -7,6 +7,7 @@
 #include "elementwise.cuh"
 #include "engine.h"
 #include "gemm.cuh"
+#include "input.cuh"
 #include "loss.cuh"
 #include "matcher.cuh"
 
@@ -221,6 +222,20 @@ int sam3b_matcher(const sam3b_matcher_desc* d, float* cost, int32_t* query_of_co
   a.w_class = d->w_class; a.w_bbox = d->w_bbox; a.w_giou = d->w_giou;
   a.focal = d->focal; a.stable = d->stable; a.alpha = d->alpha; a.gamma = d->gamma;
   return matcher_run(a, cost, query_of_col, col_of_query, static_cast<cudaStream_t>(stream));
+}
+
+int sam3b_resample_coeffs(int32_t in_size, int32_t out_size, int32_t* bounds, int32_t* coeffs) {
+  return resample_coeffs(in_size, out_size, bounds, coeffs);
+}
+int sam3b_image_resize_normalize(const uint8_t* src, int32_t h, int32_t w, int32_t out, const int32_t* bounds_x, const int32_t* coeffs_x,
+                                 int32_t ks_x, const int32_t* bounds_y, const int32_t* coeffs_y, int32_t ks_y, uint8_t* tmp, float* dst,
+                                 float mean, float std, void* stream) {
+  return image_resize_normalize(src, h, w, out, bounds_x, coeffs_x, ks_x, bounds_y, coeffs_y, ks_y, tmp, dst, mean, std,
+                                static_cast<cudaStream_t>(stream));
+}
+int sam3b_rle_masks_nearest(const uint32_t* cum, const int32_t* offs, const int32_t* hw, int32_t N, int32_t out, uint8_t* dst,
+                            void* stream) {
+  return rle_masks_nearest(cum, offs, hw, N, out, dst, static_cast<cudaStream_t>(stream));
 }
 
 #define SAM3B_ST static_cast<cudaStream_t>(stream)

@@ -1,0 +1,83 @@
+"""Row f4 on the CPU: the input-pipeline oracle is pinned bit-exactly against the Pillow and PyTorch installed in the build
+container (the third-party code the reference calls), and the HOST coefficient routine of libsam3b against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import input_oracle as IO
+
+SIZES = [(64, 80, 50), (37, 53, 100), (120, 90, 48), (100, 100, 64), (33, 47, 94), (256, 200, 252)]
+
+
+@pytest.mark.parametrize("h,w,out", SIZES)
+def test_resize_oracle_is_bit_exact_with_pillow_and_torch_normalize(h, w, out):
+    from PIL import Image
+
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((out, out), Image.BILINEAR))
+    got = IO.resize_bilinear_u8(img, out, out)
+    assert np.array_equal(got, ref)
+    # ToTensor + Normalize(0.5, 0.5) as torchvision does them (float32 ops)
+    t = torch.from_numpy(ref.copy()).permute(2, 0, 1).to(torch.float32).div(255)
+    t = t.sub_(torch.tensor([0.5, 0.5, 0.5]).view(3, 1, 1)).div_(torch.tensor([0.5, 0.5, 0.5]).view(3, 1, 1))
+    assert np.array_equal(IO.to_tensor_normalize(got), t.numpy())
+
+
+@pytest.mark.parametrize("in_size,out_size", [(1024, 1008), (640, 1008), (512, 1008), (1008, 1008), (2000, 1008), (53, 100), (7, 1008)])
+def test_library_coefficients_equal_the_oracle(in_size, out_size):
+    from sam3_lora_b200.data import resample_coeffs
+
+    b, k, ks = resample_coeffs(in_size, out_size)
+    rb, rk, rks = IO.resample_coeffs(in_size, out_size)
+    assert ks == rks and np.array_equal(b, rb) and np.array_equal(k, rk)
+    assert (k.sum(1) - (1 << IO.PRECISION_BITS)).__abs__().max() <= k.shape[1]     # rows are normalised up to rounding
+
+
+def _random_rle(rng, h, w):
+    runs, left = [], h * w
+    while left > 0:
+        c = int(min(left, rng.integers(0, 3 * h)))
+        runs.append(c)
+        left -= c
+    return runs
+
+
+@pytest.mark.parametrize("h,w,out", [(40, 60, 100), (100, 50, 100), (50, 50, 100), (120, 77, 84), (1, 9, 16)])
+def test_rle_mask_oracle_matches_numpy_decode_and_torch_nearest(h, w, out):
+    rng = np.random.default_rng(h + w)
+    counts = _random_rle(rng, h, w)
+    m = IO.rle_decode(counts, h, w)
+    flat = np.concatenate([np.full(c, i & 1, np.uint8) for i, c in enumerate(counts)])[: h * w]
+    assert np.array_equal(m, np.pad(flat, (0, h * w - len(flat))).reshape(w, h).T)
+    ref = torch.nn.functional.interpolate(torch.from_numpy(m).float()[None, None], size=(out, out), mode="nearest")[0, 0] > 0.5
+    assert np.array_equal(IO.rle_mask_resized(counts, h, w, out), ref.numpy())
+
+
+def test_compressed_rle_string_round_trip():
+    """rleFrString restated twice (oracle and sam3_lora_b200.data) against an encoder written from maskApi.c's rleToString."""
+    from sam3_lora_b200.data import rle_counts
+
+    def to_string(cnts):
+        s = []
+        for i, c in enumerate(cnts):
+            x = int(c)
+            if i > 2:
+                x -= int(cnts[i - 2])
+            more = True
+            while more:
+                ch = x & 0x1F
+                x >>= 5
+                more = (x != -1) if (ch & 0x10) else (x != 0)
+                if more:
+                    ch |= 0x20
+                s.append(chr(ch + 48))
+        return "".join(s)
+
+    rng = np.random.default_rng(7)
+    for _ in range(20):
+        cnts = [int(v) for v in rng.integers(0, 5000, size=rng.integers(1, 40))]
+        enc = to_string(cnts)
+        assert IO.rle_from_string(enc) == cnts
+        assert rle_counts(enc) == cnts and rle_counts(enc.encode()) == cnts
+    assert rle_counts([3, 4, 5]) == [3, 4, 5]
