@@ -73,7 +73,11 @@ class GpuPreprocessor:
     def image(self, rgb: Union[np.ndarray, torch.Tensor]) -> torch.Tensor:
         if self.device.type != "cuda":
             raise L.Sam3bError("GpuPreprocessor needs a CUDA device (the reference's PIL code is the CPU path)")
-        t = torch.from_numpy(np.ascontiguousarray(rgb)) if isinstance(rgb, np.ndarray) else rgb
+        if isinstance(rgb, np.ndarray):
+            rgb = np.ascontiguousarray(rgb)
+            if not rgb.flags.writeable:          # e.g. np.asarray(PIL image): torch wants a writable buffer
+                rgb = rgb.copy()
+        t = torch.from_numpy(rgb) if isinstance(rgb, np.ndarray) else rgb
         if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
             raise L.Sam3bError(f"image: expected uint8 [H, W, 3], got {t.dtype} {tuple(t.shape)}")
         t = t.to(self.device, non_blocking=True).contiguous()

@@ -76,7 +76,14 @@ def _ann_to_mask(ann: Dict, h: int, w: int) -> np.ndarray:
 class COCOSegmentDataset(torch.utils.data.Dataset):
     """Same directory contract as the reference: `<data_dir>/<split>/_annotations.coco.json` + images."""
 
-    def __init__(self, data_dir, split: str = "train", mask_size: int = 72, resolution: int = RESOLUTION):
+    def __init__(self, data_dir, split: str = "train", mask_size: int = 72, resolution: int = RESOLUTION, device=None):
+        # device: a CUDA device -> the image is resized / normalised on the GPU by data.GpuPreprocessor (bit-identical to the
+        # PIL + numpy path below; only the raw uint8 pixels cross PCIe).  None -> host path (CPU tests, the reference's way).
+        self.gpu_prep = None
+        if device is not None and torch.device(device).type == "cuda":
+            from .data import GpuPreprocessor  # noqa: PLC0415
+
+            self.gpu_prep = GpuPreprocessor(resolution, device=device)
         self.split_dir = Path(data_dir) / split
         ann_file = self.split_dir / "_annotations.coco.json"
         if not ann_file.exists():
@@ -104,9 +111,12 @@ class COCOSegmentDataset(torch.utils.data.Dataset):
         info = self.images[self.image_ids[idx]]
         img = Image.open(self.split_dir / info["file_name"]).convert("RGB")
         w0, h0 = img.size
-        img = img.resize((self.resolution, self.resolution), Image.BILINEAR)
-        x = torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1)
-        x = (x - 0.5) / 0.5
+        if self.gpu_prep is not None:
+            x = self.gpu_prep.image(np.asarray(img))
+        else:
+            img = img.resize((self.resolution, self.resolution), Image.BILINEAR)
+            x = torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1)
+            x = (x - 0.5) / 0.5
         union = np.zeros((h0, w0), dtype=np.uint8)
         names = []
         for a in self.img_to_anns.get(info["id"], []):
@@ -189,11 +199,13 @@ class SAM3TrainerNative:
 
     def _loader(self, split: str, epoch: int, shuffle: bool):
         spec = self.model.trunk.spec
-        ds = COCOSegmentDataset(self.config["training"]["data_dir"], split, mask_size=spec.grid, resolution=spec.img_size)
+        gpu_prep = bool(self.config["training"].get("gpu_preprocess", True))      # not a reference key; default on
+        ds = COCOSegmentDataset(self.config["training"]["data_dir"], split, mask_size=spec.grid, resolution=spec.img_size,
+                                device=self.device if gpu_prep else None)
         idx = D.shard_indices(len(ds), self.rank, self.world, epoch=epoch, shuffle=shuffle)
         sub = torch.utils.data.Subset(ds, idx)
         return torch.utils.data.DataLoader(sub, batch_size=self.batch_size, shuffle=False, num_workers=0, collate_fn=collate,
-                                           pin_memory=True, drop_last=False)
+                                           pin_memory=not gpu_prep, drop_last=False)
 
     def _sync_head_grads(self):
         if self.world > 1:

@@ -39,3 +39,18 @@ def test_trainer_runs_saves_and_learns(tmp_path):
     assert (out / "best_lora_weights.pt").exists()
     assert set(blob) == set(before) and all(k.startswith("backbone.vision_backbone.trunk.blocks.") for k in blob)
     assert any(not torch.equal(blob[k].cpu(), before[k].cpu()) for k in blob if k.endswith("lora_B"))
+
+
+def test_dataset_gpu_preprocessing_equals_the_host_path(tmp_path):
+    """COCOSegmentDataset(device="cuda") resizes / normalises on the GPU (data.GpuPreprocessor): bit-identical images."""
+    data = tmp_path / "coco"
+    subprocess.run([sys.executable, str(ROOT / "tools" / "make_synthetic_coco.py"), str(data), "--n-train", "2", "--n-valid", "1",
+                    "--size", "160"], check=True)
+    from sam3_lora_b200.train_native import COCOSegmentDataset
+
+    host = COCOSegmentDataset(data, "train", mask_size=16, resolution=224)
+    gpu = COCOSegmentDataset(data, "train", mask_size=16, resolution=224, device="cuda")
+    for i in range(len(host)):
+        a, b = host[i], gpu[i]
+        assert b["image"].is_cuda and torch.equal(b["image"].cpu(), a["image"])
+        assert torch.equal(a["mask"], b["mask"]) and a["prompt"] == b["prompt"]
