@@ -40,7 +40,7 @@ def test_ctypes_signatures_cover_the_header():
 
 def test_struct_layouts_match_header_field_order():
     from sam3_lora_b200 import _lib
-    from sam3_lora_b200._abi import AttnDesc, LoraSite
+    from sam3_lora_b200._abi import AttnDesc, LoraSite, MatcherDesc
     from sam3_lora_b200.engine import LoraEntryC, VitConfigC
 
     header = (ROOT / "include" / "sam3b.h").read_text()
@@ -67,6 +67,36 @@ def test_struct_layouts_match_header_field_order():
     assert fields("sam3b_lora_site") == py(LoraSite)
     assert fields("sam3b_vit_config") == py(VitConfigC)
     assert fields("sam3b_lora_entry") == py(LoraEntryC)
+    assert fields("sam3b_matcher_desc") == py(MatcherDesc)
+
+
+def test_neck_matcher_loss_and_input_paths_fail_loudly_without_gpu():
+    """Rows a8 / f1 / f2 / f4 have no CPU fallback either: CPU tensors raise Sam3bError before any kernel is launched."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    import torch.nn as nn
+
+    from sam3_lora_b200 import _lib, conv_ops
+    from sam3_lora_b200.data import GpuPreprocessor
+    from sam3_lora_b200.losses import mask_losses, sigmoid_focal_loss
+    from sam3_lora_b200.matcher import BinaryHungarianMatcherV2
+
+    with pytest.raises(_lib.Sam3bError):
+        conv_ops.conv1x1_forward(torch.zeros(1, 8, 4, 4), nn.Conv2d(8, 8, 1).requires_grad_(False))
+    with pytest.raises(_lib.Sam3bError):
+        conv_ops.mask_einsum(torch.zeros(1, 8, 8), torch.zeros(1, 8, 4, 4))
+    with pytest.raises(_lib.Sam3bError):
+        mask_losses(torch.zeros(1, 4, 4), torch.zeros(1, 8, 8), 1.0)
+    with pytest.raises(_lib.Sam3bError):
+        sigmoid_focal_loss(torch.zeros(2, 8), torch.zeros(2, 8), 1.0)
+    with pytest.raises(_lib.Sam3bError):
+        BinaryHungarianMatcherV2()({"pred_logits": torch.zeros(1, 4, 1), "pred_boxes": torch.rand(1, 4, 4)},
+                                   {"boxes_padded": torch.rand(1, 2, 4), "num_boxes": torch.tensor([2])})
+    with pytest.raises(_lib.Sam3bError):
+        GpuPreprocessor(64, device="cpu").image(np.zeros((8, 8, 3), np.uint8))
 
 
 def test_hot_path_fails_loudly_without_gpu():
