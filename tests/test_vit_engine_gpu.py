@@ -212,6 +212,31 @@ def test_full_width_blocks_match_oracle():
         assert e < GRAD_TOL, (k, e)
 
 
+def test_full_size_properties_linearity_batch_independence_determinism():
+    """BASELINE.json's full size (32 blocks, D = 1024, 1008 x 1008, batch 8, r = 16): too large for the CPU oracle, so the
+    trunk is checked through size-independent properties: the backward is linear in the output cotangent, images of a batch
+    do not interact (reversing the batch reverses the outputs), and repeated runs agree."""
+    cfg = O.ViTConfig()
+    spec = O.LoRASpec(rank=16, alpha=32.0)
+    params = O.make_params(cfg, spec, seed=29)
+    gen = torch.Generator().manual_seed(30)
+    B = 8
+    img = torch.randn(B, 3, cfg.img_size, cfg.img_size, generator=gen)
+    gout = torch.randn(B, cfg.embed_dim, cfg.grid, cfg.grid, generator=gen) * 0.05
+    eng = _engine_for(cfg, spec, params, max_batch=B)
+    out1, g1 = _run(eng, cfg, params, img, gout)
+    assert torch.isfinite(out1).all() and all(torch.isfinite(v).all() for v in g1.values())
+    out2, g2 = _run(eng, cfg, params, img, gout)                        # determinism
+    assert torch.equal(out1, out2)
+    assert max(rel_l2(g2[k], g1[k]) for k in g1) < 1e-5                 # split-K fp32 atomics: last bits only
+    _, g3 = _run(eng, cfg, params, img, gout * 3.0)                     # linearity of the backward in the cotangent
+    worst = max(rel_l2(g3[k] / 3.0, g1[k]) for k in g1)
+    assert worst < 2e-3, worst
+    out_r, _ = _run(eng, cfg, params, img.flip(0), None)                # batch independence
+    assert rel_l2(out_r.flip(0), out1) < 1e-6
+    _report("full_size_properties", {"linearity_rel_l2": worst, "grad_keys": len(g1)})
+
+
 def test_forward_tolerance_budget():
     """North-star bar: 1e-3 relative on fp32 outputs.  Checked as rel-L2 on the small golden forward."""
     g = load_small_golden()
