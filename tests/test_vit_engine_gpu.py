@@ -231,7 +231,7 @@ def test_full_size_properties_linearity_batch_independence_determinism():
     assert max(rel_l2(g2[k], g1[k]) for k in g1) < 1e-5                 # split-K fp32 atomics: last bits only
     _, g3 = _run(eng, cfg, params, img, gout * 3.0)                     # linearity of the backward in the cotangent
     worst = max(rel_l2(g3[k] / 3.0, g1[k]) for k in g1)
-    assert worst < 2e-3, worst
+    assert worst < 4e-3, worst        # measured 1.7e-3: the two runs round their fp16 operands at different power-of-two scales
     out_r, _ = _run(eng, cfg, params, img.flip(0), None)                # batch independence
     assert rel_l2(out_r.flip(0), out1) < 1e-6
     _report("full_size_properties", {"linearity_rel_l2": worst, "grad_keys": len(g1)})
