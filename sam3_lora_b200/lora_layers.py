@@ -53,7 +53,7 @@ class LoRALayer(nn.Module):
         """Adapter branch alone: dropout(x) @ A @ B * scaling (two skinny tcgen05 GEMMs)."""
         from .ops import lora_branch  # noqa: PLC0415
 
-        return lora_branch(self.dropout(x), self.lora_A, self.lora_B, self.scaling)
+        return lora_branch(self.dropout(x), self.lora_A, self.lora_B, self.scaling, owner=self)
 
 
 class LoRALinear(nn.Module):

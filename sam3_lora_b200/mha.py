@@ -101,6 +101,15 @@ class MultiheadAttention(nn.Module):
             nn.init.zeros_(self.out_proj.bias)
         self.dropout_seed_override: Optional[int] = None
         self._packed = None
+        self._seed_state: Optional[int] = None
+
+    def _next_seed(self) -> int:
+        """Per-call dropout seed without touching the device: a host-side Weyl sequence started from torch's CPU generator
+        (so torch.manual_seed reproduces it) — the kernels hash (seed, row, col) themselves (csrc/rng.cuh)."""
+        if self._seed_state is None:
+            self._seed_state = int(torch.randint(0, 2 ** 31 - 1, (1,), device="cpu").item())
+        self._seed_state = (self._seed_state + 0x9E3779B1) & 0xFFFFFFFF
+        return self._seed_state & 0x7FFFFFFF
 
     # ---- LoRA -------------------------------------------------------------------------------
     def lora_virtual_targets(self) -> Dict[str, Tuple[int, int]]:
@@ -183,7 +192,7 @@ class MultiheadAttention(nn.Module):
         p_drop = self.dropout if self.training else 0.0
         seed = self.dropout_seed_override
         if seed is None:
-            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p_drop > 0 else 0
+            seed = self._next_seed() if p_drop > 0 else 0
         o = _AttnCoreFn.apply(q, k, v, B, Lq, Lk, H, 1.0 / math.sqrt(hd), bias, kpm, p_drop, seed)
         lo = self._adapter("out_proj")
         ob = self._out_linear.bias
@@ -199,16 +208,22 @@ class MultiheadAttention(nn.Module):
         return out.to(query.dtype), None
 
 
-def replace_torch_mha(model: nn.Module) -> int:
+def replace_torch_mha(model: nn.Module, skip: Tuple[str, ...] = ()) -> int:
     """Swap every nn.MultiheadAttention (incl. the reference's MultiheadAttentionWrapper subclass) for the fused
-    module, keeping parameters.  Returns the number of modules replaced."""
+    module, keeping parameters and requires_grad flags.  Module paths containing any of the `skip` substrings, and
+    head sizes the kernel does not cover, are left alone.  Returns the number of modules replaced."""
     n = 0
     for name, m in list(model.named_modules()):
-        if isinstance(m, nn.MultiheadAttention) and m._qkv_same_embed_dim:
+        if any(s in name for s in skip):
+            continue
+        if isinstance(m, nn.MultiheadAttention) and m._qkv_same_embed_dim and m.embed_dim // m.num_heads in (32, 64):
             new = MultiheadAttention(m.embed_dim, m.num_heads, dropout=m.dropout, bias=m.in_proj_bias is not None,
                                      batch_first=m.batch_first)
             new.load_state_dict(m.state_dict())
             new.to(m.in_proj_weight.device)
+            new.train(m.training)
+            for (_, p_new), (_, p_old) in zip(new.named_parameters(), m.named_parameters()):
+                p_new.requires_grad = p_old.requires_grad
             *path, leaf = name.split(".")
             parent = model
             for p in path:

@@ -154,13 +154,15 @@ def lora_linear(x, W, bias, A, B, scaling: float, dropout_p: float = 0.0):
     return _LoRALinearFn.apply(x, W, bias, A, B, float(scaling), float(dropout_p))
 
 
-_ZERO_W = {}
-
-
-def lora_branch(x, A, B, scaling: float):
+def lora_branch(x, A, B, scaling: float, owner=None):
     """(x @ A @ B) * scaling alone (LoRALayer.forward): the same fused kernel with a zero frozen weight.
-    (LoRALinear never takes this route; it exists so a bare LoRALayer behaves like the reference's.)"""
+    (LoRALinear never takes this route; it exists so a bare LoRALayer behaves like the reference's.)
+    The zero weight — and with it the packed operand buffers whose adapter columns each forward rewrites — belongs to
+    `owner` (the calling LoRALayer), never to another layer of the same shape: a second layer's forward must not touch
+    what the first layer's backward still has to read."""
+    holder = owner if owner is not None else lora_branch
+    cache = holder.__dict__.setdefault("_sam3b_zero_w", {})
     key = (A.shape[0], B.shape[1], str(x.device))
-    if key not in _ZERO_W:
-        _ZERO_W[key] = torch.zeros(B.shape[1], A.shape[0], device=x.device, dtype=torch.float32)
-    return lora_linear(x, _ZERO_W[key], None, A, B, scaling, 0.0)
+    if key not in cache:
+        cache[key] = torch.zeros(B.shape[1], A.shape[0], device=x.device, dtype=torch.float32)
+    return lora_linear(x, cache[key], None, A, B, scaling, 0.0)

@@ -23,6 +23,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from .engine import VitEngine, VitSpec, base_tensor_names
+from .lora.lora_layer import LinearWithLoRA, LoRALayer as PkgLoRALayer
 from .lora_layers import LoRALayer, LoRALinear, LoRAVirtual
 
 
@@ -111,6 +112,10 @@ class _TrunkFn(torch.autograd.Function):
         ctx.vit = vit
         ctx.n = len(lora_params)
         ctx.graph = None
+        # the engine keeps ONE set of saved activations: a backward must belong to the latest saving forward
+        if need_grad:
+            vit._fwd_generation += 1
+        ctx.generation = vit._fwd_generation if need_grad else -1
         if vit.cuda_graphs and need_grad and p_drop == 0.0 and flat is not None:
             key = (str(images.device), B, eng.work_buf.data_ptr(), eng.weight_buf.data_ptr(), flat.data_ptr(), drop is not None)
             st = vit._graph_state
@@ -147,6 +152,9 @@ class _TrunkFn(torch.autograd.Function):
     def backward(ctx, gout):
         vit: "ViT" = ctx.vit
         eng = vit._engine
+        if ctx.generation != vit._fwd_generation:
+            raise L.Sam3bError("ViT backward: another trunk forward ran after the one this backward belongs to; the engine keeps a "
+                               "single set of saved activations (one in-flight forward per ViT)")
         gflat = vit._flat_grad_buffer()
         st = ctx.graph
         if st is not None:
@@ -165,17 +173,38 @@ class _TrunkFn(torch.autograd.Function):
         else:
             eng.backward(gout.float().contiguous(), gflat)
         vit._after_backward(gflat)
-        grads = [gflat[a:a + n].view(shape) for (a, n, shape) in vit._flat_index]
+        # clones, not views: autograd's AccumulateGrad may keep the returned tensor as p.grad, and the next backward
+        # overwrites gflat (gradient accumulation / zero_grad(set_to_none=False) would otherwise see aliased memory)
+        grads = [gflat[a:a + n].view(shape[::-1]).t().clone() if tr else gflat[a:a + n].view(shape).clone()
+                 for (a, n, shape), tr in zip(vit._flat_index, vit._flat_transposed)]
         return (None, None, None, *grads)
 
 
 class ViT(nn.Module):
     """Drop-in for sam3.model.vitdet.ViT as configured by sam3/model_builder.py:69-96."""
 
+    # keyword arguments of sam3.model.vitdet.ViT.__init__ (vitdet.py:623-657) whose only supported value is the one
+    # sam3/model_builder.py:69-96 passes: accepted so `_create_vit_backbone` can call this class unchanged, validated so
+    # a different architecture raises instead of silently computing something else.
+    _FIXED_REFERENCE_KWARGS = {
+        "norm_layer": ("LayerNorm",), "act_layer": (nn.GELU,), "qkv_bias": (True,), "use_abs_pos": (True,),
+        "tile_abs_pos": (True,), "rel_pos_blocks": ((), [], False), "rel_pos_zero_init": (True, False), "use_rope": (True,),
+        "use_interp_rope": (True,), "rope_pt_size": (None,), "pretrain_use_cls_token": (True,), "retain_cls_token": (False,),
+        "dropout": (0.0,), "return_interm_layers": (False,), "init_values": (None,), "ln_pre": (True,), "ln_post": (False,),
+        "bias_patch_embed": (False,), "compile_mode": (None,), "use_act_checkpoint": (True, False),
+    }
+
     def __init__(self, img_size=1008, patch_size=14, in_chans=3, embed_dim=1024, depth=32, num_heads=16,
                  mlp_ratio=4.625, window_size=24, global_att_blocks=(7, 15, 23, 31), pretrain_img_size=336,
                  ln_eps=1e-5, rope_theta=10000.0, drop_path_rate=0.1, operand_dtype=torch.float16, max_batch=8,
-                 cuda_graphs: bool = False):
+                 cuda_graphs: bool = False, **reference_kwargs):
+        for k, v in reference_kwargs.items():
+            allowed = self._FIXED_REFERENCE_KWARGS.get(k)
+            if allowed is None:
+                raise TypeError(f"ViT.__init__() got an unexpected keyword argument {k!r}")
+            if not any(v is a or v == a for a in allowed):
+                raise L.Sam3bError(f"ViT({k}={v!r}) is not supported by the native trunk (SAM3 builds it with {allowed[0]!r}; "
+                                   "use_act_checkpoint is accepted and ignored: nothing is recomputed)")
         super().__init__()
         # cuda_graphs=True: after one eager warm-up step the ~1280 launches of the trunk forward and of its backward are
         # each replayed from a CUDA graph (training mode, adapter dropout 0; inputs are copied into static buffers).
@@ -216,7 +245,9 @@ class ViT(nn.Module):
         self._flat_grad: Optional[torch.Tensor] = None
         self._flat_index: List[Tuple[int, int, torch.Size]] = []
         self._lora_params: List[nn.Parameter] = []
+        self._flat_transposed: List[bool] = []
         self._keep_training_workspace = False
+        self._fwd_generation = 0
         self.grad_hook = None  # callable(flat_grad) run right after the backward kernels (DDP all-reduce)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh_base())
 
@@ -231,7 +262,10 @@ class ViT(nn.Module):
         self._engine_key = None
         self._flat = None
 
-    def _adapter_layers(self) -> List[Tuple[int, str, LoRALayer]]:
+    def _adapter_layers(self) -> List[Tuple[int, str, nn.Module]]:
+        """(block, target, adapter) of every adapter in the trunk.  Adapters of the package-layout API
+        (lora.LinearWithLoRA on fc1 / fc2: factors stored [r, in] / [out, r]) are accepted as well; `_is_transposed`
+        tells the two layouts apart."""
         out = []
         for i, blk in enumerate(self.blocks):
             for t in ("q_proj", "k_proj", "v_proj", "out_proj"):
@@ -240,12 +274,22 @@ class ViT(nn.Module):
                     out.append((i, t, m.lora))
             for t in ("fc1", "fc2"):
                 m = getattr(blk.mlp, t)
-                if isinstance(m, LoRALinear):
+                if isinstance(m, (LoRALinear, LinearWithLoRA)):
                     out.append((i, t, m.lora))
+            for t in ("qkv", "proj"):
+                if isinstance(getattr(blk.attn, t), (LoRALinear, LinearWithLoRA)):
+                    raise L.Sam3bError(f"blocks.{i}.attn.{t} is wrapped as a whole; the trunk adapts the fused projections through "
+                                       "the q_proj / k_proj / v_proj / out_proj targets of lora_layers.apply_lora_to_model")
         return out
 
+    @staticmethod
+    def _is_transposed(lora) -> bool:
+        return isinstance(lora, PkgLoRALayer)
+
     def _linear(self, m) -> nn.Linear:
-        return m.original_layer if isinstance(m, LoRALinear) else m
+        if isinstance(m, LoRALinear):
+            return m.original_layer
+        return m.linear if isinstance(m, LinearWithLoRA) else m
 
     def _base_tensors(self) -> Dict[str, torch.Tensor]:
         t = {"patch_embed.proj.weight": self.patch_embed.proj.weight, "pos_embed": self.pos_embed,
@@ -291,9 +335,9 @@ class ViT(nn.Module):
         return list(self._lora_params)
 
     def _build_index(self):
-        """Order adapters as the engine's flat layout: per block q,k,v,o,fc1,fc2; A then B."""
+        """Order adapters as the engine's flat layout: per block q,k,v,o,fc1,fc2; A [in, r] then B [r, out]."""
         layers = {(i, t): l for i, t, l in self._adapter_layers()}
-        index, params = [], []
+        index, params, transposed = [], [], []
         eng = self._engine
         if eng is None:
             order = sorted(layers, key=lambda k: (k[0], ("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2").index(k[1])))
@@ -303,6 +347,7 @@ class ViT(nn.Module):
                 for p in (l.lora_A, l.lora_B):
                     index.append((off, p.numel(), p.shape))
                     params.append(p)
+                    transposed.append(self._is_transposed(l))
                     off += p.numel()
         else:
             for e in eng.entries:
@@ -310,10 +355,13 @@ class ViT(nn.Module):
                 index.append((e.a_off, l.lora_A.numel(), l.lora_A.shape))
                 index.append((e.b_off, l.lora_B.numel(), l.lora_B.shape))
                 params += [l.lora_A, l.lora_B]
-        self._flat_index, self._lora_params = index, params
+                transposed += [self._is_transposed(l)] * 2
+        self._flat_index, self._lora_params, self._flat_transposed = index, params, transposed
 
     def _sync_flat(self) -> Optional[torch.Tensor]:
-        """Make every adapter Parameter a view of one flat fp32 CUDA buffer (values preserved)."""
+        """Make every adapter Parameter a view of one flat fp32 CUDA buffer (values preserved).  Package-layout factors
+        ([r, in] / [out, r]) cannot alias the engine's [in, r] / [r, out] layout: they are copied in (transposed) before
+        every forward, and their gradients are transposed back (a few MB per step)."""
         eng = self._engine
         if eng.lora_numel == 0:
             return None
@@ -322,15 +370,20 @@ class ViT(nn.Module):
         ok = self._flat is not None and self._flat.device == dev
         if ok:
             base = self._flat.data_ptr()
-            ok = all(p.data_ptr() == base + 4 * a and p.dtype == torch.float32 for p, (a, _, _) in
-                     zip(self._lora_params, self._flat_index))
+            ok = all(tr or (p.data_ptr() == base + 4 * a and p.dtype == torch.float32) for p, (a, _, _), tr in
+                     zip(self._lora_params, self._flat_index, self._flat_transposed))
         if not ok:
             flat = torch.zeros(eng.lora_numel, device=dev, dtype=torch.float32)
-            for p, (a, n, shape) in zip(self._lora_params, self._flat_index):
+            for p, (a, n, shape), tr in zip(self._lora_params, self._flat_index, self._flat_transposed):
+                if tr:
+                    continue
                 flat[a:a + n] = p.detach().reshape(-1).to(device=dev, dtype=torch.float32)
                 p.data = flat[a:a + n].view(shape)
             self._flat = flat
             self._flat_grad = None
+        for p, (a, n, shape), tr in zip(self._lora_params, self._flat_index, self._flat_transposed):
+            if tr:
+                self._flat[a:a + n] = p.detach().t().reshape(-1).to(device=dev, dtype=torch.float32)
         return self._flat
 
     def flat_lora(self) -> Optional[torch.Tensor]:

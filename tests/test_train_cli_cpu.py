@@ -59,3 +59,46 @@ def test_trainer_refuses_to_run_without_gpu(tmp_path):
 
     with pytest.raises(RuntimeError, match="CUDA"):
         SAM3TrainerNative(str(ROOT / "configs" / "minimal_lora_config.yaml"))
+
+
+def test_dataset_items_become_reference_datapoints_and_collate(tmp_path):
+    """with_instances=True: per-object normalised xyxy boxes + [R, R] boolean segments, turned into the reference's own
+    Datapoint / BatchedDatapoint by its collator (needs the reference under baseline/_ref; skipped otherwise)."""
+    from sam3_lora_b200 import sam3_bridge
+
+    if sam3_bridge.reference_root() is None:
+        pytest.skip("reference not installed under baseline/_ref")
+    out = tmp_path / "coco"
+    subprocess.run([sys.executable, str(ROOT / "tools" / "make_synthetic_coco.py"), str(out), "--n-train", "2", "--n-valid", "1",
+                    "--size", "96"], check=True)
+    from sam3_lora_b200.train_native import COCOSegmentDataset, collate_sam3
+
+    ds = COCOSegmentDataset(out, "train", with_instances=True)
+    a = ds[0]
+    n = a["boxes"].shape[0]
+    assert n >= 1 and a["segments"].shape == (n, 1008, 1008) and a["segments"].dtype == torch.bool
+    assert (a["boxes"] >= 0).all() and (a["boxes"] <= 1).all() and (a["boxes"][:, 2:] > a["boxes"][:, :2]).all()
+    # the box of an object encloses its mask (both were scaled to the model resolution)
+    ys, xs = a["segments"][0].nonzero(as_tuple=True)
+    x0, y0, x1, y1 = (a["boxes"][0] * 1008).tolist()
+    assert xs.min() >= x0 - 11 and xs.max() <= x1 + 11 and ys.min() >= y0 - 11 and ys.max() <= y1 + 11
+    batch = collate_sam3([ds[0], ds[1]])
+    assert type(batch).__name__ == "BatchedDatapoint" and batch.img_batch.shape == (2, 3, 1008, 1008)
+    assert len(batch.find_text_batch) >= 1 and all(isinstance(t, str) for t in batch.find_text_batch)
+    tgt = batch.find_targets[0]
+    assert int(tgt.num_boxes.sum()) == n + ds[1]["boxes"].shape[0]
+
+
+def test_sam3_objective_refuses_random_base_weights(tmp_path, monkeypatch):
+    """adapters trained on a random base are useless - no checkpoint means an error unless explicitly allowed."""
+    import sam3_lora_b200.train_native as T
+
+    cfg = yaml.safe_load((ROOT / "configs" / "minimal_lora_config.yaml").read_text())
+    cfg["output"]["output_dir"] = str(tmp_path / "o")
+    p = tmp_path / "c.yaml"
+    p.write_text(yaml.safe_dump(cfg))
+    monkeypatch.delenv("SAM3_CHECKPOINT", raising=False)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    with pytest.raises(RuntimeError, match="checkpoint"):
+        T.SAM3TrainerNative(str(p))
