@@ -78,7 +78,7 @@ def apply_rope(x: Tensor, ang: Tensor) -> Tensor:
     (apply_rotary_enc, vitdet.py:68-90)."""
     xr = x.reshape(*x.shape[:-1], -1, 2)
     a, b = xr[..., 0], xr[..., 1]
-    c, s = ang.cos().to(x.dtype), ang.sin().to(x.dtype)
+    c, s = ang.cos().to(device=x.device, dtype=x.dtype), ang.sin().to(device=x.device, dtype=x.dtype)
     return torch.stack([a * c - b * s, a * s + b * c], dim=-1).reshape(x.shape)
 
 

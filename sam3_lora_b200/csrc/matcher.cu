@@ -141,13 +141,18 @@ __global__ void __launch_bounds__(256) matcher_lsa_kernel(const float* __restric
           if (better(wbest[w], bst)) bst = wbest[w];
         SR[i] = 1;
         s_min = bst.val;
-        const int j = bst.j;             // j < 0 cannot happen: Cn >= R and at least one column is free
-        SC[j] = 1;
-        if (row4col[j] == -1) s_sink = j; else s_i = row4col[j];
+        const int j = bst.j;             // j < 0 only if every remaining cost is NaN (Cn >= R: a free column always exists)
+        if (j < 0) {
+          s_sink = -2;                   // non-finite costs (diverged model): leave this image unmatched instead of faulting
+        } else {
+          SC[j] = 1;
+          if (row4col[j] == -1) s_sink = j; else s_i = row4col[j];
+        }
       }
       __syncthreads();
-      if (s_sink >= 0) break;
+      if (s_sink != -1) break;
     }
+    if (s_sink < 0) break;               // uniform across the block (shared flag)
     const double minVal = s_min;
     // dual updates (rectangular_lsap.cpp: u[curRow] += minVal; u[i] += minVal - spc[col4row[i]] for i in SR; v[j] -= minVal - spc[j] for j in SC)
     for (int i = threadIdx.x; i < R; i += blockDim.x) {

@@ -16,6 +16,10 @@ class _FocalFn(torch.autograd.Function):
             raise L.Sam3bError("sigmoid_focal_loss: inputs are on the CPU; the fused loss has no CPU fallback")
         x = inputs.detach().float().contiguous()
         y = targets.detach().float().contiguous()
+        if x.data_ptr() % 16:          # a contiguous slice of a larger tensor: the kernel's float4 loads need 16-byte alignment
+            x = x.clone()
+        if y.data_ptr() % 16:
+            y = y.clone()
         lib = L.load()
         n = x.numel()
         ctx.save_for_backward(x, y)

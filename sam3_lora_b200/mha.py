@@ -67,7 +67,10 @@ class _AttnCoreFn(torch.autograd.Function):
         dev = gO.device
         dO16 = torch.empty(nseg * Lq, Ep, device=dev, dtype=q16.dtype)
         g32 = gO.float().contiguous()
-        sc = L.grad_scale(g32)                    # backward on s*gO (linear in gO), outputs times 1/s; see _lib.grad_scale
+        # backward on s*gO (linear in gO), outputs times 1/s; see _lib.grad_scale.  dV[k] = sum_q P[q,k] dO[q] and dK are sums
+        # over all Lq queries and are stored in 16 bits: with max|s*gO| = T the sums are bounded by Lq*T, so T = 32768/Lq keeps
+        # them below fp16's 65504 whatever the attention pattern (5184 image tokens attending 33 prompt tokens overflowed at 256)
+        sc = L.grad_scale(g32, target=min(L.GRAD_SCALE_TARGET, max(1.0, 32768.0 / Lq)))
         L.cast_rows_16(g32, dO16, sc[0:1])
         delta = torch.zeros_like(lse2)
         dq16 = torch.empty(nseg * Lq, Ep, device=dev, dtype=q16.dtype)

@@ -302,11 +302,13 @@ def swap_trunk(model: nn.Module, max_batch: int = 8, operand_dtype=torch.float16
     if isinstance(ref, ViT):
         return model
     blk0 = ref.blocks[0]
-    native = ViT(img_size=ref.patch_embed.proj.kernel_size[0] * int((ref.blocks[ref.full_attn_ids[0]].attn.freqs_cis.shape[0]) ** 0.5),
-                 patch_size=ref.patch_embed.proj.kernel_size[0], in_chans=ref.patch_embed.proj.in_channels,
+    patch = ref.patch_embed.proj.kernel_size[0]
+    grid = int(round(ref.blocks[ref.full_attn_ids[0]].attn.freqs_cis.shape[0] ** 0.5))     # global blocks: rope over the full grid
+    pos_side = int(round((ref.pos_embed.shape[1] - 1) ** 0.5))                             # cls slot + pretrain grid (vitdet.py:715-731)
+    native = ViT(img_size=patch * grid, patch_size=patch, in_chans=ref.patch_embed.proj.in_channels,
                  embed_dim=blk0.attn.qkv.in_features, depth=len(ref.blocks), num_heads=blk0.attn.num_heads,
                  mlp_ratio=blk0.mlp.fc1.out_features / blk0.attn.qkv.in_features, window_size=blk0.window_size,
-                 global_att_blocks=tuple(ref.full_attn_ids), pretrain_img_size=ref.pretrain_img_size,
+                 global_att_blocks=tuple(ref.full_attn_ids), pretrain_img_size=pos_side * patch,
                  ln_eps=blk0.norm1.eps, drop_path_rate=_drop_path_rate(ref), operand_dtype=operand_dtype, max_batch=max_batch,
                  cuda_graphs=cuda_graphs)
     _copy_state(native, ref, "trunk")
@@ -370,9 +372,27 @@ def swap_mha(model: nn.Module, skip: Iterable[str] = ()) -> int:
     return replace_torch_mha(model, skip=tuple(skip))
 
 
+def swap_matcher(model: nn.Module) -> nn.Module:
+    """model.matcher (the in-forward Hungarian pass, sam3_image.py:578-581; SciPy + 3 host syncs per call in the reference,
+    sam3/train/matcher.py:539-617) -> the GPU-resident matcher with the same cost weights."""
+    from .matcher import BinaryHungarianMatcherV2  # noqa: PLC0415
+
+    ref = getattr(model, "matcher", None)
+    if ref is None or isinstance(ref, BinaryHungarianMatcherV2):
+        return model
+    if type(ref).__name__ != "BinaryHungarianMatcherV2":
+        raise RuntimeError(f"swap_matcher: unexpected matcher {type(ref).__name__}")
+    norm = getattr(ref, "norm", None)
+    focal = bool(getattr(ref, "focal", type(norm).__name__ == "Sigmoid" if norm is not None else True))
+    model.matcher = BinaryHungarianMatcherV2(cost_class=ref.cost_class, cost_bbox=ref.cost_bbox, cost_giou=ref.cost_giou, focal=focal,
+                                             alpha=getattr(ref, "alpha", 0.25), gamma=getattr(ref, "gamma", 2.0),
+                                             stable=bool(getattr(ref, "stable", False)))
+    return model
+
+
 def build_native_model(device="cuda", *, checkpoint_path: Optional[str] = None, seed: Optional[int] = 0, max_batch: int = 8,
                        operand_dtype=torch.float16, cuda_graphs: bool = False, eval_mode: bool = False,
-                       parts: Iterable[str] = ("trunk", "neck", "pixel_decoder", "mha"), reference_model: Optional[nn.Module] = None):
+                       parts: Iterable[str] = ("trunk", "neck", "pixel_decoder", "mha", "matcher"), reference_model: Optional[nn.Module] = None):
     """Reference `Sam3Image` with the hot-path modules swapped for the native ones.  `parts` selects which."""
     model = reference_model if reference_model is not None else build_reference_model(
         "cpu", eval_mode=eval_mode, checkpoint_path=checkpoint_path, seed=seed)
@@ -385,4 +405,6 @@ def build_native_model(device="cuda", *, checkpoint_path: Optional[str] = None, 
         swap_pixel_decoder(model)
     if "mha" in parts:
         swap_mha(model)
+    if "matcher" in parts:
+        swap_matcher(model)
     return model.to(device)

@@ -93,8 +93,6 @@ def disable_stochastic(model: nn.Module) -> nn.Module:
             m.drop_path_rates = [0.0] * len(m.drop_path_rates)
         elif type(m).__name__ == "DropPath":
             m.drop_prob = 0.0
-        if hasattr(m, "dropout_p") and isinstance(getattr(m, "dropout_p"), float):
-            m.dropout_p = 0.0
     return model
 
 

@@ -156,6 +156,7 @@ def test_package_layout_adapters_inside_the_trunk_engine():
     for p in L.get_lora_parameters(a):
         p.requires_grad = True
         nn.init.normal_(p, std=0.05)
+    a.cuda()
     apply_lora_to_model(b, RootCfg(rank=4, alpha=8, target_modules=["fc1", "fc2"], strict_reference_names=True))
     b.cuda()
     with torch.no_grad():
