@@ -132,16 +132,38 @@ def cpu_line(times, cores, steps, warmup, kind="port"):
                            f"{len(times)} timed passes of {t:.2f} s; images/sec = 1 / (8 units x pass time)"}
 
 
+def cpu_reference_arm(steps: int, warmup: int, budget_s: float):
+    """The CPU baseline: the reference's OWN trunk (sam3.model.vitdet.ViT from baseline/_ref, all 32 blocks, its per-block
+    activation checkpointing, its LoRALinear on mlp.fc1/fc2) on ONE image per step — kind "reference".  Falls back to the
+    oracle port's 4-block unit (kind "port") only when the reference is not installed.  Returns (images/sec, cpu_baseline
+    dict, mean seconds per step, timed steps)."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import bench_arms  # noqa: PLC0415
+
+    if bench_arms.reference_available():
+        times, cores = bench_arms.time_trunk_cpu(steps, warmup, budget_s)
+        t = statistics.mean(times)
+        cb = {"value": 1.0 / t, "unit": "images/sec", "cores": cores, "kind": "reference",
+              "sample": f"unmodified sam3.model.vitdet.ViT (baseline/_ref): 32 blocks, 1008x1008, fp32, per-block activation "
+                        f"checkpointing as shipped (vitdet.py:837-838), reference LoRALinear r=16 on mlp.fc1/fc2 (its name matching "
+                        f"reaches no q/k/v/o in the fused-qkv trunk; the adapters are 1.5 % of the FLOPs), forward + backward + AdamW, "
+                        f"ONE image per step ({len(times)} timed steps of {t:.1f} s within a {budget_s:.0f} s budget); a batch of 8 is "
+                        f"8 such passes on a CPU, so images/sec = 1 / seconds per image"}
+        return 1.0 / t, cb, t, len(times)
+    times, cores = cpu_unit_seconds(max(1, min(steps, 6)), max(0, min(warmup, 1)))
+    ips, cb = cpu_line(times, cores, steps, warmup)
+    return ips, cb, statistics.mean(times), len(times)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times, cores = cpu_unit_seconds(max(1, args.steps), max(0, min(args.warmup, 1)))
-    ips, cb = cpu_line(times, cores, args.steps, args.warmup)
+    ips, cb, t, n = cpu_reference_arm(max(1, args.steps), max(0, min(args.warmup, 1)), args.cpu_budget)
     line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": n,
+        "steps_requested": args.steps, "warmup": max(0, min(args.warmup, 1)), "ms_per_step": 1000.0 * t, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, cpu=True),
         "cpu_baseline": cb,
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -156,7 +178,9 @@ def workload_config(args, cpu=False):
                         "adapters; full_lora_config.yaml shape at r=16",
             "batch_per_gpu": args.batch, "global_batch": args.batch * (1 if cpu else args.gpus), "image": "3x1008x1008",
             "parallelism": f"dp{args.gpus}", "l2_policy": "per-step working set (>50 GB of activations) exceeds the 126 MB L2",
-            "depth": args.depth, "cuda_graph": not getattr(args, "no_graph", False)}
+            "depth": args.depth, "cuda_graph": not getattr(args, "no_graph", False),
+            "allreduce": "none (1 GPU)" if cpu or args.gpus == 1 else
+                         f"flat LoRA gradient in {args.segments} slices, each all-reduced (NCCL, side stream) while the next block range of the backward runs"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -217,30 +241,53 @@ def run_native(args):
 
     out_buf = torch.empty(B, 1024, 72, 72, device=dev)
 
-    def fwd_bwd():
-        eng.forward(images, flat, out_buf, save_for_backward=True)
-        eng.backward(gout, gflat)
+    # N > 1: the backward runs in `--segments` block ranges; each range's slice of the flat gradient is all-reduced on a side
+    # stream while the next range computes (dist.LoRAGradAllReducer), so only the last slice's collective is exposed.
+    from sam3_lora_b200.dist import LoRAGradAllReducer
 
-    # The ~1280 kernel launches of one forward+backward are captured once in a CUDA graph and replayed (all
-    # pointers are fixed, TMA descriptors are by-value kernel parameters); the all-reduce and AdamW stay eager.
-    graph = None
+    segs = eng.segments(args.segments if world > 1 else 1)
+    reducer = LoRAGradAllReducer(average=False, segments=len(segs))      # the 1/world factor is folded into AdamW's grad scale
+    ranges = [eng.grad_range(hi, lo) for hi, lo in segs]
+
+    def part(k):
+        if k == 0:
+            eng.forward(images, flat, out_buf, save_for_backward=True)
+        if len(segs) == 1:
+            eng.backward(gout, gflat)
+        else:
+            eng.backward_segment(gout if k == 0 else None, gflat, segs[k][0], segs[k][1])
+
+    def fwd_bwd():
+        for k in range(len(segs)):
+            part(k)
+
+    # The ~1000 kernel launches of one forward+backward are captured once in CUDA graphs (one per backward range) and
+    # replayed (all pointers are fixed, TMA descriptors are by-value kernel parameters); all-reduce and AdamW stay eager.
+    graphs = None
     launches_per_fwd_bwd = None
     if not args.no_graph:
         fwd_bwd()                                   # first-use cudaFuncSetAttribute calls happen outside capture
         torch.cuda.synchronize()
         n_before = L.launch_count()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            fwd_bwd()
+        graphs = []
+        for k in range(len(segs)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                part(k)
+            graphs.append(g)
         launches_per_fwd_bwd = L.launch_count() - n_before
 
     def native_step():
-        if graph is not None:
-            graph.replay()
-        else:
-            fwd_bwd()
+        for k in range(len(segs)):
+            if graphs is not None:
+                graphs[k].replay()
+            else:
+                part(k)
+            if world > 1:
+                a, b = ranges[k]
+                reducer.reduce_slice(gflat[a:b])
         if world > 1:
-            dist.all_reduce(gflat)
+            reducer.finish()
         step_no[0] += 1
         L.adamw_step(flat, gflat, m_buf, v_buf, args.lr, 0.9, 0.999, 1e-8, 0.01, step_no[0], 1.0 / world)
 
@@ -283,7 +330,7 @@ def run_native(args):
     model.cuda_graphs = not args.e2e_eager and not args.no_graph
     params = model.lora_parameters()
     if world > 1:
-        model.grad_hook = lambda g: dist.all_reduce(g)
+        model.grad_hook = LoRAGradAllReducer(average=False, segments=args.segments)
     opt = torch.optim.AdamW(params, lr=args.lr, weight_decay=0.01, fused=True)
     # double-buffered input: the H2D copy of step i+1 (pinned host memory, side stream) overlaps the compute of
     # step i, as an input pipeline would; every step still copies its own batch inside the timed region.
@@ -357,7 +404,8 @@ def run_native(args):
     k1.record()
     torch.cuda.synchronize()
     kms = k0.elapsed_time(k1) / iters
-    achieved = 2.0 * M * N * K / kms / 1e9
+    K_alg = 1024 + args.rank                      # algorithmic K: the 64-wide K-extension carries `rank` live columns
+    achieved = 2.0 * M * N * K_alg / kms / 1e9
     traffic = None
     tf = ROOT / "profiles" / "gemm_traffic.json"
     if tf.exists():
@@ -368,6 +416,7 @@ def run_native(args):
     roofline = {"bound": "tensor", "kernel": "gemm2_kernel<EPI_GELU> (CTA pair 256x256) M=%d N=%d K=%d" % (M, N, K),
                 "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s", "frac": achieved / peaks["burst"],
                 "peak_source": peaks["source"] + " cuBLAS bf16 burst", "traffic": traffic,
+                "algorithmic_flops": 2.0 * M * N * K_alg, "launch_ms": kms, "executed_flops_incl_k_padding": 2.0 * M * N * K,
                 "algorithmic_bytes": M * K * 2 + N * K * 2 + M * N * 2 * 2,
                 "step_trunk_tflops": value / world * GF_TRUNK_TRAIN / 1e3,
                 "step_trunk_frac_of_sustained": value / world * GF_TRUNK_TRAIN / 1e3 / peaks["sustained"],
@@ -429,11 +478,40 @@ def run_native(args):
         others.append({"error": f"{type(e).__name__}: {e}"[:200]})
     roofline["other_kernels"] = others
 
-    # -------- CPU baseline beside it (rank 0, N=1 only) --------
+    # -------- reference arms beside it (rank 0, N=1 only) --------
     cpu_baseline = None
-    if world == 1 and not args.no_cpu:
-        times, cores = cpu_unit_seconds(6, 1)     # ~15 s of CPU work on the box's host cores (bounded sample)
-        _, cpu_baseline = cpu_line(times, cores, args.steps, args.warmup)
+    gpu_eager = None
+    whole = None
+    if world == 1:
+        del A, W, H, G
+        torch.cuda.empty_cache()
+        sys.path.insert(0, str(ROOT / "tools"))
+        import bench_arms  # noqa: PLC0415
+
+        have_ref = bench_arms.reference_available()
+        if have_ref and not args.no_gpu_eager:
+            # the reference's own GPU path on the same device: the real bar for the trunk step
+            try:
+                ms_ref, what = bench_arms.time_trunk_gpu(B, 3, 2, rank=args.rank, device=dev)
+                gpu_eager = {"value": B / ms_ref * 1e3, "unit": "images/sec", "ms_per_step": ms_ref, "kind": "reference", "what": what,
+                             "native_over_reference": value / (B / ms_ref * 1e3)}
+            except Exception as e:  # noqa: BLE001
+                gpu_eager = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if have_ref and not args.no_whole_model:
+            # BASELINE.md section 3 variant (ii): the whole detector step, native swaps vs the untouched reference, same GPU
+            whole = {"workload": f"Sam3Image training step (forward, Hungarian matching, Sam3LossWrapper objective, backward, AdamW), "
+                                 f"batch {B}, r={args.rank} adapters on the trunk's fc1/fc2 (the set both sides express), dropout / "
+                                 f"DropPath on, synthetic COCO-shaped batch resident on the device"}
+            for key, native in (("native", True), ("reference_gpu_eager", False)):
+                try:
+                    ms_w, info = bench_arms.time_whole_model(native, B, 3, 3, rank=args.rank, device=dev)
+                    whole[key] = {"value": B / ms_w * 1e3, "unit": "images/sec", "ms_per_step": ms_w, **info}
+                except Exception as e:  # noqa: BLE001
+                    whole[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            if "value" in whole.get("native", {}) and "value" in whole.get("reference_gpu_eager", {}):
+                whole["native_over_reference"] = whole["native"]["value"] / whole["reference_gpu_eager"]["value"]
+        if not args.no_cpu:
+            _, cpu_baseline, _, _ = cpu_reference_arm(1, 0, 60.0)     # one image through the reference trunk on the host cores
 
     line = {
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -446,6 +524,8 @@ def run_native(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "gpu_eager_baseline": gpu_eager,
+        "other_workloads": {"sam3_whole_model_step": whole} if whole is not None else None,
         "trainable_parameters": counts["trainable_parameters"],
     }
     print(json.dumps(line), flush=True)
@@ -466,8 +546,14 @@ def main():
                     help="tensor-core operand format (fp32 accumulate, fp32 residual stream)")
     ap.add_argument("--lr", type=float, default=5e-5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference's GPU-eager trunk leg (needs baseline/_ref)")
+    ap.add_argument("--no-whole-model", action="store_true", help="skip the whole-detector step legs (needs baseline/_ref)")
+    ap.add_argument("--cpu-budget", type=float, default=240.0,
+                    help="--impl reference: wall-clock budget in seconds; the arm stops after the step that exceeds it")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (use with `ncu --profile-from-start off`)")
+    ap.add_argument("--segments", type=int, default=4,
+                    help="N > 1: block ranges of the backward whose gradient slices are all-reduced while the next range runs")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--e2e-eager", action="store_true", help="run the end-to-end leg without ViT(cuda_graphs=True)")
     args = ap.parse_args()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SAM3B_ABI_VERSION 1
+#define SAM3B_ABI_VERSION 2
 
 /* operand formats of the tensor-core path (fp32 accumulate always) */
 #define SAM3B_F16 0
@@ -198,6 +198,13 @@ int sam3b_dropout_rows16(const void* x16, int64_t ldx, int32_t rows, int32_t col
                          uint32_t seed, int32_t dtype, void* stream);
 /* gout: dLoss/dout fp32 NCHW; lora_grad_flat: flat fp32 gradients (overwritten, same layout as lora_flat) */
 int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, void* stream);
+/* The same backward cut into consecutive block ranges [block_hi .. block_lo] (descending; the first call starts at
+ * depth - 1 and is the only one that reads gout).  When a call returns (stream order), the gradients of ITS blocks are
+ * final in elements [lo, hi) of lora_grad_flat (sam3b_vit_lora_grad_range), so a data-parallel caller can all-reduce that
+ * slice while the next range runs — DDP's bucketed overlap (sam3_lora/train/native_trainer.py:322-340) without buckets. */
+int sam3b_vit_backward_segment(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, int32_t block_hi, int32_t block_lo,
+                               void* stream);
+int sam3b_vit_lora_grad_range(sam3b_vit* v, int32_t block_hi, int32_t block_lo, int64_t* lo, int64_t* hi);
 
 /* ---- fused sigmoid focal loss (replaces the Triton kernels sam3/train/loss/sigmoid_focal_loss.py:35-208; arithmetic of
  * sam3/train/loss/loss_fns.py:159-167).  fp32, n elements; `loss` (elementwise) and `sum` (scalar) are optional outputs. */

@@ -195,6 +195,16 @@ int sam3b_vit_backward(sam3b_vit* v, const float* gout_nchw, float* lora_grad_fl
   if (!v) return fail(-1, "sam3b_vit_backward: null handle");
   return v->eng->backward(gout_nchw, lora_grad_flat, static_cast<cudaStream_t>(stream));
 }
+int sam3b_vit_backward_segment(sam3b_vit* v, const float* gout_nchw, float* lora_grad_flat, int32_t block_hi, int32_t block_lo,
+                               void* stream) {
+  if (!v) return fail(-1, "sam3b_vit_backward_segment: null handle");
+  return v->eng->backward_segment(gout_nchw, lora_grad_flat, block_hi, block_lo, static_cast<cudaStream_t>(stream));
+}
+int sam3b_vit_lora_grad_range(sam3b_vit* v, int32_t block_hi, int32_t block_lo, int64_t* lo, int64_t* hi) {
+  if (!v || !lo || !hi) return fail(-1, "sam3b_vit_lora_grad_range: null argument");
+  v->eng->lora_grad_range(block_hi, block_lo, lo, hi);
+  return 0;
+}
 
 int sam3b_focal_loss_fwd(const float* x, const float* y, int64_t n, float alpha, float gamma, float* loss, float* sum, void* stream) {
   return focal_loss_fwd(x, y, n, alpha, gamma, loss, sum, static_cast<cudaStream_t>(stream));

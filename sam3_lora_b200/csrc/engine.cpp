@@ -318,7 +318,10 @@ int VitEngine::pack_site(const Site& st, const float* lora_flat, cudaStream_t s)
 void VitEngine::build_site_descs() {
   site_desc_host_.clear();
   site_max_work_ = 0;
-  for (auto& w : blocks_)
+  site_first_.assign(blocks_.size() + 1, 0);
+  int blk_i = 0;
+  for (auto& w : blocks_) {
+    site_first_[blk_i++] = (int)site_desc_host_.size();
     for (const Site* st : {&w.qkv, &w.proj, &w.fc1, &w.fc2}) {
       if (st->R == 0) continue;
       LoraSiteDesc d{};
@@ -334,6 +337,8 @@ void VitEngine::build_site_descs() {
       site_desc_host_.push_back(d);
       site_max_work_ = std::max(site_max_work_, st->R * std::max(st->in, st->out));
     }
+  }
+  site_first_[blocks_.size()] = (int)site_desc_host_.size();
   site_desc_dirty_ = true;
 }
 
@@ -516,24 +521,40 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
 
 // ---------------------------------------------------------------------------------------------
 int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s) {
+  return backward_segment(gout_nchw, grad_flat, cfg_.depth - 1, 0, s);
+}
+
+// Blocks [blk_hi .. blk_lo] of the backward (descending).  The first segment (blk_hi = depth - 1) consumes gout; the
+// residual-gradient ping-pong buffers carry the state to the next segment; every segment ends by un-packing the weight
+// gradients of ITS blocks into grad_flat (a contiguous slice, lora_grad_range), so a data-parallel caller can start the
+// all-reduce of that slice while the next segment runs (reference DDP semantics: native_trainer.py:322-340).
+int VitEngine::backward_segment(const float* gout_nchw, float* grad_flat, int blk_hi, int blk_lo, cudaStream_t s) {
   SAM3B_REQUIRE(last_saved_, "vit backward: needs a forward(save_for_backward=1) first");
-  SAM3B_REQUIRE(gout_nchw && (lora_numel_ == 0 || grad_flat), "vit backward: null argument");
+  SAM3B_REQUIRE(lora_numel_ == 0 || grad_flat, "vit backward: null argument");
+  SAM3B_REQUIRE(blk_hi < cfg_.depth && blk_lo >= 0 && blk_lo <= blk_hi, "vit backward: bad block range [%d, %d]", blk_hi, blk_lo);
+  const bool first = blk_hi == cfg_.depth - 1;
+  SAM3B_REQUIRE(first ? gout_nchw != nullptr : bwd_next_ == blk_hi,
+                "vit backward: segment [%d, %d] out of order (next expected block %d)", blk_hi, blk_lo, bwd_next_);
   const int M = last_batch_ * T_;
   const int dt = cfg_.dtype;
   const int ws2 = cfg_.window_size * cfg_.window_size;
   int rc;
-  float* dx = dxa_;      // gradient w.r.t. the current block's output (fp32)
-  float* dx_alt = dxb_;
   int64_t ld_dx16 = D_ + Rmax_;
   const float* ds = fwd_drop_scales_;
   const int Bn = last_batch_;
   auto drop = [&](int blk, int branch) -> const float* { return ds ? ds + (int64_t)(2 * blk + branch) * Bn : nullptr; };
-  // The whole backward is linear in gout, so it runs on s * gout with s a power of two chosen on the device from
-  // max|gout| (fp16 operands would otherwise flush a mean-reduced loss gradient, ~1e-9 per element, to zero); the
-  // LoRA gradients are multiplied by 1/s when they are unpacked into grad_flat.
-  if ((rc = grad_scale(gout_nchw, (int64_t)last_batch_ * D_ * T_, 256.f, gscale_, s))) return rc;
-  if (wgrad_pack_bytes_ > 0) SAM3B_CHECK_CUDA(cudaMemsetAsync(wgrad_pack_, 0, (size_t)wgrad_pack_bytes_, s));   // all split-K accumulators at once
-  if ((rc = nchw_to_tokens(gout_nchw, last_batch_, G_, cfg_.window_size, D_, dx, dx16_, ld_dx16, dt, s, drop(cfg_.depth - 1, 1), gscale_))) return rc;
+  if (first) {
+    bwd_dx_ = dxa_;       // gradient w.r.t. the current block's output (fp32)
+    bwd_dx_alt_ = dxb_;
+    // The whole backward is linear in gout, so it runs on s * gout with s a power of two chosen on the device from
+    // max|gout| (fp16 operands would otherwise flush a mean-reduced loss gradient, ~1e-9 per element, to zero); the
+    // LoRA gradients are multiplied by 1/s when they are unpacked into grad_flat.
+    if ((rc = grad_scale(gout_nchw, (int64_t)last_batch_ * D_ * T_, 256.f, gscale_, s))) return rc;
+    if (wgrad_pack_bytes_ > 0) SAM3B_CHECK_CUDA(cudaMemsetAsync(wgrad_pack_, 0, (size_t)wgrad_pack_bytes_, s));   // all split-K accumulators at once
+    if ((rc = nchw_to_tokens(gout_nchw, last_batch_, G_, cfg_.window_size, D_, bwd_dx_, dx16_, ld_dx16, dt, s, drop(cfg_.depth - 1, 1), gscale_))) return rc;
+  }
+  float*& dx = bwd_dx_;
+  float*& dx_alt = bwd_dx_alt_;
 
   // dst16[:, out .. out+R) = s * dy[:, :out] . B^T      (skinny GEMM; B operand = up_pack [R][out])
   auto site_up_grad = [&](const Site& st, uint16_t* dy, int64_t ld) -> int {
@@ -565,7 +586,7 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
     return gemm_launch(b, s);
   };
 
-  for (int i = cfg_.depth - 1; i >= 0; --i) {
+  for (int i = blk_hi; i >= blk_lo; --i) {
     BlockW& w = blocks_[i];
     BlockAct& a = acts_[i];
     const int64_t ld_xn1 = D_ + w.qkv.R, ld_O = D_ + w.proj.R, ld_xn2 = D_ + w.fc1.R, ld_g = Dm_ + w.fc2.R;
@@ -619,11 +640,26 @@ int VitEngine::backward(const float* gout_nchw, float* grad_flat, cudaStream_t s
     if ((rc = layernorm_bwd(dxn16_, D_, x_[i], a.mean1, a.rstd1, w.g1, dx, M, D_, dx_alt, dx16_, ld_dx16, dt, s, drop(i - 1, 1), T_))) return rc;
     std::swap(dx, dx_alt);
   }
-  // every site's packed weight gradients -> the flat gradient buffer, times 1/s, in one launch
-  if (!site_desc_host_.empty() &&
-      (rc = lora_unpack_all(site_desc_dev_, (int)site_desc_host_.size(), site_max_work_, grad_flat, gscale_ + 1, s))) return rc;
-  last_saved_ = false;
+  // this segment's packed weight gradients -> their slice of the flat gradient buffer, times 1/s, in one launch
+  if (!site_desc_host_.empty()) {
+    const int d0 = site_first_[blk_lo], d1 = site_first_[blk_hi + 1];
+    if (d1 > d0 && (rc = lora_unpack_all(site_desc_dev_ + d0, d1 - d0, site_max_work_, grad_flat, gscale_ + 1, s))) return rc;
+  }
+  bwd_next_ = blk_lo - 1;
+  if (blk_lo == 0) last_saved_ = false;
   return 0;
+}
+
+// Element range [lo, hi) of the flat LoRA buffers that belongs to blocks [blk_lo .. blk_hi].
+void VitEngine::lora_grad_range(int blk_hi, int blk_lo, int64_t* lo, int64_t* hi) const {
+  int64_t a = lora_numel_, b = 0;
+  for (const LoraEntry& e : entries_)
+    if (e.block >= blk_lo && e.block <= blk_hi) {
+      a = std::min(a, e.a_off);
+      b = std::max(b, e.b_off + (int64_t)e.rank * e.out);
+    }
+  *lo = std::min(a, b);
+  *hi = b;
 }
 
 }  // namespace sam3b

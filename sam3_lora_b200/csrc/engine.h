@@ -51,6 +51,11 @@ class VitEngine {
   int load_base(const float* const* tensors, int n, cudaStream_t s);
   int forward(const float* img, int batch, const float* lora_flat, float* out_nchw, bool save, cudaStream_t s);
   int backward(const float* gout_nchw, float* lora_grad_flat, cudaStream_t s);
+  // The same backward cut into block ranges [blk_hi .. blk_lo] (descending, consecutive, starting at depth - 1): each call
+  // leaves the weight gradients of its blocks final in their slice of lora_grad_flat (lora_grad_range), so the caller can
+  // all-reduce that slice while the next range runs.
+  int backward_segment(const float* gout_nchw, float* lora_grad_flat, int blk_hi, int blk_lo, cudaStream_t s);
+  void lora_grad_range(int blk_hi, int blk_lo, int64_t* lo, int64_t* hi) const;
   // Stochastic depth (DropPath, vitdet.py:610-611): device array [depth][2][batch] of per-image branch scales
   // (0 or 1/keep; [i][0] attention branch, [i][1] MLP branch) used by the next forward AND its backward.
   // nullptr disables it (eval mode / drop_path 0).
@@ -113,6 +118,9 @@ class VitEngine {
   LoraSiteDesc* site_desc_dev_ = nullptr;
   std::vector<LoraSiteDesc> site_desc_host_;
   int site_max_work_ = 0;
+  std::vector<int> site_first_;    // first descriptor of each block (+ end sentinel)
+  float *bwd_dx_ = nullptr, *bwd_dx_alt_ = nullptr;   // residual-gradient ping-pong state between backward segments
+  int bwd_next_ = -1;              // next block a backward segment must start at
   bool site_desc_dirty_ = true;
   void build_site_descs();
   float* gscale_ = nullptr;   // device [s, 1/s, scratch]: power-of-two scale of the incoming gradient (grad_scale, conv.cuh)

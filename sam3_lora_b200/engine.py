@@ -96,6 +96,10 @@ def _declare(lib):
     lib.sam3b_vit_set_lora_dropout.restype = C.c_int
     lib.sam3b_vit_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sam3b_vit_backward.restype = C.c_int
+    lib.sam3b_vit_backward_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, C.c_void_p]
+    lib.sam3b_vit_backward_segment.restype = C.c_int
+    lib.sam3b_vit_lora_grad_range.argtypes = [C.c_void_p, i32, i32, P(i64), P(i64)]
+    lib.sam3b_vit_lora_grad_range.restype = C.c_int
     lib._vit_declared = True
 
 
@@ -221,3 +225,21 @@ class VitEngine:
 
     def backward(self, gout, grad_flat):
         _lib.check(self.lib.sam3b_vit_backward(self._h, gout.data_ptr(), _lib.ptr(grad_flat), _lib.current_stream()))
+
+    def backward_segment(self, gout, grad_flat, block_hi: int, block_lo: int):
+        """Blocks [block_hi .. block_lo] of the backward (consecutive calls from depth - 1 down to 0; only the first reads gout).
+        On return (stream order) grad_flat[slice(*self.grad_range(block_hi, block_lo))] is final."""
+        _lib.check(self.lib.sam3b_vit_backward_segment(self._h, _lib.ptr(gout), _lib.ptr(grad_flat), block_hi, block_lo,
+                                                       _lib.current_stream()))
+
+    def grad_range(self, block_hi: int, block_lo: int) -> Tuple[int, int]:
+        lo, hi = i64(), i64()
+        _lib.check(self.lib.sam3b_vit_lora_grad_range(self._h, block_hi, block_lo, C.byref(lo), C.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def segments(self, n: int) -> List[Tuple[int, int]]:
+        """n (or fewer) consecutive block ranges (hi, lo) covering depth - 1 .. 0, earlier ranges first."""
+        depth = self.spec.depth
+        n = max(1, min(n, depth))
+        cuts = [depth - (depth * k) // n for k in range(n + 1)]          # depth, ..., 0
+        return [(cuts[k] - 1, cuts[k + 1]) for k in range(n) if cuts[k] > cuts[k + 1]]

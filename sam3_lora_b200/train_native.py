@@ -318,7 +318,7 @@ class SAM3TrainerNative:
         trunk_ids = {id(p) for p in self.trunk.lora_parameters()}
         self._sync_rest = _FlatGradSync([p for p in params if id(p) not in trunk_ids])
         if self.world > 1:
-            self.trunk.grad_hook = D.LoRAGradAllReducer()
+            self.trunk.grad_hook = D.LoRAGradAllReducer(segments=4)      # slices are reduced while the backward continues
         self.out_dir = Path(self.config["output"]["output_dir"])
         self.out_dir.mkdir(parents=True, exist_ok=True)
 

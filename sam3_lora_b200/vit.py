@@ -157,21 +157,44 @@ class _TrunkFn(torch.autograd.Function):
                                "single set of saved activations (one in-flight forward per ViT)")
         gflat = vit._flat_grad_buffer()
         st = ctx.graph
+        hook = vit.grad_hook
+        nseg = int(getattr(hook, "segments", 1)) if hook is not None and hasattr(hook, "reduce_slice") else 1
+        segs = eng.segments(nseg)
+        g_in = gout.float().contiguous() if st is None else st.gout
         if st is not None:
             st.gout.copy_(gout)
-            if not st.warm:
-                eng.backward(st.gout, gflat)
-                st.warm = True
-            elif st.g_bwd is None or st.g_bwd[1] != gflat.data_ptr():
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    eng.backward(st.gout, gflat)
-                st.g_bwd = (g, gflat.data_ptr())
-                g.replay()
+
+        def run_segment(k):
+            hi, lo = segs[k]
+            if len(segs) == 1:
+                eng.backward(g_in, gflat)
             else:
-                st.g_bwd[0].replay()
-        else:
-            eng.backward(gout.float().contiguous(), gflat)
+                eng.backward_segment(g_in if k == 0 else None, gflat, hi, lo)
+
+        for k in range(len(segs)):
+            if st is None or not st.warm:
+                run_segment(k)
+            else:
+                key = (gflat.data_ptr(), len(segs))
+                if st.g_bwd is None or st.g_bwd[0] != key:
+                    st.g_bwd = (key, {})
+                graphs = st.g_bwd[1]
+                if k not in graphs:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        run_segment(k)
+                    graphs[k] = g
+                graphs[k].replay()
+            if len(segs) > 1:
+                a, b = eng.grad_range(*segs[k])
+                hook.reduce_slice(gflat[a:b])
+        if st is not None:
+            st.warm = True
+        if len(segs) > 1:
+            hook.finish()
+            grads = [gflat[a:a + n].view(shape[::-1]).t().clone() if tr else gflat[a:a + n].view(shape).clone()
+                     for (a, n, shape), tr in zip(vit._flat_index, vit._flat_transposed)]
+            return (None, None, None, *grads)
         vit._after_backward(gflat)
         # clones, not views: autograd's AccumulateGrad may keep the returned tensor as p.grad, and the next backward
         # overwrites gflat (gradient accumulation / zero_grad(set_to_none=False) would otherwise see aliased memory)

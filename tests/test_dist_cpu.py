@@ -23,6 +23,13 @@ def _worker(rank, world, port, q):
     flat2 = torch.ones(10) * (rank + 1)
     LoRAGradAllReducer(average=False)(flat2)
     ok = ok and torch.allclose(flat2, torch.ones(10) * sum(range(1, world + 1))) and red.calls == 1 and red.bytes == 4000
+    # sliced form (the overlapped path of the trunk backward): slices reduced one by one == one reduction of the whole buffer
+    flat3 = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    red3 = LoRAGradAllReducer(segments=4)
+    for a, b in ((750, 1000), (500, 750), (250, 500), (0, 250)):
+        red3.reduce_slice(flat3[a:b])
+    red3.finish()
+    ok = ok and torch.allclose(flat3, expect) and red3.calls == 4 and red3.bytes == 4000
     idx = shard_indices(10, r, w, epoch=3)
     gathered = [None] * w
     dist.all_gather_object(gathered, idx)

@@ -42,11 +42,11 @@ def _oracle_params(m):
     return p, leaves
 
 
-def _compare(m, q, k, v, attn_mask=None, kpm=None, dropout=None, batch_first=True):
+def _compare(m, q, k, v, attn_mask=None, kpm=None, dropout=None, batch_first=True, g_scale=1.0):
     m.dropout_seed_override = dropout[1] if dropout else None
     qc, kc, vc = (t.clone().cuda().requires_grad_(True) for t in (q, k, v))
     out = m(qc, kc, vc, key_padding_mask=None if kpm is None else kpm.cuda(), attn_mask=None if attn_mask is None else attn_mask.cuda())[0]
-    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)) * g_scale
     out.backward(g.cuda())
     p, leaves = _oracle_params(m)
     qo, ko, vo = (t.clone().requires_grad_(True) for t in (q, k, v))
@@ -94,6 +94,42 @@ def test_decoder_cross_attention_with_additive_bias_seq_first():
     q, mem = torch.randn(201, 2, 256, generator=gen), torch.randn(640, 2, 256, generator=gen)
     bias = torch.randn(2 * 8, 201, 640, generator=gen)
     _compare(m, q, mem, mem, attn_mask=bias, batch_first=False)
+
+
+# ---- the real DETR sizes: 72 x 72 = 5184 image tokens, 200 + 200 + 1 queries, 32 + 1 prompt tokens -----------
+def test_encoder_self_attention_at_5184_tokens_with_dropout():
+    """TransformerEncoderLayer.forward_pre's self-attention (encoder.py:176-186): q = k = x + pos, v = x over the 5184
+    image tokens, attention dropout 0.1 active (same stateless mask in the oracle)."""
+    holder, m = _make(dropout=0.1)
+    m.train()
+    gen = torch.Generator().manual_seed(10)
+    x, pos = torch.randn(1, 5184, 256, generator=gen), torch.randn(1, 5184, 256, generator=gen)
+    _compare(m, x + pos, x + pos, x, dropout=(0.1, 777))
+
+
+def test_decoder_image_cross_attention_401x5184_with_box_rpb_bias():
+    """TransformerDecoderLayer's image cross-attention (decoder.py:156-175): 401 queries (200 o2o + 200 o2m + presence)
+    against 5184 memory tokens with the additive fp32 box-RPB bias [B*8, 401, 5184] (decoder.py:331-408, 516-524),
+    sequence-first layout."""
+    holder, m = _make(batch_first=False)
+    m.eval()
+    gen = torch.Generator().manual_seed(11)
+    q, mem = torch.randn(401, 1, 256, generator=gen), torch.randn(5184, 1, 256, generator=gen)
+    bias = torch.randn(8, 401, 5184, generator=gen) * 2.0
+    _compare(m, q, mem, mem, attn_mask=bias, batch_first=False)
+
+
+def test_image_to_prompt_cross_attention_with_loss_sized_gradients():
+    """Encoder cross-attention of the 5184 image tokens to the 33 prompt tokens (encoder.py:188-198) with cotangents of the
+    size a real loss hands back (1e-8): dK / dV are sums over all 5184 queries; with the backward running on a power-of-two
+    multiple of the cotangent they overflowed fp16 before the scale was bounded by 32768 / Lq (found by the a9 step)."""
+    holder, m = _make()
+    m.eval()
+    gen = torch.Generator().manual_seed(12)
+    q, mem = torch.randn(1, 5184, 256, generator=gen), torch.randn(1, 33, 256, generator=gen)
+    kpm = torch.zeros(1, 33, dtype=torch.bool)
+    kpm[0, 20:] = True
+    _compare(m, q, mem, mem, kpm=kpm, g_scale=1e-8)
 
 
 def test_no_adapters_matches_torch_module_directly():

@@ -294,6 +294,39 @@ def test_full_size_properties_linearity_batch_independence_determinism():
     _report("full_size_properties", {"linearity_rel_l2": worst, "grad_keys": len(g1)})
 
 
+def test_segmented_backward_equals_the_single_call():
+    """engine.backward_segment over consecutive block ranges (the form whose gradient slices are all-reduced while the next
+    range runs) gives the gradients of the one-call backward; each range's slice is final when its call returns."""
+    g = load_small_golden()
+    cfg, spec, params = g["cfg"], g["spec"], g["params"]
+    eng = _engine_for(cfg, spec, params)
+    dev = "cuda"
+    eng.bind(dev, 1, training=True)
+    eng.load_base({k: v.to(dev) for k, v in params.items() if ".lora." not in k})
+    flat = _flat_lora(eng, params, dev)
+    out = torch.empty(1, cfg.embed_dim, cfg.grid, cfg.grid, device=dev)
+    gout = g["gout"].to(dev).contiguous()
+    eng.forward(g["img"].to(dev), flat, out, save_for_backward=True)
+    whole = torch.zeros_like(flat)
+    eng.backward(gout, whole)
+    assert eng.segments(2) == [(1, 1), (0, 0)] and eng.segments(5) == [(1, 1), (0, 0)] and eng.segments(1) == [(1, 0)]
+    eng.forward(g["img"].to(dev), flat, out, save_for_backward=True)
+    seg = torch.full_like(flat, float("nan"))
+    a1, b1 = eng.grad_range(1, 1)
+    a0, b0 = eng.grad_range(0, 0)
+    assert (a0, b1) == (0, flat.numel()) and b0 == a1
+    eng.backward_segment(gout, seg, 1, 1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(seg[a1:b1]).all() and torch.isnan(seg[a0:b0]).all()      # only block 1's slice has been written
+    eng.backward_segment(None, seg, 0, 0)
+    torch.cuda.synchronize()
+    assert rel_l2(seg.cpu(), whole.cpu()) < 1e-5
+    from sam3_lora_b200._lib import Sam3bError
+
+    with pytest.raises(Sam3bError):          # out of order: no saved forward / wrong start block
+        eng.backward_segment(None, seg, 0, 0)
+
+
 def test_forward_tolerance_budget():
     """North-star bar: 1e-3 relative on fp32 outputs.  Checked as rel-L2 on the small golden forward."""
     g = load_small_golden()
