@@ -44,19 +44,24 @@ def test_trunk_neck_mask_head_matcher_loss_chain_matches_cpu_oracles():
     tmasks = torch.stack([((yy - 60 - 30 * k) ** 2 + (xx - 90 - 20 * k) ** 2) < (25 + 6 * k) ** 2 for k in range(sum(nb))])   # packed [sum T, H, W]
     num_boxes = float(sum(nb))
 
-    # ---------------- CPU: the oracles, chained ----------------
+    # ---------------- CPU: the oracles, chained (exact fp32, and with operands rounded where the CUDA path rounds) ----------------
     keys = O.lora_keys(params)
-    leaf = {k: params[k].detach().clone().requires_grad_(True) for k in keys}
-    p = dict(params); p.update(leaf)
-    feat_r = O.vit_forward(img, p, cfg, spec.scaling)
-    feat_r.retain_grad()
-    fr = SO.neck(feat_r, pn, SCALES, operand_dtype=torch.float16)
-    masks_r, _ = SO.seg_head(fr, queries, ps, operand_dtype=torch.float16)
     C = MO.cost_matrix(logits[..., 0].numpy(), pboxes.numpy(), tboxes.numpy(), 2.0, 5.0, 2.0, True)
     bi_r, si_r, _ = MO.match(C, nb, 1)
-    lr = LO.mask_losses(masks_r[(torch.from_numpy(bi_r), torch.from_numpy(si_r))], tmasks, num_boxes)
-    loss_r = 20.0 * lr["loss_mask"] + lr["loss_dice"]
-    loss_r.backward()
+
+    def oracle_chain(operand_dtype):
+        leaf = {k: params[k].detach().clone().requires_grad_(True) for k in keys}
+        p = dict(params); p.update(leaf)
+        feat_r = O.vit_forward(img, p, cfg, spec.scaling)
+        fr = SO.neck(feat_r, pn, SCALES, operand_dtype=operand_dtype)
+        masks_r, _ = SO.seg_head(fr, queries, ps, operand_dtype=operand_dtype)
+        lr = LO.mask_losses(masks_r[(torch.from_numpy(bi_r), torch.from_numpy(si_r))], tmasks, num_boxes)
+        loss_r = 20.0 * lr["loss_mask"] + lr["loss_dice"]
+        loss_r.backward()
+        return masks_r.detach(), loss_r.item(), {k: leaf[k].grad for k in keys}
+
+    masks_r, loss_r, grads_r = oracle_chain(None)                    # exact fp32: what the bounds below are stated against
+    masks_h, loss_h, grads_h = oracle_chain(torch.float16)           # same chain with 16-bit operand rounding, for the report
 
     # ---------------- GPU: the product path ----------------
     model = ViT(img_size=224, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4.75, window_size=8, global_att_blocks=(1,),
@@ -88,13 +93,22 @@ def test_trunk_neck_mask_head_matcher_loss_chain_matches_cpu_oracles():
     loss = 20.0 * lg["loss_mask"] + lg["loss_dice"]
     loss.backward()
 
-    assert rel_l2(masks.detach().cpu(), masks_r.detach()) < 5e-3
-    assert abs(loss.item() - loss_r.item()) < 5e-3 * abs(loss_r.item())
+    from tests.test_vit_engine_gpu import _report
+
     named = dict(model.named_parameters())
-    errs = {k: rel_l2(named[k].grad.cpu(), leaf[k].grad) for k in keys}
-    worst = max(errs.values())
-    print(f"chain: loss {loss.item():.5f} (oracle {loss_r.item():.5f}), worst LoRA-gradient rel-L2 {worst:.2e}")
-    # fp16 operands in the trunk shift the neck's inputs by ~3e-4, which can still flip a few ReLU / GroupNorm decisions in the
-    # decoder relative to the oracle (see tests/test_seg_gpu.py); hence a bound looser than the per-row tests' 5e-3.
-    assert worst < 5e-2, errs
+    errs = {k: rel_l2(named[k].grad.cpu(), grads_r[k]) for k in keys}
+    errs_h = {k: rel_l2(named[k].grad.cpu(), grads_h[k]) for k in keys}
+    e_mask, e_mask_h = rel_l2(masks.detach().cpu(), masks_r), rel_l2(masks.detach().cpu(), masks_h)
+    worst, med = max(errs.values()), sorted(errs.values())[len(errs) // 2]
+    _report("chain_trunk_neck_head_matcher_loss", {
+        "vs_exact_fp32_oracle": {"mask_logits_rel_l2": e_mask, "loss_rel": abs(loss.item() - loss_r) / abs(loss_r),
+                                 "lora_grad_rel_l2_max": worst, "lora_grad_rel_l2_median": med},
+        "vs_oracle_with_16bit_operands": {"mask_logits_rel_l2": e_mask_h, "lora_grad_rel_l2_max": max(errs_h.values())}})
+    # Bounds against the EXACT fp32 oracle.  Mask logits: 2e-3 (trunk 3e-4 + three 16-bit-operand conv stages).  Adapter
+    # gradients: ReLU / max-pool decisions within ~1e-3 of zero flip under any 10-bit-mantissa product and move whole gradient
+    # contributions; the reference's own TF32 GPU run sits 3.3 % from its fp32 CPU gradients on the real detector
+    # (tests/test_sam3_step_gpu.py, parity_report "reference_tf32_gpu"), so 6e-2 is the same bound as there.
+    assert e_mask < 2e-3, e_mask
+    assert abs(loss.item() - loss_r) < 2e-3 * abs(loss_r)
+    assert worst < 6e-2 and med < 3e-2, errs
     assert all(torch.isfinite(named[k].grad).all() for k in keys)
