@@ -482,6 +482,7 @@ def run_native(args):
     cpu_baseline = None
     gpu_eager = None
     whole = None
+    other_cfgs = None
     if world == 1:
         del A, W, H, G
         torch.cuda.empty_cache()
@@ -510,6 +511,19 @@ def run_native(args):
                     whole[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
             if "value" in whole.get("native", {}) and "value" in whole.get("reference_gpu_eager", {}):
                 whole["native_over_reference"] = whole["native"]["value"] / whole["reference_gpu_eager"]["value"]
+        if not args.no_other_configs:
+            # the other shipped shapes of BASELINE.json at the per-GPU level (the trunk is the same 32-block ViT in every
+            # config; rank, per-GPU batch and adapter dropout differ), through the public API with graph replay
+            other_cfgs = []
+            for name, rk, bb, dp in (("full_lora_config.yaml as shipped: r=32, alpha 64, lora.dropout 0.1, batch 8", 32, 8, 0.1),
+                                     ("configs[3] shape: r=32 on q,k,v,o,fc1,fc2, batch 4 per GPU (16 over 4 GPUs), dropout 0.1", 32, 4, 0.1),
+                                     ("configs[4] shape (crack_detection_config.yaml as BASELINE.json quotes it): r=8, batch 4 per GPU (32 over 8 GPUs), dropout 0.1", 8, 4, 0.1)):
+                try:
+                    ms_c, n_c = bench_arms.time_trunk_native(rk, bb, dp, 5, 3, device=dev)
+                    other_cfgs.append({"config": name, "value": bb / ms_c * 1e3, "unit": "images/sec per GPU", "ms_per_step": ms_c,
+                                       "trainable_parameters": n_c, "path": "vit.ViT(cuda_graphs=True) + autograd + fused torch AdamW"})
+                except Exception as e:  # noqa: BLE001
+                    other_cfgs.append({"config": name, "error": f"{type(e).__name__}: {e}"[:300]})
         if not args.no_cpu:
             _, cpu_baseline, _, _ = cpu_reference_arm(1, 0, 60.0)     # one image through the reference trunk on the host cores
 
@@ -525,7 +539,8 @@ def run_native(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "gpu_eager_baseline": gpu_eager,
-        "other_workloads": {"sam3_whole_model_step": whole} if whole is not None else None,
+        "other_workloads": {"sam3_whole_model_step": whole, "trunk_step_other_configs": other_cfgs}
+                           if (whole is not None or other_cfgs is not None) else None,
         "trainable_parameters": counts["trainable_parameters"],
     }
     print(json.dumps(line), flush=True)
@@ -547,6 +562,7 @@ def main():
     ap.add_argument("--lr", type=float, default=5e-5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference's GPU-eager trunk leg (needs baseline/_ref)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the trunk step at the other shipped ranks / batches")
     ap.add_argument("--no-whole-model", action="store_true", help="skip the whole-detector step legs (needs baseline/_ref)")
     ap.add_argument("--cpu-budget", type=float, default=240.0,
                     help="--impl reference: wall-clock budget in seconds; the arm stops after the step that exceeds it")

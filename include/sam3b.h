@@ -193,6 +193,9 @@ int sam3b_vit_set_drop_path(sam3b_vit* v, const float* scales);
 /* Adapter dropout (nn.Dropout on the LoRA branch input only, lora_layers.py:43,54) for the next forward + backward.
  * The mask is a stateless hash of (seed, block, site, row, col) — csrc/rng.cuh — regenerated where needed. p = 0: off */
 int sam3b_vit_set_lora_dropout(sam3b_vit* v, float p, uint32_t seed);
+/* same, with a device-resident word that the kernels ADD to `seed`: a captured CUDA graph then draws a fresh mask on every
+ * replay if the caller rewrites *seed_dev between replays (the forward and its backward must see the same value) */
+int sam3b_vit_set_lora_dropout_dev(sam3b_vit* v, float p, uint32_t seed, const uint32_t* seed_dev);
 /* out16 = inverted-dropout(x16) with that mask (exposed for tests of the mask definition) */
 int sam3b_dropout_rows16(const void* x16, int64_t ldx, int32_t rows, int32_t cols, void* out16, int64_t ldo, float p,
                          uint32_t seed, int32_t dtype, void* stream);
@@ -253,6 +256,14 @@ int sam3b_image_resize_normalize(const uint8_t* src, int32_t h, int32_t w, int32
 /* N RLE masks (cumulative run lengths, column-major, first run = zeros) -> dst [N][out][out] uint8 in {0, 1} */
 int sam3b_rle_masks_nearest(const uint32_t* cum, const int32_t* offs, const int32_t* hw, int32_t N, int32_t out, uint8_t* dst,
                             void* stream);
+/* Polygon masks: pycocotools frPyObjects + merge + decode (common/maskApi.c rleFrPoly) + nearest resize, the polygon branch
+ * of train_sam3_lora_native.py:152-163.  Step 1: every point of the 5x up-sampled boundary walk decides whether it toggles
+ * the column-major fill; edges [n_edges][8] int32 = (xs, ys, xe, ye, polygon list id, image h, image w, first-edge flag),
+ * pt_start [n_edges + 1] prefix sums of points per edge; keys [total_pts] = (list id << 32 | x*h + y) or INT64_MAX.
+ * The caller sorts keys.  Step 2: object n = union of lists list_ofs[n] .. list_ofs[n+1]-1, parity fill, nearest resize. */
+int sam3b_poly_crossings(const int32_t* edges, const int32_t* pt_start, int32_t n_edges, int64_t total_pts, int64_t* keys, void* stream);
+int sam3b_poly_masks_nearest(const int64_t* keys_sorted, int64_t n_keys, const int32_t* list_ofs, const int32_t* hw, int32_t N,
+                             int32_t out, uint8_t* dst, void* stream);
 
 /* ---- neck / pixel decoder / mask head helpers (row a8: sam3/model/necks.py:100-125, maskformer_segmentation.py:23-51,
  * 203-219).  The convolutions run on sam3b_gemm; these are the HBM-bound kernels around it.  Activations: channels-last

@@ -139,3 +139,84 @@ def rle_mask_resized(counts: Sequence[int], h: int, w: int, out: int) -> np.ndar
     ys = np.array([nearest_index(i, h, out) for i in range(out)])
     xs = np.array([nearest_index(i, w, out) for i in range(out)])
     return m[ys][:, xs] > 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Polygon masks: pycocotools `frPyObjects` (list of polygons) -> `merge` -> `decode`, the call sequence of
+# train_sam3_lora_native.py:152-156.  Third-party arithmetic restated from the published algorithm of
+# pycocotools/common/maskApi.c `rleFrPoly` (pycocotools >= 2.0.6, requirements.txt; not installed here: PARITY UNPINNED
+# beyond the known answers in tests/test_input_oracle.py - an axis-aligned integer box polygon covers exactly w*h pixels).
+# ------------------------------------------------------------------------------------------------------------------
+def _c_int(v: float) -> int:
+    """C's (int) cast: truncation toward zero."""
+    return int(v)
+
+
+def poly_crossings(xy: Sequence[float], h: int, w: int) -> np.ndarray:
+    """The sorted column-major positions x*h + y at which rleFrPoly toggles the fill for one polygon (k vertices as
+    x0, y0, x1, y1, ...): boundary up-sampled by 5, walked edge by edge along its longer axis, reduced to the points where
+    the walk enters a new up-sampled column that maps onto a pixel centre column.  Duplicates are kept (parity counts)."""
+    scale = 5.0
+    k = len(xy) // 2
+    x = [_c_int(scale * float(xy[2 * j]) + 0.5) for j in range(k)]
+    y = [_c_int(scale * float(xy[2 * j + 1]) + 0.5) for j in range(k)]
+    x.append(x[0])
+    y.append(y[0])
+    u: List[int] = []
+    v: List[int] = []
+    for j in range(k):
+        xs, xe, ys, ye = x[j], x[j + 1], y[j], y[j + 1]
+        dx, dy = abs(xe - xs), abs(ys - ye)
+        flip = (dx >= dy and xs > xe) or (dx < dy and ys > ye)
+        if flip:
+            xs, xe, ys, ye = xe, xs, ye, ys
+        if dx >= dy:
+            s = (ye - ys) / dx if dx > 0 else 0.0          # dx == dy == 0: C divides 0/0; the single point is (xs, ys) either way
+            for d in range(dx + 1):
+                t = dx - d if flip else d
+                u.append(t + xs)
+                v.append(_c_int(ys + s * t + 0.5))
+        else:
+            s = (xe - xs) / dy
+            for d in range(dy + 1):
+                t = dy - d if flip else d
+                v.append(t + ys)
+                u.append(_c_int(xs + s * t + 0.5))
+    out: List[int] = []
+    for j in range(1, len(u)):
+        if u[j] == u[j - 1]:
+            continue
+        xd = float(u[j] if u[j] < u[j - 1] else u[j] - 1)
+        xd = (xd + 0.5) / scale - 0.5
+        if math.floor(xd) != xd or xd < 0 or xd > w - 1:
+            continue
+        yd = float(v[j] if v[j] < v[j - 1] else v[j - 1])
+        yd = (yd + 0.5) / scale - 0.5
+        yd = 0.0 if yd < 0 else (float(h) if yd > h else yd)
+        yd = math.ceil(yd)
+        out.append(int(xd) * h + int(yd))
+    return np.sort(np.asarray(out, dtype=np.int64))
+
+
+def poly_mask(polygons: Sequence[Sequence[float]], h: int, w: int) -> np.ndarray:
+    """frPyObjects + merge (union) + decode of a COCO polygon list -> uint8 [h, w].  A position's value inside one polygon is
+    the parity of the number of crossings at or before it in column-major order (rleFrPoly's run construction merges
+    zero-length runs, i.e. equal crossing positions cancel in pairs)."""
+    total = np.zeros(h * w, np.uint8)
+    for poly in polygons:
+        if len(poly) < 6:
+            continue
+        a = poly_crossings(poly, h, w)
+        a = a[a < h * w]
+        toggles = np.zeros(h * w + 1, np.int64)
+        np.add.at(toggles, a, 1)
+        total |= (np.cumsum(toggles[:-1]) & 1).astype(np.uint8)
+    return total.reshape(w, h).T.copy()
+
+
+def poly_mask_resized(polygons: Sequence[Sequence[float]], h: int, w: int, out: int) -> np.ndarray:
+    """poly_mask + F.interpolate(mode="nearest") to [out, out] + `> 0.5` (train_sam3_lora_native.py:158-163) -> bool."""
+    m = poly_mask(polygons, h, w)
+    ys = np.array([nearest_index(i, h, out) for i in range(out)])
+    xs = np.array([nearest_index(i, w, out) for i in range(out)])
+    return m[ys][:, xs] > 0

@@ -67,6 +67,8 @@ SIGNATURES: dict[str, tuple] = {
     "sam3b_resample_coeffs": (C.c_int, [i32, i32, vp, vp]),
     "sam3b_image_resize_normalize": (C.c_int, [vp, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp, vp, f32, f32, vp]),
     "sam3b_rle_masks_nearest": (C.c_int, [vp, vp, vp, i32, i32, vp, vp]),
+    "sam3b_poly_crossings": (C.c_int, [vp, vp, i32, i64, vp, vp]),
+    "sam3b_poly_masks_nearest": (C.c_int, [vp, i64, vp, vp, i32, i32, vp, vp]),
     "sam3b_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]),
     "sam3b_grad_scale": (C.c_int, [vp, i64, f32, vp, vp]),
     "sam3b_scale_cast": (C.c_int, [vp, i32, vp, i32, i64, i32, vp, i32, vp]),

@@ -187,6 +187,10 @@ int sam3b_vit_set_lora_dropout(sam3b_vit* v, float p, uint32_t seed) {
   if (!v) return fail(-1, "sam3b_vit_set_lora_dropout: null handle");
   return v->eng->set_lora_dropout(p, seed);
 }
+int sam3b_vit_set_lora_dropout_dev(sam3b_vit* v, float p, uint32_t seed, const uint32_t* seed_dev) {
+  if (!v) return fail(-1, "sam3b_vit_set_lora_dropout_dev: null handle");
+  return v->eng->set_lora_dropout(p, seed, seed_dev);
+}
 int sam3b_dropout_rows16(const void* x16, int64_t ldx, int32_t rows, int32_t cols, void* out16, int64_t ldo, float p,
                          uint32_t seed, int32_t dtype, void* stream) {
   return dropout_rows16(x16, ldx, rows, cols, out16, ldo, p, seed, dtype, static_cast<cudaStream_t>(stream));
@@ -246,6 +250,13 @@ int sam3b_image_resize_normalize(const uint8_t* src, int32_t h, int32_t w, int32
 int sam3b_rle_masks_nearest(const uint32_t* cum, const int32_t* offs, const int32_t* hw, int32_t N, int32_t out, uint8_t* dst,
                             void* stream) {
   return rle_masks_nearest(cum, offs, hw, N, out, dst, static_cast<cudaStream_t>(stream));
+}
+int sam3b_poly_crossings(const int32_t* edges, const int32_t* pt_start, int32_t n_edges, int64_t total_pts, int64_t* keys, void* stream) {
+  return poly_crossings(edges, pt_start, n_edges, total_pts, keys, static_cast<cudaStream_t>(stream));
+}
+int sam3b_poly_masks_nearest(const int64_t* keys_sorted, int64_t n_keys, const int32_t* list_ofs, const int32_t* hw, int32_t N,
+                             int32_t out, uint8_t* dst, void* stream) {
+  return poly_masks_nearest(keys_sorted, n_keys, list_ofs, hw, N, out, dst, static_cast<cudaStream_t>(stream));
 }
 
 #define SAM3B_ST static_cast<cudaStream_t>(stream)

@@ -446,7 +446,8 @@ __global__ void __launch_bounds__(256) build_pos_table_kernel(const float* __res
 template <int DT>
 __global__ void __launch_bounds__(256) dropout_rows16_kernel(const uint16_t* __restrict__ x, int64_t ldx, int rows, int cols,
                                                              uint16_t* __restrict__ out, int64_t ldo, float inv_keep,
-                                                             uint32_t seed, uint32_t thr) {
+                                                             uint32_t seed, uint32_t thr, const uint32_t* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed += __ldg(seed_dev);     // per-step seed kept in device memory (CUDA-graph replays)
   const int c8 = cols / 8;
   const int64_t n = (int64_t)rows * c8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -545,15 +546,15 @@ int build_pos_table(const float* pos_embed, int side, int G, int ws, int D, floa
 }
 
 int dropout_rows16(const void* x16, int64_t ldx, int rows, int cols, void* out16, int64_t ldo, float p, uint32_t seed,
-                   int dtype, cudaStream_t s) {
+                   int dtype, cudaStream_t s, const uint32_t* seed_dev) {
   SAM3B_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "dropout_rows16: cols / ld must be multiples of 8");
   SAM3B_REQUIRE(p >= 0.f && p < 1.f, "dropout_rows16: p=%f outside [0,1)", p);
   const int64_t n = (int64_t)rows * (cols / 8);
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
   const float inv_keep = 1.f / (1.f - p);
   const uint32_t thr = dropout_threshold(p);
-  if (dtype == 0) dropout_rows16_kernel<0><<<blocks, 256, 0, s>>>((const uint16_t*)x16, ldx, rows, cols, (uint16_t*)out16, ldo, inv_keep, seed, thr);
-  else dropout_rows16_kernel<1><<<blocks, 256, 0, s>>>((const uint16_t*)x16, ldx, rows, cols, (uint16_t*)out16, ldo, inv_keep, seed, thr);
+  if (dtype == 0) dropout_rows16_kernel<0><<<blocks, 256, 0, s>>>((const uint16_t*)x16, ldx, rows, cols, (uint16_t*)out16, ldo, inv_keep, seed, thr, seed_dev);
+  else dropout_rows16_kernel<1><<<blocks, 256, 0, s>>>((const uint16_t*)x16, ldx, rows, cols, (uint16_t*)out16, ldo, inv_keep, seed, thr, seed_dev);
   SAM3B_LAUNCHED();
   return 0;
 }

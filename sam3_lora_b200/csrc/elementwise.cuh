@@ -31,7 +31,7 @@ int build_pos_table(const float* pos_embed, int side, int G, int ws, int D, floa
 
 // out16[row][c] = keep(row,c) ? x16[row][c] / (1-p) : 0  for c < cols (inverted dropout, mask from rng.cuh)
 int dropout_rows16(const void* x16, int64_t ldx, int rows, int cols, void* out16, int64_t ldo, float p, uint32_t seed,
-                   int dtype, cudaStream_t s);
+                   int dtype, cudaStream_t s, const uint32_t* seed_dev = nullptr);
 
 // y16[row][0..D) = (16-bit) x[row][0..D)
 // scale (device scalar, optional): y16 = (16-bit)(x * *scale)

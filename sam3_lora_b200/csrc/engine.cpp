@@ -342,10 +342,11 @@ void VitEngine::build_site_descs() {
   site_desc_dirty_ = true;
 }
 
-int VitEngine::set_lora_dropout(float p, uint32_t seed) {
+int VitEngine::set_lora_dropout(float p, uint32_t seed, const uint32_t* seed_dev) {
   SAM3B_REQUIRE(p >= 0.f && p < 1.f, "vit set_lora_dropout: p=%f outside [0,1)", p);
   drop_p_ = p;
   drop_seed_ = seed;
+  drop_seed_dev_ = seed_dev;
   return 0;
 }
 
@@ -357,7 +358,7 @@ int VitEngine::site_down(const Site& st, uint16_t* act, int64_t ld, int M, int b
   int64_t lds = ld;
   if (drop_p_ > 0.f) {
     SAM3B_REQUIRE(xd16_ != nullptr, "vit: adapter dropout needs a training workspace");
-    int rc = dropout_rows16(act, ld, M, st.in, xd16_, st.in, drop_p_, site_seed(drop_seed_, block, site), cfg_.dtype, s);
+    int rc = dropout_rows16(act, ld, M, st.in, xd16_, st.in, drop_p_, site_seed(drop_seed_, block, site), cfg_.dtype, s, drop_seed_dev_);
     if (rc) return rc;
     src = xd16_;
     lds = st.in;
@@ -379,7 +380,7 @@ int VitEngine::site_wgrad(const Site& st, const uint16_t* x_act, int64_t ldx, co
   const uint16_t* xa = x_act;   // operand of dA = drop(x)^T . dT''
   int64_t ldxa = ldx;
   if (fwd_drop_p_ > 0.f) {
-    int rcd = dropout_rows16(x_act, ldx, M, st.in, xd16_, st.in, fwd_drop_p_, site_seed(fwd_drop_seed_, block, site), cfg_.dtype, s);
+    int rcd = dropout_rows16(x_act, ldx, M, st.in, xd16_, st.in, fwd_drop_p_, site_seed(fwd_drop_seed_, block, site), cfg_.dtype, s, fwd_drop_seed_dev_);
     if (rcd) return rcd;
     xa = xd16_;
     ldxa = st.in;
@@ -516,6 +517,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
   fwd_drop_scales_ = drop_scales_;
   fwd_drop_p_ = drop_p_;
   fwd_drop_seed_ = drop_seed_;
+  fwd_drop_seed_dev_ = drop_seed_dev_;
   return 0;
 }
 
@@ -582,7 +584,7 @@ int VitEngine::backward_segment(const float* gout_nchw, float* grad_flat, int bl
     b.A = dy + st.out; b.lda = ld; b.B = st.wt_ext + st.out; b.ldb = st.ldwt;
     b.dtype = dt; b.epilogue = EPI_ADDMASK16; b.C = dst; b.ldc = lddst;
     if (epi == EPI_DGELU) { b.aux = aux; b.ldaux = ldaux; }
-    b.drop_p = fwd_drop_p_; b.drop_seed = site_seed(fwd_drop_seed_, block, site);
+    b.drop_p = fwd_drop_p_; b.drop_seed = site_seed(fwd_drop_seed_, block, site); b.drop_seed_dev = fwd_drop_seed_dev_;
     return gemm_launch(b, s);
   };
 

@@ -61,7 +61,9 @@ class VitEngine {
   // nullptr disables it (eval mode / drop_path 0).
   void set_drop_path(const float* scales) { drop_scales_ = scales; }
   // Adapter dropout (lora_layers.py:43,54): probability and seed for the next forward and its backward; p = 0 disables.
-  int set_lora_dropout(float p, uint32_t seed);
+  // seed_dev (optional): device word ADDED to `seed` inside the kernels, so a captured CUDA graph draws a new mask per replay
+  // when the caller rewrites that word between replays.
+  int set_lora_dropout(float p, uint32_t seed, const uint32_t* seed_dev = nullptr);
 
  private:
   struct Site {
@@ -128,6 +130,7 @@ class VitEngine {
   int Rmax_ = 0;
   float drop_p_ = 0.f, fwd_drop_p_ = 0.f;
   uint32_t drop_seed_ = 0, fwd_drop_seed_ = 0;
+  const uint32_t *drop_seed_dev_ = nullptr, *fwd_drop_seed_dev_ = nullptr;
   uint16_t* xd16_ = nullptr;  // dropout(x) scratch [M][max in]
   const float* drop_scales_ = nullptr;
   const float* fwd_drop_scales_ = nullptr;  // what the saved forward used

@@ -37,7 +37,7 @@ struct GemmParams {
   const float* bias;
   const float* res; int64_t ldres; int res_row_mod;
   const float* row_scale; int rows_per_scale;
-  float drop_inv_keep; uint32_t drop_seed, drop_thr;
+  float drop_inv_keep; uint32_t drop_seed, drop_thr; const uint32_t* drop_seed_dev;
   const void* aux; int64_t ldaux;
   const float2* rope; int rope_period; int rope_cols;
   float alpha;
@@ -234,6 +234,7 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
     uint4* c4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.C) + (int64_t)row * p.ldc + col);
     const uint4* h4 = p.aux == nullptr ? nullptr
                                        : reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row * p.ldaux + col);
+    const uint32_t mask_seed = p.drop_seed + (p.drop_seed_dev != nullptr ? __ldg(p.drop_seed_dev) : 0u);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (q * 8 < nvalid) {
@@ -246,8 +247,8 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
           float2 c = unpack2<DT>(cw[e]);
           float a0 = v[q * 8 + 2 * e] * p.drop_inv_keep, a1 = v[q * 8 + 2 * e + 1] * p.drop_inv_keep;
           if (h4 != nullptr) { const float2 hh = unpack2<DT>(hw[e]); a0 *= dgelu_erf(hh.x); a1 *= dgelu_erf(hh.y); }
-          if (dropout_keep(p.drop_seed, row, col + q * 8 + 2 * e, p.N, p.drop_thr)) c.x += a0;
-          if (dropout_keep(p.drop_seed, row, col + q * 8 + 2 * e + 1, p.N, p.drop_thr)) c.y += a1;
+          if (dropout_keep(mask_seed, row, col + q * 8 + 2 * e, p.N, p.drop_thr)) c.x += a0;
+          if (dropout_keep(mask_seed, row, col + q * 8 + 2 * e + 1, p.N, p.drop_thr)) c.y += a1;
           cw[e] = pack2<DT>(c.x, c.y);
         }
         c4[q] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
@@ -845,7 +846,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.bias = a.bias;
   p.res = a.residual; p.ldres = a.ldres; p.res_row_mod = a.res_row_mod;
   p.row_scale = a.row_scale; p.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
-  p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_seed = a.drop_seed; p.drop_thr = dropout_threshold(a.drop_p);
+  p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_seed = a.drop_seed; p.drop_thr = dropout_threshold(a.drop_p); p.drop_seed_dev = a.drop_seed_dev;
   p.aux = a.aux; p.ldaux = a.ldaux;
   p.rope = reinterpret_cast<const float2*>(a.rope); p.rope_period = a.rope_period > 0 ? a.rope_period : 1;
   p.rope_cols = a.rope_cols;

@@ -31,6 +31,7 @@ struct GemmArgs {
   const float* bias = nullptr;
   const float* residual = nullptr; int64_t ldres = 0; int res_row_mod = 0;
   float drop_p = 0.f; uint32_t drop_seed = 0;   // EPI_ADDMASK16: mask = rng.cuh dropout_keep(seed, row, col, N)
+  const uint32_t* drop_seed_dev = nullptr;      // optional device word added to drop_seed (per-step seed under CUDA graphs)
   const float* row_scale = nullptr; int rows_per_scale = 1;  // EPI_RESIDUAL_F32: out = res + row_scale[row / rows_per_scale] * (acc + bias)  (DropPath)
   const void* aux = nullptr; int64_t ldaux = 0;
   const float* rope = nullptr; int rope_period = 1; int rope_cols = 0;  // rope: [period][32] (cos,sin) pairs

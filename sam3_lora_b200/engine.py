@@ -94,6 +94,8 @@ def _declare(lib):
     lib.sam3b_vit_set_drop_path.restype = C.c_int
     lib.sam3b_vit_set_lora_dropout.argtypes = [C.c_void_p, C.c_float, C.c_uint32]
     lib.sam3b_vit_set_lora_dropout.restype = C.c_int
+    lib.sam3b_vit_set_lora_dropout_dev.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_void_p]
+    lib.sam3b_vit_set_lora_dropout_dev.restype = C.c_int
     lib.sam3b_vit_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sam3b_vit_backward.restype = C.c_int
     lib.sam3b_vit_backward_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, C.c_void_p]
@@ -220,8 +222,14 @@ class VitEngine:
         self._drop_scales = scales
         _lib.check(self.lib.sam3b_vit_set_drop_path(self._h, _lib.ptr(scales)))
 
-    def set_lora_dropout(self, p: float, seed: int):
-        _lib.check(self.lib.sam3b_vit_set_lora_dropout(self._h, float(p), int(seed) & 0xFFFFFFFF))
+    def set_lora_dropout(self, p: float, seed: int, seed_dev=None):
+        """seed_dev: optional int32 CUDA tensor (1 element) whose value the kernels add to `seed` — rewritten per step by the
+        caller so that CUDA-graph replays draw fresh masks; the caller keeps it alive."""
+        self._drop_seed_dev = seed_dev
+        if seed_dev is None:
+            _lib.check(self.lib.sam3b_vit_set_lora_dropout(self._h, float(p), int(seed) & 0xFFFFFFFF))
+        else:
+            _lib.check(self.lib.sam3b_vit_set_lora_dropout_dev(self._h, float(p), int(seed) & 0xFFFFFFFF, seed_dev.data_ptr()))
 
     def backward(self, gout, grad_flat):
         _lib.check(self.lib.sam3b_vit_backward(self._h, gout.data_ptr(), _lib.ptr(grad_flat), _lib.current_stream()))

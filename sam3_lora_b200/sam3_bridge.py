@@ -390,9 +390,40 @@ def swap_matcher(model: nn.Module) -> nn.Module:
     return model
 
 
+def disable_activation_checkpointing() -> int:
+    """The reference recomputes every DETR encoder / decoder / geometry layer in the backward (`activation_ckpt_wrapper`,
+    sam3/model/act_ckpt_utils.py:17-114, enabled by sam3/model_builder.py:146,184) to fit 24-32 GB cards.  With 180 GB of HBM
+    the activations of a batch-8 step fit several times over, so the swapped model keeps them instead (the same decision as
+    the trunk's): the wrapper is replaced, in the modules that imported it, by a direct call.  Outputs and
+    gradients are unchanged.  Returns the number of module namespaces patched."""
+    import_reference()
+
+    def direct(module):
+        def call(*args, act_ckpt_enable: bool = True, use_reentrant: bool = False, **kwargs):
+            return module(*args, **kwargs)
+        return call
+
+    n = 0
+    for name in ("sam3.model.encoder", "sam3.model.decoder", "sam3.model.geometry_encoders"):
+        mod = sys.modules.get(name) or importlib.import_module(name)
+        if hasattr(mod, "activation_ckpt_wrapper"):
+            if not hasattr(mod, "_sam3b_ref_ckpt_wrapper"):
+                mod._sam3b_ref_ckpt_wrapper = mod.activation_ckpt_wrapper
+            mod.activation_ckpt_wrapper = direct
+            n += 1
+    return n
+
+
+def restore_activation_checkpointing() -> None:
+    for name in ("sam3.model.encoder", "sam3.model.decoder", "sam3.model.geometry_encoders"):
+        mod = sys.modules.get(name)
+        if mod is not None and hasattr(mod, "_sam3b_ref_ckpt_wrapper"):
+            mod.activation_ckpt_wrapper = mod._sam3b_ref_ckpt_wrapper
+
+
 def build_native_model(device="cuda", *, checkpoint_path: Optional[str] = None, seed: Optional[int] = 0, max_batch: int = 8,
                        operand_dtype=torch.float16, cuda_graphs: bool = False, eval_mode: bool = False,
-                       parts: Iterable[str] = ("trunk", "neck", "pixel_decoder", "mha", "matcher"), reference_model: Optional[nn.Module] = None):
+                       parts: Iterable[str] = ("trunk", "neck", "pixel_decoder", "mha", "matcher", "no_recompute"), reference_model: Optional[nn.Module] = None):
     """Reference `Sam3Image` with the hot-path modules swapped for the native ones.  `parts` selects which."""
     model = reference_model if reference_model is not None else build_reference_model(
         "cpu", eval_mode=eval_mode, checkpoint_path=checkpoint_path, seed=seed)
@@ -407,4 +438,6 @@ def build_native_model(device="cuda", *, checkpoint_path: Optional[str] = None, 
         swap_mha(model)
     if "matcher" in parts:
         swap_matcher(model)
+    if "no_recompute" in parts:
+        disable_activation_checkpointing()
     return model.to(device)

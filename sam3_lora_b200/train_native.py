@@ -15,7 +15,9 @@ Objective (`training.objective`, not a reference key):
     `model.allow_random_init: true` (tests / benchmarks only).
   * "trunk_proxy" - the trunk alone with a 1x1 mask head and BCE + dice against the union mask; for smoke tests of
     non-SAM3 trunk shapes only.
-Extra optional keys: `training.gpu_preprocess` (default true), `training.seed` (default 0), `training.max_steps`.
+Extra optional keys: `training.gpu_preprocess` (default true), `training.gpu_jpeg_decode` (nvJPEG, default false),
+`training.prefetch` (batches prepared ahead by a background thread, default 2; 0 = the reference's synchronous loader),
+`training.seed` (default 0), `training.max_steps`, `training.cuda_graphs`.
 """
 from __future__ import annotations
 
@@ -79,10 +81,11 @@ class COCOSegmentDataset(torch.utils.data.Dataset):
     """Same directory contract as the reference: `<data_dir>/<split>/_annotations.coco.json` + images."""
 
     def __init__(self, data_dir, split: str = "train", mask_size: int = 72, resolution: int = RESOLUTION, device=None,
-                 with_instances: bool = False):
+                 with_instances: bool = False, gpu_jpeg: bool = False):
         # device: a CUDA device -> the image is resized / normalised on the GPU by data.GpuPreprocessor (bit-identical to the
         # PIL + numpy path below; only the raw uint8 pixels cross PCIe).  None -> host path (CPU tests, the reference's way).
         self.gpu_prep = None
+        self.gpu_jpeg = gpu_jpeg
         self.with_instances = with_instances      # per-object boxes + [R, R] boolean segments (the SAM3 objective's targets)
         if device is not None and torch.device(device).type == "cuda":
             from .data import GpuPreprocessor  # noqa: PLC0415
@@ -109,41 +112,79 @@ class COCOSegmentDataset(torch.utils.data.Dataset):
     def __len__(self):
         return len(self.image_ids)
 
+    def _open_image(self, path: Path):
+        """-> (pixels for the resize step, original width, original height).  JPEG files go through nvJPEG on the GPU when
+        `gpu_jpeg` is on (a few grey levels from libjpeg-turbo's decode: off by default, PIL decode is the reference's)."""
+        from PIL import Image
+
+        if self.gpu_prep is not None and self.gpu_jpeg and path.suffix.lower() in (".jpg", ".jpeg"):
+            u8 = self.gpu_prep.decode_jpeg(path.read_bytes())
+            return u8, u8.shape[1], u8.shape[0]
+        img = Image.open(path).convert("RGB")
+        return img, img.size[0], img.size[1]
+
+    def _segments_gpu(self, anns: List[Dict], h0: int, w0: int) -> torch.Tensor:
+        """Instance masks at the model resolution straight from the annotations on the GPU (data.GpuPreprocessor): polygons
+        through the rleFrPoly kernels, RLE through the run-length kernel, box-only annotations as their rectangle."""
+        R = self.resolution
+        out = torch.zeros(len(anns), R, R, dtype=torch.bool, device=self.gpu_prep.device)
+        poly_idx, poly_objs, rle_idx, rle_objs = [], [], [], []
+        for i, a in enumerate(anns):
+            seg = a.get("segmentation")
+            if isinstance(seg, dict):
+                hh, ww = seg.get("size", (h0, w0))
+                rle_idx.append(i)
+                rle_objs.append((seg["counts"], int(hh), int(ww)))
+            elif isinstance(seg, list) and seg:
+                poly_idx.append(i)
+                poly_objs.append((seg, h0, w0))
+            else:
+                x, y, bw, bh = a["bbox"]
+                poly_idx.append(i)
+                poly_objs.append(([[x, y, x + bw, y, x + bw, y + bh, x, y + bh]], h0, w0))
+        if poly_objs:
+            out[torch.tensor(poly_idx, device=out.device)] = self.gpu_prep.polygon_masks(poly_objs)
+        if rle_objs:
+            out[torch.tensor(rle_idx, device=out.device)] = self.gpu_prep.rle_masks(rle_objs)
+        return out
+
     def __getitem__(self, idx):
         from PIL import Image
 
         info = self.images[self.image_ids[idx]]
-        img = Image.open(self.split_dir / info["file_name"]).convert("RGB")
-        w0, h0 = img.size
+        img, w0, h0 = self._open_image(self.split_dir / info["file_name"])
         if self.gpu_prep is not None:
-            x = self.gpu_prep.image(np.asarray(img))
+            x = self.gpu_prep.image(img if isinstance(img, torch.Tensor) else np.asarray(img))
         else:
             img = img.resize((self.resolution, self.resolution), Image.BILINEAR)
             x = torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1)
             x = (x - 0.5) / 0.5
-        union = np.zeros((h0, w0), dtype=np.uint8)
-        names, boxes, masks = [], [], []
-        for a in self.img_to_anns.get(info["id"], []):
-            mk = _ann_to_mask(a, h0, w0)
-            union |= mk
-            names.append(self.categories.get(a.get("category_id"), "object"))
-            if "bbox" in a:
-                # COCO xywh -> xyxy, scaled to the model resolution and normalised (train_sam3_lora_native.py:129-143)
-                bx, by, bw, bh = (float(v) for v in a["bbox"])
-                boxes.append([bx / w0, by / h0, (bx + bw) / w0, (by + bh) / h0])
-                masks.append(mk)
-        m = torch.from_numpy(union.astype(np.float32))[None, None]
-        m = F.interpolate(m, size=(self.mask_size, self.mask_size), mode="area")[0]
-        item = {"image": x, "mask": m, "prompt": _query_text(names), "image_id": info["id"], "orig_size": (h0, w0)}
+        anns = self.img_to_anns.get(info["id"], [])
+        names = [self.categories.get(a.get("category_id"), "object") for a in anns]
+        item = {"image": x, "prompt": _query_text(names), "image_id": info["id"], "orig_size": (h0, w0)}
         if self.with_instances:
+            # per-object targets of the SAM3 objective: COCO xywh -> normalised xyxy boxes (train_sam3_lora_native.py:129-143)
+            # and [R, R] boolean segments (:146-167)
             R = self.resolution
-            if masks:
-                seg = torch.from_numpy(np.stack(masks)).to(x.device if self.gpu_prep is not None else "cpu")
-                seg = F.interpolate(seg[:, None].float(), size=(R, R), mode="nearest")[:, 0] > 0.5     # :158-163
-            else:
+            inst = [a for a in anns if "bbox" in a]
+            boxes = [[a["bbox"][0] / w0, a["bbox"][1] / h0, (a["bbox"][0] + a["bbox"][2]) / w0, (a["bbox"][1] + a["bbox"][3]) / h0]
+                     for a in inst]
+            if not inst:
                 seg = torch.zeros(0, R, R, dtype=torch.bool)
+            elif self.gpu_prep is not None:
+                seg = self._segments_gpu(inst, h0, w0)
+            else:       # host path (CPU tests): PIL's scan-line fill, which differs from pycocotools on boundary pixels
+                seg = torch.from_numpy(np.stack([_ann_to_mask(a, h0, w0) for a in inst]))
+                seg = F.interpolate(seg[:, None].float(), size=(R, R), mode="nearest")[:, 0] > 0.5
             item["boxes"] = torch.tensor(boxes, dtype=torch.float32).reshape(-1, 4)
             item["segments"] = seg
+        else:
+            # the trunk-proxy objective's target: union of the instance masks, area-averaged to the trunk grid
+            union = np.zeros((h0, w0), dtype=np.uint8)
+            for a in anns:
+                union |= _ann_to_mask(a, h0, w0)
+            m = torch.from_numpy(union.astype(np.float32))[None, None]
+            item["mask"] = F.interpolate(m, size=(self.mask_size, self.mask_size), mode="area")[0]
         return item
 
 
@@ -331,12 +372,20 @@ class SAM3TrainerNative:
         gpu_prep = bool(self.config["training"].get("gpu_preprocess", True))      # not a reference key; default on
         sam3 = self.objective == "sam3"
         ds = COCOSegmentDataset(self.config["training"]["data_dir"], split, mask_size=spec.grid, resolution=spec.img_size,
-                                device=self.device if gpu_prep else None, with_instances=sam3)
+                                device=self.device if gpu_prep else None, with_instances=sam3,
+                                gpu_jpeg=bool(self.config["training"].get("gpu_jpeg_decode", False)))
         idx = D.shard_indices(len(ds), self.rank, self.world, epoch=epoch, shuffle=shuffle)
         sub = torch.utils.data.Subset(ds, idx)
-        return torch.utils.data.DataLoader(sub, batch_size=self.batch_size, shuffle=False, num_workers=0,
-                                           collate_fn=collate_sam3 if sam3 else collate,
-                                           pin_memory=(not gpu_prep) and not sam3, drop_last=False)
+        loader = torch.utils.data.DataLoader(sub, batch_size=self.batch_size, shuffle=False, num_workers=0,
+                                             collate_fn=collate_sam3 if sam3 else collate,
+                                             pin_memory=(not gpu_prep) and not sam3, drop_last=False)
+        depth = int(self.config["training"].get("prefetch", 2))
+        if depth <= 0:
+            return loader
+        # the next batch's file reads, annotation parsing, GPU pre-processing and H2D copies run behind the current step
+        from .data import Prefetcher  # noqa: PLC0415
+
+        return Prefetcher(loader, depth=depth, device=self.device)
 
     def _loss(self, batch):
         """(loss, number of images) of one batch under the configured objective."""

@@ -91,6 +91,7 @@ class _GraphState:
         self.out = torch.empty(B, spec.embed_dim, spec.grid, spec.grid, device=device, dtype=torch.float32)
         self.gout = torch.empty_like(self.out)
         self.drop = torch.ones(spec.depth, 2, B, device=device, dtype=torch.float32) if has_drop else None
+        self.seed_dev = torch.zeros(1, device=device, dtype=torch.int32)   # per-step adapter-dropout seed (read by the kernels)
         self.g_fwd = self.g_bwd = None
         self.warm = False        # one eager step has run (first-use attribute calls, allocator warm-up)
 
@@ -116,8 +117,8 @@ class _TrunkFn(torch.autograd.Function):
         if need_grad:
             vit._fwd_generation += 1
         ctx.generation = vit._fwd_generation if need_grad else -1
-        if vit.cuda_graphs and need_grad and p_drop == 0.0 and flat is not None:
-            key = (str(images.device), B, eng.work_buf.data_ptr(), eng.weight_buf.data_ptr(), flat.data_ptr(), drop is not None)
+        if vit.cuda_graphs and need_grad and flat is not None:
+            key = (str(images.device), B, eng.work_buf.data_ptr(), eng.weight_buf.data_ptr(), flat.data_ptr(), drop is not None, p_drop)
             st = vit._graph_state
             if st is None or st.key != key:
                 st = vit._graph_state = _GraphState(key, B, spec, images.device, drop is not None)
@@ -125,7 +126,16 @@ class _TrunkFn(torch.autograd.Function):
             if drop is not None:
                 st.drop.copy_(drop)
             eng.set_drop_path(st.drop)
-            eng.set_lora_dropout(0.0, 0)
+            if p_drop > 0.0:
+                # adapter dropout under graph replay: the per-step seed lives in device memory (the kernels add it to the
+                # captured base seed), redrawn here on the device - no host round trip, reproducible under torch.manual_seed
+                if vit.lora_dropout_seed_override is not None:
+                    st.seed_dev.fill_(int(vit.lora_dropout_seed_override) & 0x7FFFFFFF)
+                else:
+                    st.seed_dev.random_(0, 2 ** 31 - 1)
+                eng.set_lora_dropout(p_drop, 0, st.seed_dev)
+            else:
+                eng.set_lora_dropout(0.0, 0)
             if not st.warm:
                 eng.forward(st.img, flat, st.out, save_for_backward=True)
             elif st.g_fwd is None:
@@ -230,7 +240,8 @@ class ViT(nn.Module):
                                    "use_act_checkpoint is accepted and ignored: nothing is recomputed)")
         super().__init__()
         # cuda_graphs=True: after one eager warm-up step the ~1280 launches of the trunk forward and of its backward are
-        # each replayed from a CUDA graph (training mode, adapter dropout 0; inputs are copied into static buffers).
+        # each replayed from a CUDA graph (training mode; inputs, DropPath scales and the adapter-dropout seed live in static
+        # device buffers that are rewritten before every replay).
         self.cuda_graphs = bool(cuda_graphs)
         self._graph_state = None
         # stochastic depth decay rule of the reference: linspace(0, rate, depth) (vitdet.py:746), 0.1 in SAM3

@@ -69,3 +69,78 @@ def test_rle_masks_are_bit_exact_and_batched():
         runs = [0] + runs
     ref = torch.nn.functional.interpolate(torch.from_numpy(m).float()[None, None], size=(1008, 1008), mode="nearest")[0, 0] > 0.5
     assert torch.equal(GpuPreprocessor(1008).rle_masks([(runs, h, w)])[0].cpu(), ref)
+
+
+def _random_polygon(rng, h, w, k):
+    ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+    r = rng.uniform(0.15, 0.6, k) * min(h, w)
+    cx, cy = rng.uniform(0.2, 0.8) * w, rng.uniform(0.2, 0.8) * h
+    pts = np.stack([cx + r * np.cos(ang), cy + r * np.sin(ang)], 1)          # may leave the image: clipping is exercised
+    return np.round(pts, 2).reshape(-1).tolist()
+
+
+def test_polygon_masks_are_bit_exact_with_the_rleFrPoly_restatement():
+    """frPyObjects + merge + decode + nearest resize on the GPU (crossing kernel -> sort -> parity fill) against the oracle:
+    star-shaped and self-intersecting polygons, several polygons per object, polygons that leave the image, short lists."""
+    from sam3_lora_b200.data import GpuPreprocessor
+
+    rng = np.random.default_rng(11)
+    prep = GpuPreprocessor(96)
+    objs = []
+    for (h, w) in ((40, 50), (64, 64), (90, 33), (120, 200)):
+        for n_poly in (1, 2):
+            polys = [_random_polygon(rng, h, w, int(rng.integers(3, 12))) for _ in range(n_poly)]
+            objs.append((polys, h, w))
+    objs.append(([[10, 10, 20, 10, 20, 20, 10, 20]], 40, 50))
+    objs.append(([[1, 1, 2, 2], [5, 5, 30, 8, 12, 33]], 40, 50))                  # first list is degenerate and skipped
+    objs.append(([[3, 3, 30, 30, 30, 3, 3, 30]], 40, 40))                         # bow-tie (self-intersecting)
+    objs.append(([], 20, 20))                                                     # object without polygons
+    got = prep.polygon_masks(objs).cpu().numpy()
+    assert got.shape == (len(objs), 96, 96) and got.dtype == np.bool_
+    for i, (polys, h, w) in enumerate(objs):
+        ref = IO.poly_mask_resized(polys, h, w, 96)
+        assert np.array_equal(got[i], ref), (i, h, w, int((got[i] ^ ref).sum()))
+    assert prep.polygon_masks([]).shape == (0, 96, 96)
+    # SAM3 size: one 1024 x 1024 annotation with a 40-vertex outline
+    h = w = 1024
+    poly = _random_polygon(rng, h, w, 40)
+    big = GpuPreprocessor(1008).polygon_masks([([poly], h, w)])[0].cpu().numpy()
+    assert np.array_equal(big, IO.poly_mask_resized([poly], h, w, 1008))
+
+
+def test_nvjpeg_decode_feeds_the_resize_kernel_and_is_close_to_pil():
+    import io
+
+    from PIL import Image
+
+    from sam3_lora_b200.data import GpuPreprocessor
+
+    yy, xx = np.mgrid[0:240, 0:320]
+    img = np.stack([(xx * 255 // 319), (yy * 255 // 239), ((xx + yy) % 256)], -1).astype(np.uint8)     # smooth: JPEG-friendly
+    buf = io.BytesIO()
+    Image.fromarray(img).save(buf, format="JPEG", quality=95, subsampling=0)
+    prep = GpuPreprocessor(128)
+    dec = prep.decode_jpeg(buf.getvalue())
+    assert dec.is_cuda and dec.dtype == torch.uint8 and dec.shape == (240, 320, 3)
+    pil = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB"))
+    diff = np.abs(dec.cpu().numpy().astype(int) - pil.astype(int))
+    assert diff.max() <= 4 and diff.mean() < 0.6           # different IDCT implementations: a few grey levels, not bit-exact
+    x = prep.image(dec)
+    ref = torch.from_numpy(IO.to_tensor_normalize(IO.resize_bilinear_u8(dec.cpu().numpy(), 128, 128)))
+    assert torch.equal(x.cpu(), ref)                        # from the decoded pixels on, the pipeline is exact
+
+
+def test_prefetcher_overlaps_and_preserves_order():
+    from sam3_lora_b200.data import Prefetcher
+
+    def make(i):
+        return {"i": i, "x": torch.full((1024,), float(i)).pin_memory()}
+
+    seen = []
+    for item in Prefetcher((make(i) for i in range(6)), depth=2, device="cuda",
+                           transform=lambda d: {"i": d["i"], "x": d["x"].to("cuda", non_blocking=True)}):
+        assert item["x"].is_cuda and float(item["x"].sum()) == 1024.0 * item["i"]
+        seen.append(item["i"])
+    assert seen == list(range(6))
+    with pytest.raises(ZeroDivisionError):
+        list(Prefetcher((1 // (3 - i) for i in range(6)), device="cuda"))

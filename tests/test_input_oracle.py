@@ -81,3 +81,32 @@ def test_compressed_rle_string_round_trip():
         assert IO.rle_from_string(enc) == cnts
         assert rle_counts(enc) == cnts and rle_counts(enc.encode()) == cnts
     assert rle_counts([3, 4, 5]) == [3, 4, 5]
+
+
+def test_polygon_oracle_known_answers():
+    """pycocotools is not installed, so rleFrPoly's restatement is checked against facts that hold for pycocotools itself:
+    an axis-aligned integer box polygon [x, y, x+w, y+h] covers exactly the w*h pixels [x, x+w) x [y, y+h) (the
+    frPyObjects / area identity every COCO tool relies on), vertex order and starting vertex do not matter, polygons are
+    clipped to the image, several polygons of one object are OR-ed (mask_utils.merge), degenerate lists are ignored."""
+    box = [10, 10, 20, 10, 20, 20, 10, 20]
+    m = IO.poly_mask([box], 40, 50)
+    assert m.shape == (40, 50) and m.sum() == 100 and m[10:20, 10:20].all()
+    assert np.array_equal(IO.poly_mask([box[2:] + box[:2]], 40, 50), m)                   # rotated start vertex
+    rev = [c for pt in reversed(list(zip(box[0::2], box[1::2]))) for c in pt]
+    assert np.array_equal(IO.poly_mask([rev], 40, 50), m)                                 # clockwise / counter-clockwise
+    big = IO.poly_mask([[5, 5, 60, 5, 60, 45, 5, 45]], 40, 50)
+    assert big.sum() == 45 * 35 and big[5:, 5:].all() and not big[:5].any()
+    two = IO.poly_mask([[0, 0, 10, 0, 10, 10, 0, 10], [5, 5, 60, 5, 60, 45, 5, 45]], 40, 50)
+    assert two.sum() == 45 * 35 + 100 - 25
+    assert IO.poly_mask([[1, 1, 2, 2]], 10, 10).sum() == 0                                 # fewer than 3 vertices
+    # a triangle: inside / outside by the even-odd rule on pixel centres, up to the one-pixel boundary band of the 5x walk
+    tri = [5.0, 5.0, 30.0, 8.0, 12.0, 33.0]
+    mt = IO.poly_mask([tri], 40, 50)
+    yy, xx = np.mgrid[0:40, 0:50] + 0.5
+
+    def side(ax, ay, bx, by):
+        return (bx - ax) * (yy - ay) - (by - ay) * (xx - ax)
+
+    inside = (side(5, 5, 30, 8) > 0) & (side(30, 8, 12, 33) > 0) & (side(12, 33, 5, 5) > 0)
+    assert abs(int(mt.sum()) - int(inside.sum())) <= 40 and (mt.astype(bool) ^ inside).sum() <= 60
+    assert IO.poly_mask_resized([box], 40, 50, 100).sum() == round(100 * (100 / 40) * (100 / 50))

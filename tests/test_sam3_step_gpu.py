@@ -144,6 +144,7 @@ def test_forward_and_adapter_gradients_match_reference_golden(native_model, gold
 def _reference_gpu_distance(golden, cot, sel):
     import lora_layers as ref_lora  # the reference's root-level module (baseline/_ref)
 
+    bridge.restore_activation_checkpointing()              # the yardstick is the UNMODIFIED reference
     model = bridge.build_reference_model("cuda", seed=0)
     cfg = ref_lora.LoRAConfig(rank=RANK, alpha=ALPHA, dropout=0.0, target_modules=TARGETS, apply_to_vision_encoder=True,
                               apply_to_text_encoder=False, apply_to_geometry_encoder=False, apply_to_detr_encoder=False,
@@ -168,6 +169,7 @@ def _reference_gpu_distance(golden, cot, sel):
     out["grad_rel_l2_median"] = sorted(full.values())[len(full) // 2]
     del model, fin, lin
     torch.cuda.empty_cache()
+    bridge.disable_activation_checkpointing()
     return out
 
 

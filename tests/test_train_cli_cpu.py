@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 def test_shipped_configs_have_the_keys_the_native_cli_reads():
-    for name in ("full_lora_config.yaml", "bench_r16_config.yaml", "minimal_lora_config.yaml"):
+    for name in ("full_lora_config.yaml", "bench_r16_config.yaml", "minimal_lora_config.yaml", "crack_detection_config.yaml"):
         cfg = yaml.safe_load((ROOT / "configs" / name).read_text())
         assert {"rank", "alpha", "dropout", "target_modules"} <= set(cfg["lora"])
         assert {"learning_rate", "weight_decay", "data_dir", "batch_size", "num_epochs"} <= set(cfg["training"])

@@ -444,6 +444,50 @@ def test_cuda_graph_mode_matches_eager_over_several_steps():
         assert torch.equal(e, a(img)[0])
 
 
+def test_cuda_graph_mode_with_adapter_dropout_redraws_the_mask_every_replay():
+    """lora.dropout > 0 (what full_lora_config.yaml sets) under ViT(cuda_graphs=True): the per-step seed is a device word the
+    kernels add to the captured base seed.  With the same injected seed an eager twin gives identical outputs and gradients
+    step by step; without injection two replays differ (fresh masks) while the graphs are reused."""
+    from sam3_lora_b200.lora_layers import LoRAConfig, apply_lora_to_model, get_lora_parameters
+    from sam3_lora_b200.vit import ViT
+
+    def make(graphs):
+        torch.manual_seed(3)
+        m = ViT(img_size=224, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4.75, window_size=8, global_att_blocks=(1,),
+                pretrain_img_size=112, drop_path_rate=0.0, max_batch=2, cuda_graphs=graphs)
+        apply_lora_to_model(m, LoRAConfig(rank=4, alpha=8, dropout=0.2, target_modules=["q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2"]))
+        for p in get_lora_parameters(m):
+            torch.nn.init.normal_(p, std=0.05)
+        return m.cuda().train()
+
+    a, b = make(False), make(True)
+    b.load_state_dict(a.state_dict())
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(4):
+        img = torch.randn(2, 3, 224, 224, device="cuda", generator=gen)
+        gout = torch.randn(2, 128, 16, 16, device="cuda", generator=gen)
+        outs, grads = [], []
+        for m in (a, b):
+            m.lora_dropout_seed_override = 1000 + 17 * step
+            for p in get_lora_parameters(m):
+                p.grad = None
+            o = m(img)[0]
+            (o * gout).sum().backward()
+            outs.append(o.detach().clone())
+            grads.append([p.grad.detach().clone() for p in get_lora_parameters(m)])
+        assert torch.equal(outs[0], outs[1]), step
+        for ga, gb in zip(*grads):
+            assert rel_l2(gb.cpu(), ga.cpu()) < 1e-5, step
+    st = b._graph_state
+    assert st is not None and st.g_fwd is not None and st.g_bwd is not None
+    fwd_graph = st.g_fwd
+    b.lora_dropout_seed_override = None                 # free-running: every replay draws its own mask on the device
+    o1 = b(img)[0].detach().clone()
+    o2 = b(img)[0].detach().clone()
+    assert not torch.equal(o1, o2) and b._graph_state.g_fwd is fwd_graph
+    assert rel_l2(o2, o1) < 0.2                          # same network, different adapter-dropout masks
+
+
 def test_adapter_dropout_mask_definition_matches_oracle_hash():
     """sam3b_dropout_rows16 (csrc/rng.cuh) == oracle.dropout_scale_mask for the same (seed, rows, cols, p)."""
     from sam3_lora_b200 import _lib as L

@@ -136,6 +136,53 @@ def time_trunk_gpu(batch: int, steps: int, warmup: int, rank: int = 16, device="
     return ms, what
 
 
+def time_trunk_native(rank: int, batch: int, dropout: float, steps: int, warmup: int, device="cuda",
+                      targets=("q_proj", "k_proj", "v_proj", "out_proj", "fc1", "fc2")):
+    """The native trunk step through the public API (vit.ViT(cuda_graphs=True) + lora_layers + autograd + fused torch AdamW,
+    batch resident on the device) for another shipped configuration: rank / per-GPU batch / adapter dropout.  Returns
+    (ms per step, trainable parameter count)."""
+    import torch
+
+    from sam3_lora_b200.lora_layers import LoRAConfig, apply_lora_to_model, get_lora_parameters
+    from sam3_lora_b200.vit import ViT
+
+    torch.manual_seed(0)
+    model = ViT(max_batch=batch, cuda_graphs=True)
+    with contextlib.redirect_stdout(sys.stderr):
+        apply_lora_to_model(model, LoRAConfig(rank=rank, alpha=2 * rank, dropout=dropout, target_modules=list(targets)))
+    for p in get_lora_parameters(model):
+        if p.shape[0] == rank:
+            torch.nn.init.normal_(p, std=0.02)
+    model = model.to(device).train()
+    img = torch.randn(batch, 3, 1008, 1008, device=device)
+    gout = torch.randn(batch, 1024, 72, 72, device=device) * 1e-3
+    model(img)                                    # builds the engine, flattens the adapters
+    params = model.lora_parameters()
+    opt = torch.optim.AdamW(params, lr=5e-5, weight_decay=0.01, fused=True)
+
+    def step():
+        f = model(img)[0]
+        loss = (f * gout).sum()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+
+    for _ in range(max(3, warmup)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n = sum(p.numel() for p in params)
+    del model, opt, params
+    torch.cuda.empty_cache()
+    return ms, n
+
+
 def time_whole_model(native: bool, batch: int, steps: int, warmup: int, rank: int = 16, device="cuda", stochastic: bool = True):
     """One SAM3 training step of the detector (forward, matcher, Sam3LossWrapper objective, backward, AdamW) at `batch`
     images, synthetic COCO-shaped batch resident on the device.  native=False: the reference model untouched, its SciPy
@@ -148,6 +195,8 @@ def time_whole_model(native: bool, batch: int, steps: int, warmup: int, rank: in
     torch.manual_seed(0)
     model = sam3_bridge.build_reference_model("cpu", seed=0)
     info = {}
+    if not native:
+        sam3_bridge.restore_activation_checkpointing()       # the reference arm runs the reference's own recompute wrapper
     if native:
         from sam3_lora_b200.lora_layers import LoRAConfig, apply_lora_to_model
 
