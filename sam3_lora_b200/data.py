@@ -224,6 +224,8 @@ class Prefetcher:
                  transform: Optional[Callable] = None):
         self.iterable, self.depth, self.transform = iterable, max(1, int(depth)), transform
         self.device = torch.device(device) if device is not None else None
+        if self.device is not None and self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.stream = torch.cuda.Stream(self.device) if self.device is not None and self.device.type == "cuda" else None
 
     def __len__(self):
