@@ -274,6 +274,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
   const uint32_t tm_K = tmem_base + 384, tm_V = tmem_base + 416, tm_P = tmem_base + 448, tm_dS = tmem_base + 480;
@@ -558,6 +560,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dQ = tmem_base + 256;
   const uint32_t tm_Q = tmem_base + 320, tm_dO = tmem_base + 352, tm_dS = tmem_base + 384;
@@ -781,9 +785,9 @@ static int launch_bwd(const AttnArgs& a, const BwdParams& pk, const BwdParams& p
   const int items_k = pk.tiles * a.nseg * a.heads, items_q = pq.tiles * a.nseg * a.heads;
   const int grid_k = persist ? std::min(items_k, num_sms()) : items_k;
   const int grid_q = persist ? std::min(items_q, num_sms()) : items_q;
-  attn_bwd_dkdv_kernel<DT, GEN><<<grid_k, NTHREADS, DKDV_SMEM, stream>>>(tmQ64, tmdO64, pk);
+  SAM3B_CHECK_CUDA(launch_pdl(attn_bwd_dkdv_kernel<DT, GEN>, dim3(grid_k), dim3(NTHREADS), DKDV_SMEM, stream, tmQ64, tmdO64, pk));
   SAM3B_LAUNCHED();
-  attn_bwd_dq_kernel<DT, GEN><<<grid_q, NTHREADS, DQ_SMEM, stream>>>(tmKV64, pq);
+  SAM3B_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel<DT, GEN>, dim3(grid_q), dim3(NTHREADS), DQ_SMEM, stream, tmKV64, pq));
   SAM3B_LAUNCHED();
   return 0;
 }

@@ -124,6 +124,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();                             // after the TMEM allocation (see ptx.cuh)
+  pdl_wait();                                // q / k / v come from the previous kernel
   const uint32_t tmem_S = *tmem_slot;        // S_j (fp32, 64 columns); P_j (16-bit) is written back over columns [0,32)
   const uint32_t tmem_O = tmem_S + BKV;
 
@@ -357,7 +359,7 @@ static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const Fwd
     SAM3B_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr_set = true;
   }
-  attn_fwd_kernel<DT, GEN><<<grid, 192, FWD_SMEM, stream>>>(tmQ, tmKV, p);
+  SAM3B_CHECK_CUDA(launch_pdl(attn_fwd_kernel<DT, GEN>, grid, dim3(192), FWD_SMEM, stream, tmQ, tmKV, p));
   SAM3B_LAUNCHED();
   return 0;
 }

@@ -1,3 +1,4 @@
+#include <cstdlib>
 #include "common.h"
 
 #include <cstdarg>
@@ -87,6 +88,14 @@ int num_sms() {
     return v;
   }();
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("SAM3B_PDL");      // opt-in: round-2 A/B on B200 measured it 0.5-1 % SLOWER per step
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
 }
 
 }  // namespace sam3b

@@ -48,4 +48,27 @@ int num_sms();
 void count_launch();
 long long launch_count();
 
+// Programmatic dependent launch (PDL): the kernel may start (run its prologue: barrier init, TMEM allocation, descriptor
+// prefetch) while the previous kernel on the stream is still draining; it calls griddepcontrol.wait (ptx.cuh pdl_wait) before
+// touching global memory, so the visible order is unchanged.  Works under stream capture (programmatic graph edges).
+// Off by default: SAM3B_PDL=1 in the environment turns the attribute on.  Round-2 A/B inside one gpurun call (bench.py, 10
+// steps, alternating): 153.8 / 152.4 ms with it, 151.7 / 151.8 ms without - the step is paced by the 1000 W power cap, not by
+// launch gaps, and early-resident dependent CTAs do not help (profiles/r02_pdl_ab.txt).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace sam3b

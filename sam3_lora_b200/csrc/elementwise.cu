@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   constexpr int D = 128 * VPT;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * D);
   float4 v[VPT];
@@ -91,6 +93,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const uint16_t* __restrict_
   constexpr int D = 128 * VPT;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (row >= rows) return;
   const float mu = mean[row], rs = rstd[row];
   const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * D);
@@ -496,8 +500,8 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
   const int blocks = (rows + 7) / 8;
   return dispatch_vpt(D, [&](auto vpt) -> int {
     constexpr int V = decltype(vpt)::value;
-    if (dtype == 0) ln_fwd_kernel<V, 0><<<blocks, 256, 0, s>>>(x, gamma, beta, eps, rows, (uint16_t*)y16, ldy, mean, rstd);
-    else ln_fwd_kernel<V, 1><<<blocks, 256, 0, s>>>(x, gamma, beta, eps, rows, (uint16_t*)y16, ldy, mean, rstd);
+    if (dtype == 0) SAM3B_CHECK_CUDA(launch_pdl(ln_fwd_kernel<V, 0>, dim3(blocks), dim3(256), 0, s, x, gamma, beta, eps, rows, (uint16_t*)y16, ldy, mean, rstd));
+    else SAM3B_CHECK_CUDA(launch_pdl(ln_fwd_kernel<V, 1>, dim3(blocks), dim3(256), 0, s, x, gamma, beta, eps, rows, (uint16_t*)y16, ldy, mean, rstd));
     SAM3B_LAUNCHED();
     return 0;
   });
@@ -511,9 +515,9 @@ int layernorm_bwd(const void* dy16, int64_t lddy, const float* x, const float* m
   return dispatch_vpt(D, [&](auto vpt) -> int {
     constexpr int V = decltype(vpt)::value;
     if (dtype == 0)
-      ln_bwd_kernel<V, 0><<<blocks, 256, 0, s>>>((const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16, row_scale, rows_per_scale);
+      SAM3B_CHECK_CUDA(launch_pdl(ln_bwd_kernel<V, 0>, dim3(blocks), dim3(256), 0, s, (const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16, row_scale, rows_per_scale));
     else
-      ln_bwd_kernel<V, 1><<<blocks, 256, 0, s>>>((const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16, row_scale, rows_per_scale);
+      SAM3B_CHECK_CUDA(launch_pdl(ln_bwd_kernel<V, 1>, dim3(blocks), dim3(256), 0, s, (const uint16_t*)dy16, lddy, x, mean, rstd, gamma, dres, rows, dx, (uint16_t*)dx16, lddx16, row_scale, rows_per_scale));
     SAM3B_LAUNCHED();
     return 0;
   });

@@ -86,6 +86,9 @@ VitEngine::VitEngine(const VitConfig& cfg) : cfg_(cfg) {
       // skip 3 of the last k-block's 4 MMAs, but makes the operand row pitch (in + R) * 2 B a non-multiple of 128 B: every TMA
       // box row then straddles two lines; measured 0.5 % SLOWER per step (round-1 A/B), so 64 stays.
       s->R = s->n_ad > 0 ? round_up(s->n_ad * r, 64) : 0;
+      // ... but the K loop only has to cover the live columns: the operand pitch keeps the 64-wide pad (alignment), K stops at
+      // the last 16-wide MMA step that holds adapter columns (the rest of the pad is zero in both operands)
+      s->Rlive = s->n_ad > 0 ? round_up(s->n_ad * r, 16) : 0;
       s->ldw = s->in + s->R;
       s->ldwt = s->out + s->R;
       Rmax_ = std::max(Rmax_, s->R);
@@ -460,7 +463,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
     if ((rc = site_down(w.qkv, a.xn1, ld_xn1, M, i, 0, s))) return rc;
     {
       GemmArgs g;
-      g.M = M; g.N = 3 * D_; g.K = (int)ld_xn1;
+      g.M = M; g.N = 3 * D_; g.K = D_ + w.qkv.Rlive;
       g.A = a.xn1; g.lda = ld_xn1; g.B = w.qkv.w_ext; g.ldb = w.qkv.ldw;
       g.dtype = dt; g.epilogue = EPI_QKV_ROPE; g.bias = w.qkv.bias;
       g.rope = w.global ? rope_glob_ : rope_win_; g.rope_period = w.global ? T_ : ws2; g.rope_cols = 2 * D_;
@@ -479,7 +482,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
     if ((rc = site_down(w.proj, a.O, ld_O, M, i, 1, s))) return rc;
     {
       GemmArgs g;
-      g.M = M; g.N = D_; g.K = (int)ld_O;
+      g.M = M; g.N = D_; g.K = D_ + w.proj.Rlive;
       g.A = a.O; g.lda = ld_O; g.B = w.proj.w_ext; g.ldb = w.proj.ldw;
       g.dtype = dt; g.epilogue = EPI_RESIDUAL_F32; g.bias = w.proj.bias;
       g.residual = x_[i]; g.ldres = D_;
@@ -492,7 +495,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
     if ((rc = site_down(w.fc1, a.xn2, ld_xn2, M, i, 2, s))) return rc;
     {
       GemmArgs g;
-      g.M = M; g.N = Dm_; g.K = (int)ld_xn2;
+      g.M = M; g.N = Dm_; g.K = D_ + w.fc1.Rlive;
       g.A = a.xn2; g.lda = ld_xn2; g.B = w.fc1.w_ext; g.ldb = w.fc1.ldw;
       g.dtype = dt; g.epilogue = EPI_GELU; g.bias = w.fc1.bias;
       g.C = a.h; g.ldc = Dm_; g.C2 = a.g; g.ldc2 = ld_g;
@@ -501,7 +504,7 @@ int VitEngine::forward(const float* img, int batch, const float* lora_flat, floa
     if ((rc = site_down(w.fc2, a.g, ld_g, M, i, 3, s))) return rc;
     {
       GemmArgs g;
-      g.M = M; g.N = D_; g.K = (int)ld_g;
+      g.M = M; g.N = D_; g.K = Dm_ + w.fc2.Rlive;
       g.A = a.g; g.lda = ld_g; g.B = w.fc2.w_ext; g.ldb = w.fc2.ldw;
       g.dtype = dt; g.epilogue = EPI_RESIDUAL_F32; g.bias = w.fc2.bias;
       g.residual = a.x_mid; g.ldres = D_;
@@ -573,14 +576,14 @@ int VitEngine::backward_segment(const float* gout_nchw, float* grad_flat, int bl
                         const void* aux, int64_t ldaux, int block, int site) -> int {
     const bool masked = fwd_drop_p_ > 0.f && st.R > 0;
     GemmArgs a;
-    a.M = M; a.N = st.in; a.K = masked ? st.out : st.out + st.R;
+    a.M = M; a.N = st.in; a.K = masked ? st.out : st.out + st.Rlive;
     a.A = dy; a.lda = ld; a.B = st.wt_ext; a.ldb = st.ldwt;
     a.dtype = dt; a.epilogue = epi; a.C = dst; a.ldc = lddst; a.aux = aux; a.ldaux = ldaux;
     int r2 = gemm_launch(a, s);
     if (r2 || !masked) return r2;
     // adapter part under dropout: dst += mask/(1-p) * (dT'' . A^T) [* gelu'(h)], K = R
     GemmArgs b;
-    b.M = M; b.N = st.in; b.K = st.R;
+    b.M = M; b.N = st.in; b.K = st.Rlive;
     b.A = dy + st.out; b.lda = ld; b.B = st.wt_ext + st.out; b.ldb = st.ldwt;
     b.dtype = dt; b.epilogue = EPI_ADDMASK16; b.C = dst; b.ldc = lddst;
     if (epi == EPI_DGELU) { b.aux = aux; b.ldaux = ldaux; }
@@ -615,7 +618,7 @@ int VitEngine::backward_segment(const float* gout_nchw, float* grad_flat, int bl
       const int L = w.global ? T_ : ws2;
       SAM3B_CHECK_CUDA(cudaMemsetAsync(delta_, 0, (size_t)g_stat_rows(M, L) * H_ * sizeof(float), s));
       GemmArgs g;
-      g.M = M; g.N = w.proj.in; g.K = w.proj.out + w.proj.R;
+      g.M = M; g.N = w.proj.in; g.K = w.proj.out + w.proj.Rlive;
       g.A = dx16_; g.lda = ld_dx16; g.B = w.proj.wt_ext; g.ldb = w.proj.ldwt;
       g.dtype = dt; g.epilogue = EPI_STORE16_DELTA; g.C = dO16_; g.ldc = D_;
       g.aux = a.O; g.ldaux = ld_O;

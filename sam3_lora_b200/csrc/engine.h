@@ -67,7 +67,7 @@ class VitEngine {
 
  private:
   struct Site {
-    int in = 0, out = 0, n_ad = 0, R = 0;
+    int in = 0, out = 0, n_ad = 0, R = 0, Rlive = 0;   // R: K-extension pitch (64-padded); Rlive: columns the K loop must cover
     int off[3] = {0, 0, 0}, len[3] = {0, 0, 0};
     int entry[3] = {-1, -1, -1};
     uint16_t *w_ext = nullptr, *wt_ext = nullptr, *down_T = nullptr, *up_pack = nullptr;

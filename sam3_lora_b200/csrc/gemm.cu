@@ -316,6 +316,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -486,6 +488,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
@@ -582,7 +586,7 @@ static int launch_pair(const GemmArgs& a, const GemmParams& p, cudaStream_t stre
   int clusters = (a.max_ctas > 0 ? a.max_ctas : num_sms()) / 2;
   if (clusters > total) clusters = total;
   if (clusters < 1) clusters = 1;
-  kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  SAM3B_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM, stream, tmA, tmB, p));
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -804,7 +808,7 @@ static int launch_one(const GemmArgs& a, const GemmParams& p, cudaStream_t strea
   const int total = m_tiles * n_tiles * p.splitk;
   int ctas = a.max_ctas > 0 ? a.max_ctas : num_sms();
   if (ctas > total) ctas = total;
-  kern<<<ctas, 384, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  SAM3B_CHECK_CUDA(launch_pdl(kern, dim3(ctas), dim3(384), Cfg::SMEM, stream, tmA, tmB, p));
   SAM3B_LAUNCHED();
   return 0;
 }

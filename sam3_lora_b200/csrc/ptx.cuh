@@ -331,6 +331,11 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// Programmatic dependent launch (see common.h launch_pdl).  pdl_trigger: this CTA no longer objects to the NEXT kernel's CTAs
+// being scheduled (call it after the TMEM allocation: a dependent CTA that grabbed the columns first would dead-lock this
+// one).  pdl_wait: block until the PREVIOUS kernel has completed and its writes are visible; no-ops without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
                : "memory");
