@@ -93,7 +93,8 @@ def test_sam3_objective_refuses_random_base_weights(tmp_path, monkeypatch):
     """adapters trained on a random base are useless - no checkpoint means an error unless explicitly allowed."""
     import sam3_lora_b200.train_native as T
 
-    cfg = yaml.safe_load((ROOT / "configs" / "minimal_lora_config.yaml").read_text())
+    cfg = yaml.safe_load((ROOT / "configs" / "full_lora_config.yaml").read_text())       # ships without allow_random_init
+    assert not (cfg.get("model") or {}).get("allow_random_init", False)
     cfg["output"]["output_dir"] = str(tmp_path / "o")
     p = tmp_path / "c.yaml"
     p.write_text(yaml.safe_dump(cfg))
