@@ -465,6 +465,31 @@ def run_native(args):
                            "achieved": 2.5 * fl / ms_b / 1e9, "unit": "TFLOP/s (5 algorithmic matmuls)", "floor_ms": 2 * mufu_s * 1e3,
                            "frac_of_floor": 2 * mufu_s * 1e3 / ms_b})
             del qkv, O, lse2, dO, delta, dqkv
+        # row a7: the nn.MultiheadAttention core at the DETR sizes (E=256, 8 heads of 32 run as zero-padded 64-wide heads):
+        # encoder self-attention over the 5184 image tokens with and without attention dropout, decoder image cross-attention
+        # 401 x 5184 with the additive fp32 box-RPB bias
+        H7, Ep = 8, 8 * 64
+        for name, Lq, Lk, pd, with_bias in (("encoder self-attn 5184x5184, dropout 0.1", 5184, 5184, 0.1, False),
+                                            ("encoder self-attn 5184x5184, dropout 0", 5184, 5184, 0.0, False),
+                                            ("decoder image cross-attn 401x5184 + box-RPB bias", 401, 5184, 0.0, True)):
+            q7 = (torch.randn(B * Lq, Ep, device=dev) * 0.5).to(dt)
+            kv7 = (torch.randn(B * Lk, 2 * Ep, device=dev) * 0.5).to(dt)
+            O7 = torch.empty(B * Lq, Ep, device=dev, dtype=dt)
+            Ls7 = (Lq + 63) // 64 * 64
+            lse7 = torch.zeros(H7, B * Ls7, device=dev)
+            bias7 = torch.randn(B * H7, Lq, Lk, device=dev) if with_bias else None
+            d7 = L.mha_desc(q7, kv7, B, Lq, Lk, H7, 32 ** -0.5, O7, lse7, bias=bias7, drop_p=pd, drop_seed=123)
+            ms_f = timed(lambda: L.mha_fwd(d7))
+            dO7 = (torch.randn(B * Lq, Ep, device=dev) * 0.5).to(dt)
+            delta7 = torch.zeros_like(lse7)
+            dq7 = torch.empty_like(q7)
+            dkv7 = torch.empty_like(kv7)
+            ms_b = timed(lambda: L.mha_bwd(d7, dO7, delta7, dq7, dkv7))
+            fl7 = 4.0 * B * H7 * Lq * Lk * 32            # algorithmic: head_dim 32
+            others.append({"kernel": "row a7 MHA core (attn_fwd / attn_bwd GEN), %s, B=%d" % (name, B), "ms_fwd": ms_f, "ms_bwd": ms_b,
+                           "ms": ms_f + ms_b, "bound": "mufu-ex2 + per-score dropout hash" if pd > 0 else "mufu-ex2",
+                           "achieved": 3.5 * fl7 / (ms_f + ms_b) / 1e9, "unit": "TFLOP/s (algorithmic, head_dim 32; executed at 64)"})
+            del q7, kv7, O7, lse7, bias7, dO7, delta7, dq7, dkv7
         # row a8's dominant kernel: the im2col-free 3x3 convolution at the 288x288 level (256 -> 256 channels)
         from sam3_lora_b200 import conv_ops as CO  # noqa: PLC0415
         xc = (torch.randn(B, 288, 288, 256, device=dev) * 0.5).to(dt)

@@ -55,6 +55,24 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
   return 0;
 }
 
+int make_tmap_store16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  auto fn = encode_fn();
+  if (!fn) return fail(-3, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-1, "TMA store base pointer %p not 16-byte aligned", ptr);
+  if ((ld * 2) % 16 != 0) return fail(-1, "TMA store row pitch %llu B not a multiple of 16", (unsigned long long)(ld * 2));
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(-3, "cuTensorMapEncodeTiled (store) failed with %d (rows=%llu cols=%llu ld=%llu)", (int)r, (unsigned long long)rows,
+                (unsigned long long)cols, (unsigned long long)ld);
+  return 0;
+}
+
 int make_tmap_nhwc(CUtensorMap* out, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_c,
                    uint32_t box_w, uint32_t box_h) {
   auto fn = encode_fn();

@@ -38,6 +38,11 @@ const char* last_error_message();
 int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, int elem_bytes = 2);
 
+// Store-side map for the GEMM epilogues: 16-bit [rows][cols] tensor, box [32 rows][32 cols] = 32 x 64 bytes, SWIZZLE_64B —
+// the layout of the epilogue's staging tile (stage.cuh: 16-byte chunk index XOR (row >> 1) & 3), so a tile written by the
+// epilogue lanes is stored with one cp.async.bulk.tensor; rows / columns past the tensor's extent are clipped by the TMA unit.
+int make_tmap_store16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld);
+
 // 4-D map over a channels-last 16-bit tensor [B][H][W][C]: dimensions (C, W, H, B), box (box_c, box_w, box_h, 1),
 // SWIZZLE_128B (box_c * 2 bytes == 128).  Coordinates may be negative / past the end: those elements read as zero,
 // which is exactly the zero padding of a convolution.

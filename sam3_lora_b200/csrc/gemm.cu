@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -44,6 +45,7 @@ struct GemmParams {
   int c_trans;
   uint32_t mn_lbo, mn_sbo;
   float* delta; int delta_Lq, delta_Lq_stat; int64_t delta_stride;
+  int tma_store;   // gemm2_kernel: bit 0 = C, bit 1 = C2 go out through TMA stores (16-bit outputs)
 };
 
 
@@ -67,6 +69,38 @@ struct GemmCfg {
 // one instruction covers 8 rows x 64 contiguous bytes (16 full sectors).  The 16-byte chunks are XOR-swizzled by
 // (row >> 1) & 3, which is conflict-free for both access patterns.
 // ---------------------------------------------------------------------------------------
+
+// Per-warp state of the TMA-store epilogue (gemm2_kernel).  The staging tile IS the TMA box (32 rows x 64 bytes, 64-byte
+// swizzle = stage.cuh's chunk XOR), so after the lanes have written their rows one elected lane issues ONE
+// cp.async.bulk.tensor per 32 x 32 block instead of the warp reading the tile back and issuing 8-row global stores: per 2 KB
+// block the LSU data pipe sees 16 wavefronts (the st.shared) instead of ~60 (st.shared + ld.shared + 8-row STGs at half-line
+// efficiency).  That pipe is shared with the tensor core's operand reads: ncu on the GELU GEMM showed 58 % LSU + 31 % tensor
+// wavefronts = a saturated pipe with the tensor pipe only 66 % active (profiles/r02_ncu_gemm2_gelu.txt).
+// tmc == nullptr: staged global stores (gemm_kernel, conv3x3_kernel, and fp32 outputs everywhere).
+struct TmaStore {
+  const CUtensorMap* tmc = nullptr;    // map of C
+  const CUtensorMap* tmc2 = nullptr;   // map of C2 (GELU epilogue)
+  uint8_t* tile0 = nullptr;            // two adjacent 512-byte-aligned staging tiles of this warp: tile0, tile0 + STG_BYTES
+  int flip = 0;
+};
+
+// this lane's 32 values -> 16-bit -> one TMA store of rows [row0, row0+32) x columns [col, col+32).  OUTSTANDING = how many
+// earlier stores of this warp may still be reading their tile (1 when the caller alternates tiles, 0 when it reuses one).
+template <int DT, int OUTSTANDING>
+__device__ __forceinline__ void store16x32_tma(uint8_t* tile, int lane, const CUtensorMap* tm, int row0, int col, const float (&v)[32]) {
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = pack2<DT>(v[2 * i], v[2 * i + 1]);
+  if (lane == 0) tma_store_wait_read<OUTSTANDING>();
+  __syncwarp();
+  stage_put_row(tile, lane, w);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tm, tile, col, row0);
+    tma_store_commit();
+  }
+}
 
 // this lane's 32 values -> 16-bit -> rows [row0, row0+32) x columns [col, col+32) of `base` (leading dimension ld elements)
 template <int DT>
@@ -113,7 +147,25 @@ __device__ __forceinline__ void addload32x32(uint8_t* stg, int lane, const float
 // One epilogue step: the warp owns output rows [row0, row0+32) (this lane: row0 + lane), columns [col, col+32).
 // Executed by all 32 lanes (the staged stores are cooperative); rows >= M are clipped by rows_valid.
 template <int EPI, int DT, bool FULL>
-__device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t* stg, int lane, int row0, int col, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t* stg, int lane, int row0, int col, const uint32_t (&r)[32],
+                                                    TmaStore* ts) {
+  // 16-bit output block: TMA store when the kernel provides maps, staged global stores otherwise
+  auto put16 = [&](void* base, int64_t ld, const CUtensorMap* tm, const float (&vals)[32], int which, int rows_valid_, int nvalid_) {
+    if (ts != nullptr && tm != nullptr) {
+      if (which < 0) {            // single-output epilogue without an aux load: alternate the two tiles
+        store16x32_tma<DT, 1>(ts->tile0 + ts->flip * STG_BYTES, lane, tm, row0, col, vals);
+        ts->flip ^= 1;
+      } else if (which < 2) {     // two-output epilogue: output `which` owns tile `which`
+        store16x32_tma<DT, 1>(ts->tile0 + which * STG_BYTES, lane, tm, row0, col, vals);
+      } else {                    // epilogue whose aux load uses tile 0: stores go through tile 1 only
+        store16x32_tma<DT, 0>(ts->tile0 + STG_BYTES, lane, tm, row0, col, vals);
+      }
+    } else {
+      store16x32<DT>(stg, lane, base, ld, row0, col, vals, rows_valid_, nvalid_);
+    }
+  };
+  const CUtensorMap* tmc = ts != nullptr ? ts->tmc : nullptr;
+  const CUtensorMap* tmc2 = ts != nullptr ? ts->tmc2 : nullptr;
   const int nvalid = FULL ? 32 : min(32, p.N - col);  // multiple of 8 (host-checked); FULL folds every column predicate
   const int row = row0 + lane;
   const int rows_valid = min(32, p.M - row0);
@@ -141,7 +193,7 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
   }
 
   if constexpr (EPI == EPI_STORE16) {
-    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
+    put16(p.C, p.ldc, tmc, v, -1, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_STORE32) {
     if (p.row_scale != nullptr) {  // device-resident scale (1/grad-scale of the neck / mask-head backward, conv_ops.py)
       const float sc = __ldg(p.row_scale + min(row, p.M - 1) / p.rows_per_scale);
@@ -166,7 +218,7 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
         v[q * 4 + 3] = a1 * cs.w + b1 * cs.z;
       }
     }
-    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
+    put16(p.C, p.ldc, tmc, v, -1, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_RESIDUAL_F32) {
     if (p.row_scale != nullptr) {  // stochastic depth: per-image 0 or 1/keep on the branch (vitdet.py:610-611)
       const float sc = __ldg(p.row_scale + min(row, p.M - 1) / p.rows_per_scale);
@@ -190,10 +242,10 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
     }
     store32x32(stg, lane, reinterpret_cast<float*>(p.C), p.ldc, row0, col, v, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_GELU) {
-    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
+    put16(p.C, p.ldc, tmc, v, 0, rows_valid, nvalid);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-    store16x32<DT>(stg, lane, p.C2, p.ldc2, row0, col, v, rows_valid, nvalid);
+    put16(p.C2, p.ldc2, tmc2, v, 1, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_DGELU) {
     // h (the fc1 pre-activation, 16-bit) through the staging tile: 64 bytes per row
     stage_fill(stg, lane, reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row0 * p.ldaux + col),
@@ -208,7 +260,7 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
       v[2 * i] *= dgelu_erf(hh.x);
       v[2 * i + 1] *= dgelu_erf(hh.y);
     }
-    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
+    put16(p.C, p.ldc, tmc, v, 2, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_STORE16_DELTA) {
     // O (the forward attention output, 16-bit) through the staging tile, like h in the DGELU epilogue
     stage_fill(stg, lane, reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row0 * p.ldaux + col),
@@ -227,7 +279,7 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
     }
     // two 32-column chunks per 64-wide head: two commutative adds per (row, head) -> bitwise deterministic
     if (row_ok) atomicAdd(p.delta + (int64_t)(col >> 6) * p.delta_stride + (int64_t)(row / p.delta_Lq) * p.delta_Lq_stat + row % p.delta_Lq, dsum);
-    store16x32<DT>(stg, lane, p.C, p.ldc, row0, col, v, rows_valid, nvalid);
+    put16(p.C, p.ldc, tmc, v, 2, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_ADDMASK16) {
     if (row_ok) {
     // data-gradient of the adapter branch under dropout: dx += mask/(1-p) * (dT''.A^T) [* gelu'(h) on the fc2 site]
@@ -268,10 +320,11 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
 }
 
 template <int EPI, int DT>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* stg, int lane, int row0, int col, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* stg, int lane, int row0, int col, const uint32_t (&r)[32],
+                                               TmaStore* ts = nullptr) {
   if (row0 >= p.M || col >= p.N) return;   // warp-uniform
-  if (col + 32 <= p.N) epilogue_chunk_impl<EPI, DT, true>(p, stg, lane, row0, col, r);
-  else epilogue_chunk_impl<EPI, DT, false>(p, stg, lane, row0, col, r);
+  if (col + 32 <= p.N) epilogue_chunk_impl<EPI, DT, true>(p, stg, lane, row0, col, r, ts);
+  else epilogue_chunk_impl<EPI, DT, false>(p, stg, lane, row0, col, r, ts);
 }
 
 template <int BN, int EPI, int DT, bool A_MN, bool B_MN>
@@ -440,12 +493,17 @@ struct Gemm2Cfg {
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 256 + EPI_WARPS * STG_BYTES + 1024;
+  // barriers (256 B, padded to 512 so the staging tiles are 512-byte aligned: the TMA 64-byte swizzle is a function of the
+  // absolute shared-memory address bits [7:8]) + two staging tiles per epilogue warp
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 2 * EPI_WARPS * STG_BYTES + 1024;
+  static_assert(SMEM <= 232448, "gemm2_kernel: shared memory over the 227 KB limit");
 };
 
 template <int EPI, int DT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+             const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
@@ -459,7 +517,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = bars + 2 * STAGES;   // in both CTAs (multicast commit)
   uint64_t* tempty = tfull + 2;          // used in the leader CTA only, one arrival per epilogue warp of both CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + 256 + ((threadIdx.x >> 5) >= 4 ? ((threadIdx.x >> 5) - 4) * STG_BYTES : 0);
+  uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES + ((threadIdx.x >> 5) >= 4 ? ((threadIdx.x >> 5) - 4) * 2 * STG_BYTES : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -474,6 +532,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store & 1) tma_prefetch_desc(&tmC);
+    if (p.tma_store & 2) tma_prefetch_desc(&tmC2);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -538,6 +598,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
     const int ew = warp & 3;
     const int c_lo = ((warp - 4) >> 2) * Cfg::COLS_PER_WARP;
+    TmaStore ts_state;
+    ts_state.tmc = (p.tma_store & 1) ? &tmC : nullptr;
+    ts_state.tmc2 = (p.tma_store & 2) ? &tmC2 : nullptr;
+    ts_state.tile0 = stg;
+    TmaStore* ts = p.tma_store ? &ts_state : nullptr;
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = cluster_id; w < total_work; w += n_clusters) {
       const int n_blk = w % n_tiles, m_pair = w / n_tiles;
@@ -550,7 +615,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t r[32];
         tmem_ld_x32(t_row + c, r);
         tmem_ld_wait();
-        epilogue_chunk<EPI, DT>(p, stg, lane, row0, n_blk * BN + c, r);
+        epilogue_chunk<EPI, DT>(p, stg, lane, row0, n_blk * BN + c, r, ts);
       }
       tc_fence_before();
       __syncwarp();
@@ -562,6 +627,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (ts != nullptr && lane == 0) tma_store_wait_all();   // this lane's bulk stores: sources read and global writes performed
   }
 
   tc_fence_before();
@@ -572,10 +638,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 template <int EPI, int DT>
 static int launch_pair(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmC2;
   int rc;
   if ((rc = make_tmap_2d(&tmA, a.A, a.M, a.K, a.lda, 128, 64))) return rc;
   if ((rc = make_tmap_2d(&tmB, a.B, a.N, a.K, a.ldb, 128, 64))) return rc;
+  // 16-bit outputs leave through TMA stores (SAM3B_TMA_STORE=0: staged global stores, for A/B measurements)
+  static const bool tma_store_on = [] { const char* e = getenv("SAM3B_TMA_STORE"); return !(e && e[0] == '0'); }();
+  GemmParams pp = p;
+  pp.tma_store = 0;
+  constexpr bool kStore16 = EPI == EPI_STORE16 || EPI == EPI_QKV_ROPE || EPI == EPI_GELU || EPI == EPI_DGELU || EPI == EPI_STORE16_DELTA;
+  std::memset(&tmC, 0, sizeof(tmC));
+  std::memset(&tmC2, 0, sizeof(tmC2));
+  if (kStore16 && tma_store_on && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * 2) % 16 == 0) {
+    if ((rc = make_tmap_store16(&tmC, a.C, a.M, a.N, a.ldc))) return rc;
+    pp.tma_store |= 1;
+    if (EPI == EPI_GELU) {
+      if ((reinterpret_cast<uintptr_t>(a.C2) & 15) == 0 && (a.ldc2 * 2) % 16 == 0) {
+        if ((rc = make_tmap_store16(&tmC2, a.C2, a.M, a.N, a.ldc2))) return rc;
+        pp.tma_store |= 2;
+      } else {
+        pp.tma_store = 0;      // both outputs or neither: the two-tile scheme assumes both stores are TMA stores
+      }
+    }
+  }
   auto kern = gemm2_kernel<EPI, DT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -586,7 +671,7 @@ static int launch_pair(const GemmArgs& a, const GemmParams& p, cudaStream_t stre
   int clusters = (a.max_ctas > 0 ? a.max_ctas : num_sms()) / 2;
   if (clusters > total) clusters = total;
   if (clusters < 1) clusters = 1;
-  SAM3B_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM, stream, tmA, tmB, p));
+  SAM3B_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM, stream, tmA, tmB, tmC, tmC2, pp));
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -855,6 +940,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.rope = reinterpret_cast<const float2*>(a.rope); p.rope_period = a.rope_period > 0 ? a.rope_period : 1;
   p.rope_cols = a.rope_cols;
   p.alpha = a.alpha; p.c_trans = a.c_trans;
+  p.tma_store = 0;
   p.delta = a.delta; p.delta_Lq = a.delta_Lq > 0 ? a.delta_Lq : 1; p.delta_Lq_stat = a.delta_Lq_stat; p.delta_stride = a.delta_stride;
   p.mn_lbo = a.dbg_lbo > 0 ? a.dbg_lbo : 8192;
   p.mn_sbo = a.dbg_sbo > 0 ? a.dbg_sbo : 1024;

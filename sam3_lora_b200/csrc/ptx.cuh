@@ -331,6 +331,21 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA store (shared -> global through a tensor map; out-of-range rows / columns are clipped by the TMA unit).
+// Generic-proxy writes to the source tile must be made visible to the async proxy first (fence_proxy_async_smem by every
+// writing thread, then a warp / CTA sync, then ONE thread issues the copy).  Bulk groups are per issuing thread.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source (the tile may then be rewritten)
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// wait until all of this thread's bulk groups have completed (global writes performed)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Programmatic dependent launch (see common.h launch_pdl).  pdl_trigger: this CTA no longer objects to the NEXT kernel's CTAs
 // being scheduled (call it after the TMEM allocation: a dependent CTA that grabbed the columns first would dead-lock this
 // one).  pdl_wait: block until the PREVIOUS kernel has completed and its writes are visible; no-ops without the attribute.

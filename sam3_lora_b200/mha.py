@@ -83,6 +83,121 @@ class _AttnCoreFn(torch.autograd.Function):
                 None, None, None, None, None, None, None, None, None)
 
 
+class _FusedMHAFn(torch.autograd.Function):
+    """The whole adapter-free module in 16-bit between the kernels: input cast(s) -> projection GEMMs that write the padded-
+    head q | k | v layout the attention kernel reads (q and k share one GEMM when they share their input: the encoder's
+    q = k = x + pos; k and v likewise in cross attention) -> flash attention -> output projection (fp32 out).  Backward:
+    out-proj dgrad -> attention backward -> projection dgrads (one GEMM for a shared input).  No fp32 round trip of q, k, v,
+    O or their gradients; frozen weights need no weight gradients."""
+
+    @staticmethod
+    def forward(ctx, q_in, k_in, v_in, same_qk: bool, same_kv: bool, packs, nseg: int, Lq: int, Lk: int, heads: int, scale: float,
+                bias, kpm, drop_p: float, seed: int):
+        from .ops import _OPERAND_DTYPE as dt  # noqa: PLC0415
+
+        Ep = heads * 64
+        dev = q_in.device
+        E = q_in.shape[1]
+        Mq, Mk = nseg * Lq, nseg * Lk
+        W = packs[dt]
+
+        def cast(x):
+            y = torch.empty(x.shape[0], E, device=dev, dtype=dt)
+            L.cast_rows_16(x.float().contiguous(), y)
+            return y
+
+        xq = cast(q_in)
+        xk = xq if same_qk else cast(k_in)
+        xv = xk if same_kv else (xq if (v_in is q_in) else cast(v_in))
+        self_attn = same_qk and Mq == Mk
+        if self_attn:
+            buf = torch.empty(Mq, 3 * Ep, device=dev, dtype=dt)            # q | k | v
+            if same_kv:                                                     # q = k = v = x (the text tower's resblocks)
+                L.gemm(xq, W["Wqkv"], buf, epilogue=L.EPI_STORE16, bias=W["bqkv"])
+            else:
+                L.gemm(xq, W["Wqk"], buf[:, :2 * Ep], epilogue=L.EPI_STORE16, bias=W["bqk"])
+                L.gemm(xv, W["Wv"], buf[:, 2 * Ep:], epilogue=L.EPI_STORE16, bias=W["bv"])
+            q16, kv16, qc, kc, vc = buf, buf, 0, Ep, 2 * Ep
+        else:
+            q16 = torch.empty(Mq, Ep, device=dev, dtype=dt)
+            kv16 = torch.empty(Mk, 2 * Ep, device=dev, dtype=dt)
+            L.gemm(xq, W["Wq"], q16, epilogue=L.EPI_STORE16, bias=W["bq"])
+            if same_kv:
+                L.gemm(xk, W["Wkv"], kv16, epilogue=L.EPI_STORE16, bias=W["bkv"])
+            else:
+                L.gemm(xk, W["Wk"], kv16[:, :Ep], epilogue=L.EPI_STORE16, bias=W["bk"])
+                L.gemm(xv, W["Wv"], kv16[:, Ep:], epilogue=L.EPI_STORE16, bias=W["bv"])
+            qc, kc, vc = 0, 0, Ep
+        O16 = torch.empty(Mq, Ep, device=dev, dtype=dt)
+        Ls = (Lq + 63) // 64 * 64
+        lse2 = torch.zeros(heads, nseg * Ls, device=dev, dtype=torch.float32)
+        d = L.mha_desc(q16, kv16, nseg, Lq, Lk, heads, scale, O16, lse2, q_col0=qc, k_col0=kc, v_col0=vc, bias=bias, kpm=kpm,
+                       drop_p=drop_p, drop_seed=seed)
+        L.mha_fwd(d)
+        out = torch.empty(Mq, E, device=dev, dtype=torch.float32)
+        L.gemm(O16, W["Wo"], out, epilogue=L.EPI_STORE32, bias=W["bo"])
+        ctx.save_for_backward(q16, kv16, O16, lse2, bias if bias is not None else torch.empty(0, device=dev),
+                              kpm if kpm is not None else torch.empty(0, device=dev, dtype=torch.uint8))
+        ctx.meta = (nseg, Lq, Lk, heads, scale, bias is not None, kpm is not None, drop_p, seed, q_in.dtype, same_qk, same_kv,
+                    self_attn, (qc, kc, vc), E, v_in is q_in)
+        ctx.W = W
+        return out.to(q_in.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        q16, kv16, O16, lse2, bias, kpm = ctx.saved_tensors
+        (nseg, Lq, Lk, heads, scale, has_bias, has_kpm, drop_p, seed, xdt, same_qk, same_kv, self_attn, (qc, kc, vc), E,
+         v_is_q) = ctx.meta
+        W = ctx.W
+        Ep = heads * 64
+        dev = g.device
+        dt = q16.dtype
+        Mq, Mk = nseg * Lq, nseg * Lk
+        g32 = g.reshape(Mq, E).float().contiguous()
+        sc = L.grad_scale(g32, target=min(L.GRAD_SCALE_TARGET, max(1.0, 32768.0 / Lq)))      # see _AttnCoreFn.backward
+        dy16 = torch.empty(Mq, E, device=dev, dtype=dt)
+        L.cast_rows_16(g32, dy16, sc[0:1])
+        dO16 = torch.empty(Mq, Ep, device=dev, dtype=dt)
+        L.gemm(dy16, W["WoT"], dO16, epilogue=L.EPI_STORE16)
+        delta = torch.zeros_like(lse2)
+        d = L.mha_desc(q16, kv16, nseg, Lq, Lk, heads, scale, O16, lse2, q_col0=qc, k_col0=kc, v_col0=vc,
+                       bias=bias if has_bias else None, kpm=kpm if has_kpm else None, drop_p=drop_p, drop_seed=seed)
+        inv = sc[1:2]
+        need_q, need_k, need_v = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+
+        def dgrad(dy, Wt, rows):
+            dx = torch.empty(rows, E, device=dev, dtype=torch.float32)
+            L.gemm(dy, Wt, dx, epilogue=L.EPI_STORE32, row_scale=inv, rows_per_scale=L.ALL_ROWS)
+            return dx.to(xdt)
+
+        if self_attn:
+            dbuf = torch.empty(Mq, 3 * Ep, device=dev, dtype=dt)          # dq | dk | dv
+            L.mha_bwd(d, dO16, delta, dbuf, dbuf, dk_col0=Ep, dv_col0=2 * Ep)
+            if same_kv:
+                return ((dgrad(dbuf, W["WqkvT"], Mq) if need_q else None), None, None) + (None,) * 12
+            gq = dgrad(dbuf[:, :2 * Ep], W["WqkT"], Mq) if (need_q or need_k) else None      # [dq | dk] . [Wq ; Wk]
+            gv = dgrad(dbuf[:, 2 * Ep:], W["WvT"], Mk) if (need_v or (v_is_q and need_q)) else None
+            if v_is_q and gv is not None:
+                gq = gv if gq is None else gq + gv
+                gv = None
+            return (gq, None, gv) + (None,) * 12
+        dq16 = torch.empty(Mq, Ep, device=dev, dtype=dt)
+        dkv16 = torch.empty(Mk, 2 * Ep, device=dev, dtype=dt)
+        L.mha_bwd(d, dO16, delta, dq16, dkv16)
+        gq = dgrad(dq16, W["WqT"], Mq) if need_q else None
+        gk = gv = None
+        if same_kv:
+            if need_k or need_v:
+                gk = dgrad(dkv16, W["WkvT"], Mk)                          # [dk | dv] . [Wk ; Wv]
+        else:
+            gk = dgrad(dkv16[:, :Ep], W["WkT"], Mk) if need_k else None
+            gv = dgrad(dkv16[:, Ep:], W["WvT"], Mk) if need_v else None
+        if same_qk and gk is not None:                                    # cross-shaped call with q is k (Mq == Mk handled above)
+            gq = gk if gq is None else gq + gk
+            gk = None
+        return (gq, gk, gv) + (None,) * 12
+
+
 class MultiheadAttention(nn.Module):
     lora_out_proj_ok = True   # apply_lora_to_model may wrap out_proj in a LoRALinear (see lora_layers.py)
 
@@ -104,6 +219,8 @@ class MultiheadAttention(nn.Module):
             nn.init.zeros_(self.out_proj.bias)
         self.dropout_seed_override: Optional[int] = None
         self._packed = None
+        self._packed16: Dict = {}
+        self.fused = True          # adapter-free calls take the 16-bit fused path (_FusedMHAFn); False = the composed path
         self._seed_state: Optional[int] = None
 
     def _next_seed(self) -> int:
@@ -148,8 +265,48 @@ class MultiheadAttention(nn.Module):
         Wo = torch.zeros(E, Ep, device=W.device, dtype=torch.float32)
         Wo[:, idx] = ow.detach().float()
         out["Wo"] = Wo
+        out["bo"] = None if self._out_linear.bias is None else self._out_linear.bias.detach().float().contiguous()
         self._packed = (key, out)
+        self._packed16 = {}
         return out
+
+    def _pack16(self, dt):
+        """16-bit operand copies of the frozen projections for the fused path: forward [N, K] and transposed (dgrad) forms,
+        single and concatenated (q|k, k|v share one GEMM when they share their input).  Built once per weight version."""
+        pk = self._pack()
+        hit = self._packed16.get(dt)
+        if hit is not None:
+            return {dt: hit}
+        c = lambda t: t.to(dt).contiguous()                                                   # noqa: E731
+        Wq, Wk, Wv, Wo = pk["Wq"], pk["Wk"], pk["Wv"], pk["Wo"]
+        w = {"Wq": c(Wq), "Wk": c(Wk), "Wv": c(Wv), "Wqk": c(torch.cat([Wq, Wk], 0)), "Wkv": c(torch.cat([Wk, Wv], 0)), "Wo": c(Wo),
+             "WqT": c(Wq.t()), "WkT": c(Wk.t()), "WvT": c(Wv.t()), "WqkT": c(torch.cat([Wq, Wk], 0).t()),
+             "WkvT": c(torch.cat([Wk, Wv], 0).t()), "WoT": c(Wo.t()),
+             "Wqkv": c(torch.cat([Wq, Wk, Wv], 0)), "WqkvT": c(torch.cat([Wq, Wk, Wv], 0).t()),
+             "bqkv": torch.cat([pk["bq"], pk["bk"], pk["bv"]]).contiguous(),
+             "bq": pk["bq"], "bk": pk["bk"], "bv": pk["bv"], "bqk": torch.cat([pk["bq"], pk["bk"]]).contiguous(),
+             "bkv": torch.cat([pk["bk"], pk["bv"]]).contiguous(), "bo": pk["bo"]}
+        self._packed16[dt] = w
+        return {dt: w}
+
+    @staticmethod
+    def _masks(attn_mask, key_padding_mask, B, H, Lq, Lk, device):
+        """torch's attn_mask (bool = masked, or additive float; [Lq, Lk] or [B*H, Lq, Lk]) and key_padding_mask -> the kernel's
+        additive fp32 bias [B*H, Lq, Lk] and uint8 key mask [B, Lk]."""
+        bias = None
+        if attn_mask is not None:
+            if attn_mask.dtype == torch.bool:
+                bias = torch.zeros(attn_mask.shape, device=device, dtype=torch.float32).masked_fill_(attn_mask, float("-inf"))
+            else:
+                bias = attn_mask.float()
+            if bias.dim() == 2:
+                bias = bias.expand(B * H, Lq, Lk)
+            bias = bias.contiguous()
+        kpm = None
+        if key_padding_mask is not None:
+            kpm = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask.dtype == torch.bool \
+                else (key_padding_mask != 0).to(torch.uint8).contiguous()
+        return bias, kpm
 
     def forward(self, query, key, value, key_padding_mask=None, need_weights: bool = False, attn_mask=None, **_unused):
         if need_weights:
@@ -166,9 +323,26 @@ class MultiheadAttention(nn.Module):
             Lq, B, _ = query.shape
             Lk = key.shape[0]
             q_in, k_in, v_in = query.transpose(0, 1), key.transpose(0, 1), value.transpose(0, 1)
-        q_in, k_in, v_in = (t.reshape(-1, E) for t in (q_in.contiguous(), k_in.contiguous(), v_in.contiguous()))
+        same_qk, same_kv, v_is_q = key is query, value is key, value is query
+        q_in = q_in.contiguous().reshape(-1, E)
+        k_in = q_in if same_qk else k_in.contiguous().reshape(-1, E)
+        v_in = k_in if same_kv else (q_in if v_is_q else v_in.contiguous().reshape(-1, E))
         pk = self._pack()
         idx = pk["idx"]
+        if self.fused and all(self._adapter(n) is None for n in ("q_proj", "k_proj", "v_proj", "out_proj")):
+            from .ops import _OPERAND_DTYPE  # noqa: PLC0415
+
+            bias, kpm = self._masks(attn_mask, key_padding_mask, B, H, Lq, Lk, query.device)
+            p_drop = self.dropout if self.training else 0.0
+            seed = self.dropout_seed_override
+            if seed is None:
+                seed = self._next_seed() if p_drop > 0 else 0
+            out = _FusedMHAFn.apply(q_in, k_in, v_in, same_qk, same_kv, self._pack16(_OPERAND_DTYPE), B, Lq, Lk, H,
+                                    1.0 / math.sqrt(hd), bias, kpm, p_drop, seed)
+            out = out.reshape(B, Lq, E)
+            if not self.batch_first:
+                out = out.transpose(0, 1)
+            return out.to(query.dtype), None
 
         def proj(x, n):
             lo = self._adapter(n + "_proj")
@@ -179,19 +353,7 @@ class MultiheadAttention(nn.Module):
             return lora_linear(x, pk["W" + n], pk["b" + n], lo.lora_A, Bp, lo.scaling, dropout_p=p)
 
         q, k, v = proj(q_in, "q"), proj(k_in, "k"), proj(v_in, "v")
-        bias = None
-        if attn_mask is not None:
-            if attn_mask.dtype == torch.bool:
-                bias = torch.zeros(attn_mask.shape, device=query.device, dtype=torch.float32).masked_fill_(attn_mask, float("-inf"))
-            else:
-                bias = attn_mask.float()
-            if bias.dim() == 2:
-                bias = bias.expand(B * H, Lq, Lk)
-            bias = bias.contiguous()
-        kpm = None
-        if key_padding_mask is not None:
-            kpm = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask.dtype == torch.bool \
-                else (key_padding_mask != 0).to(torch.uint8).contiguous()
+        bias, kpm = self._masks(attn_mask, key_padding_mask, B, H, Lq, Lk, query.device)
         p_drop = self.dropout if self.training else 0.0
         seed = self.dropout_seed_override
         if seed is None:

@@ -176,8 +176,10 @@ def training_loss(model: nn.Module, batch, matcher, loss_wrapper) -> Tuple[torch
     from sam3.model.model_misc import SAM3Output  # noqa: PLC0415
     from sam3.train.loss.loss_fns import CORE_LOSS_KEY  # noqa: PLC0415
 
-    outputs_list = model(batch)
+    with torch.cuda.nvtx.range("sam3b.step.forward"):
+        outputs_list = model(batch)
     find_targets = [model.back_convert(t) for t in batch.find_targets]
+    torch.cuda.nvtx.range_push("sam3b.step.matcher+loss")
     with SAM3Output.iteration_mode(outputs_list, iter_mode=SAM3Output.IterMode.ALL_STEPS_PER_STAGE) as outputs_iter:
         for stage_outputs, stage_targets in zip(outputs_iter, find_targets):
             for outputs in stage_outputs:
@@ -185,6 +187,7 @@ def training_loss(model: nn.Module, batch, matcher, loss_wrapper) -> Tuple[torch
                 for aux in outputs.get("aux_outputs", ()):
                     aux["indices"] = matcher(aux, stage_targets)
     loss_dict = loss_wrapper(outputs_list, find_targets)
+    torch.cuda.nvtx.range_pop()
     return loss_dict[CORE_LOSS_KEY], loss_dict
 
 

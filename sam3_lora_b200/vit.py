@@ -101,6 +101,11 @@ class _TrunkFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, images, vit: "ViT", need_grad: bool, *lora_params):
+        with torch.cuda.nvtx.range("sam3b.trunk.forward"):           # NVTX ranges: visible in nsys / ncu --nvtx timelines
+            return _TrunkFn._forward(ctx, images, vit, need_grad, *lora_params)
+
+    @staticmethod
+    def _forward(ctx, images, vit: "ViT", need_grad: bool, *lora_params):
         eng = vit._engine_for(images)
         B = images.shape[0]
         eng.bind(images.device, B, training=need_grad or vit._keep_training_workspace)
@@ -160,6 +165,11 @@ class _TrunkFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        with torch.cuda.nvtx.range("sam3b.trunk.backward"):
+            return _TrunkFn._backward(ctx, gout)
+
+    @staticmethod
+    def _backward(ctx, gout):
         vit: "ViT" = ctx.vit
         eng = vit._engine
         if ctx.generation != vit._fwd_generation:
