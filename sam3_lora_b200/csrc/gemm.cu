@@ -45,7 +45,7 @@ struct GemmParams {
   int c_trans;
   uint32_t mn_lbo, mn_sbo;
   float* delta; int delta_Lq, delta_Lq_stat; int64_t delta_stride;
-  int tma_store;   // gemm2_kernel: bit 0 = C, bit 1 = C2 go out through TMA stores (16-bit outputs)
+  int tma_store;   // gemm2_kernel: bit 0 = C, bit 1 = C2 go out through TMA stores (16-bit outputs); bit 2 = aux comes in by TMA
 };
 
 
@@ -82,7 +82,43 @@ struct TmaStore {
   const CUtensorMap* tmc2 = nullptr;   // map of C2 (GELU epilogue)
   uint8_t* tile0 = nullptr;            // two adjacent 512-byte-aligned staging tiles of this warp: tile0, tile0 + STG_BYTES
   int flip = 0;
+  // aux operand (h of the GELU' epilogue, O of the delta epilogue) fetched by TMA into tile0, one block ahead: the kernel
+  // issues the tile's first block before it waits for the accumulator, each block issues its successor once it has read tile0
+  const CUtensorMap* tmaux = nullptr;
+  uint64_t* auxbar = nullptr;          // this warp's mbarrier
+  uint32_t aux_phase = 0;
+  int aux_next_col = -1;               // column of the next block of this warp in this tile, -1: none
 };
+
+// Request the next aux block into tile0.  Call it only AFTER every lane has CONSUMED the words it read from tile0 (the
+// ld.shared data has then arrived; a __syncwarp right after issuing the loads does not order them against the async-proxy
+// write of the TMA unit: a full-size run showed run-to-run gradient differences of 3 % with the request placed there).
+__device__ __forceinline__ void aux_prefetch_next(TmaStore* ts, int lane, int row0);
+__device__ __forceinline__ void aux_issue(TmaStore* ts, int lane, int col, int row0) {
+  if (lane == 0) {
+    mbar_arrive_expect_tx(ts->auxbar, STG_BYTES);
+    tma_load_2d(ts->tile0, ts->tmaux, ts->auxbar, col, row0);
+  }
+}
+__device__ __forceinline__ void aux_prefetch_next(TmaStore* ts, int lane, int row0) {
+  if (ts == nullptr || ts->tmaux == nullptr) return;
+  __syncwarp();
+  if (ts->aux_next_col >= 0) aux_issue(ts, lane, ts->aux_next_col, row0);
+}
+// 32 x 32 block of the 16-bit aux operand -> this lane's row (16 packed words); falls back to the staged global loads
+template <typename FillFn>
+__device__ __forceinline__ void aux_get_row(TmaStore* ts, uint8_t* stg, int lane, int row0, uint32_t (&w)[16], FillFn fill) {
+  if (ts != nullptr && ts->tmaux != nullptr) {
+    mbar_wait(ts->auxbar, ts->aux_phase, 500);
+    ts->aux_phase ^= 1;
+    stage_get_row(ts->tile0, lane, w);
+  } else {
+    fill();
+    __syncwarp();
+    stage_get_row(stg, lane, w);
+    __syncwarp();
+  }
+}
 
 // this lane's 32 values -> 16-bit -> one TMA store of rows [row0, row0+32) x columns [col, col+32).  OUTSTANDING = how many
 // earlier stores of this warp may still be reading their tile (1 when the caller alternates tiles, 0 when it reuses one).
@@ -248,27 +284,26 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
     put16(p.C2, p.ldc2, tmc2, v, 1, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_DGELU) {
     // h (the fc1 pre-activation, 16-bit) through the staging tile: 64 bytes per row
-    stage_fill(stg, lane, reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row0 * p.ldaux + col),
-               p.ldaux * 2, rows_valid, nvalid * 2);
-    __syncwarp();
     uint32_t hw[16];
-    stage_get_row(stg, lane, hw);
-    __syncwarp();
+    aux_get_row(ts, stg, lane, row0, hw, [&] {
+      stage_fill(stg, lane, reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row0 * p.ldaux + col),
+                 p.ldaux * 2, rows_valid, nvalid * 2);
+    });
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float2 hh = unpack2<DT>(hw[i]);
       v[2 * i] *= dgelu_erf(hh.x);
       v[2 * i + 1] *= dgelu_erf(hh.y);
     }
+    aux_prefetch_next(ts, lane, row0);
     put16(p.C, p.ldc, tmc, v, 2, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_STORE16_DELTA) {
     // O (the forward attention output, 16-bit) through the staging tile, like h in the DGELU epilogue
-    stage_fill(stg, lane, reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row0 * p.ldaux + col),
-               p.ldaux * 2, rows_valid, nvalid * 2);
-    __syncwarp();
     uint32_t ow[16];
-    stage_get_row(stg, lane, ow);
-    __syncwarp();
+    aux_get_row(ts, stg, lane, row0, ow, [&] {
+      stage_fill(stg, lane, reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint16_t*>(p.aux) + (int64_t)row0 * p.ldaux + col),
+                 p.ldaux * 2, rows_valid, nvalid * 2);
+    });
     float dsum = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -279,6 +314,7 @@ __device__ __forceinline__ void epilogue_chunk_impl(const GemmParams& p, uint8_t
     }
     // two 32-column chunks per 64-wide head: two commutative adds per (row, head) -> bitwise deterministic
     if (row_ok) atomicAdd(p.delta + (int64_t)(col >> 6) * p.delta_stride + (int64_t)(row / p.delta_Lq) * p.delta_Lq_stat + row % p.delta_Lq, dsum);
+    aux_prefetch_next(ts, lane, row0);
     put16(p.C, p.ldc, tmc, v, 2, rows_valid, nvalid);
   } else if constexpr (EPI == EPI_ADDMASK16) {
     if (row_ok) {
@@ -517,6 +553,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = bars + 2 * STAGES;   // in both CTAs (multicast commit)
   uint64_t* tempty = tfull + 2;          // used in the leader CTA only, one arrival per epilogue warp of both CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* auxbar = bars + 32;          // byte 256 of the barrier block: one mbarrier per epilogue warp (aux TMA loads)
   uint8_t* stg = reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES + ((threadIdx.x >> 5) >= 4 ? ((threadIdx.x >> 5) - 4) * 2 * STG_BYTES : 0);
 
   const int warp = threadIdx.x >> 5;
@@ -533,11 +570,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (p.tma_store & 1) tma_prefetch_desc(&tmC);
-    if (p.tma_store & 2) tma_prefetch_desc(&tmC2);
+    if (p.tma_store & 6) tma_prefetch_desc(&tmC2);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * Cfg::EPI_WARPS); }
+    for (int i = 0; i < Cfg::EPI_WARPS; ++i) mbar_init(&auxbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -602,19 +640,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     ts_state.tmc = (p.tma_store & 1) ? &tmC : nullptr;
     ts_state.tmc2 = (p.tma_store & 2) ? &tmC2 : nullptr;
     ts_state.tile0 = stg;
+    ts_state.tmaux = (p.tma_store & 4) ? &tmC2 : nullptr;
+    ts_state.auxbar = &auxbar[warp - 4];
     TmaStore* ts = p.tma_store ? &ts_state : nullptr;
+    const bool aux_tma = (p.tma_store & 4) != 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = cluster_id; w < total_work; w += n_clusters) {
       const int n_blk = w % n_tiles, m_pair = w / n_tiles;
+      const int row0 = m_pair * 256 + (int)rank * 128 + ew * 32;
+      // the aux block of this warp's first chunk is requested before the accumulator wait (same skip rule as epilogue_chunk)
+      if (aux_tma && row0 < p.M && n_blk * BN + c_lo < p.N) aux_issue(ts, lane, n_blk * BN + c_lo, row0);
       mbar_wait(&tfull[acc], acc_phase, 400 + acc);
       tc_fence_after();
-      const int row0 = m_pair * 256 + (int)rank * 128 + ew * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = c_lo; c < c_lo + Cfg::COLS_PER_WARP; c += 32) {
         uint32_t r[32];
         tmem_ld_x32(t_row + c, r);
         tmem_ld_wait();
+        if (aux_tma) {
+          const int nc = n_blk * BN + c + 32;
+          ts_state.aux_next_col = (c + 32 < c_lo + Cfg::COLS_PER_WARP && nc < p.N) ? nc : -1;
+        }
         epilogue_chunk<EPI, DT>(p, stg, lane, row0, n_blk * BN + c, r, ts);
       }
       tc_fence_before();
@@ -660,6 +707,14 @@ static int launch_pair(const GemmArgs& a, const GemmParams& p, cudaStream_t stre
         pp.tma_store = 0;      // both outputs or neither: the two-tile scheme assumes both stores are TMA stores
       }
     }
+  }
+  // GELU' / delta epilogues: the 16-bit aux operand comes in through TMA loads into the warp's first staging tile (the C2 map
+  // slot is free in these epilogues); needs the TMA stores on (tile 1 is then the only store tile)
+  constexpr bool kAux = EPI == EPI_DGELU || EPI == EPI_STORE16_DELTA;
+  static const bool tma_aux_on = [] { const char* e = getenv("SAM3B_TMA_AUX"); return !(e && e[0] == '0'); }();
+  if (kAux && tma_aux_on && (pp.tma_store & 1) && a.aux != nullptr && (reinterpret_cast<uintptr_t>(a.aux) & 15) == 0 && (a.ldaux * 2) % 16 == 0) {
+    if ((rc = make_tmap_store16(&tmC2, a.aux, a.M, a.N, a.ldaux))) return rc;
+    pp.tma_store |= 4;
   }
   auto kern = gemm2_kernel<EPI, DT>;
   static bool attr_set = false;
