@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SAM3B_ABI_VERSION 2
+#define SAM3B_ABI_VERSION 3
 
 /* operand formats of the tensor-core path (fp32 accumulate always) */
 #define SAM3B_F16 0
@@ -113,7 +113,14 @@ typedef struct sam3b_attn_desc {
   void* dq; int64_t lddq; int32_t dq_col0;
   void* dkv; int64_t lddkv; int32_t dk_col0, dv_col0;
   const float* rope; int32_t rope_period; /* optional inverse RoPE on dq, dk (ViT); NULL otherwise */
+  /* ABI v3, optional: keep-bits of the dropout mask precomputed by sam3b_attention_dropout_bits (same hash, so the same mask
+   * as the inline evaluation); the three kernels then read one word per 32 scores instead of hashing each score three times */
+  const uint32_t* drop_bits; const uint32_t* drop_bitsT;
 } sam3b_attn_desc;
+/* bits[(bh*Lq + q)*(Lk/32) + k/32] bit (k & 31) and bitsT[(bh*Lk + k)*(Lq/32) + q/32] bit (q & 31) = 1 where probability
+ * (q, k) of problem bh = seg*heads + head is kept.  Lq, Lk multiples of 32; n_bh = nseg*heads. */
+int sam3b_attention_dropout_bits(int32_t n_bh, int32_t Lq, int32_t Lk, float p, uint32_t seed, uint32_t* bits, uint32_t* bitsT,
+                                 void* stream);
 int sam3b_attention_fwd(const sam3b_attn_desc* d, void* stream);
 int sam3b_attention_bwd(const sam3b_attn_desc* d, void* stream);
 

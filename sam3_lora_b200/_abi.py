@@ -24,6 +24,7 @@ class AttnDesc(C.Structure):
         ("dq", vp), ("lddq", i64), ("dq_col0", i32),
         ("dkv", vp), ("lddkv", i64), ("dk_col0", i32), ("dv_col0", i32),
         ("rope", vp), ("rope_period", i32),
+        ("drop_bits", vp), ("drop_bitsT", vp),
     ]
 
 
@@ -53,6 +54,7 @@ SIGNATURES: dict[str, tuple] = {
     "sam3b_cast_rows_16_scaled": (C.c_int, [vp, i32, i32, vp, i64, i32, vp, vp]),
     "sam3b_attention_fwd": (C.c_int, [C.POINTER(AttnDesc), vp]),
     "sam3b_attention_bwd": (C.c_int, [C.POINTER(AttnDesc), vp]),
+    "sam3b_attention_dropout_bits": (C.c_int, [i32, i32, i32, f32, C.c_uint32, vp, vp, vp]),
     "sam3b_patch_gather": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, i64, i32, i32, vp]),
     "sam3b_tokens_to_nchw": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
     "sam3b_nchw_to_tokens": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, i64, i32, vp]),

@@ -229,6 +229,28 @@ def mha_desc(q, kv, nseg, Lq, Lk, heads, scale, O, lse2, *, q_col0=0, k_col0=0, 
     return d
 
 
+# Above this many scores per (segment, head) the attention-dropout mask is generated once per call as keep-bits (both
+# orientations) and read by the three kernels, instead of each of them hashing every score.
+DROPOUT_BITS_MIN_SCORES = 1 << 16
+
+
+def attention_dropout_bits(d):
+    """Fills d.drop_bits / d.drop_bitsT when the call qualifies (dropout on, Lq and Lk multiples of 32, large problem);
+    returns the two int32 tensors (keep them alive until the backward has run) or None."""
+    import torch  # noqa: PLC0415
+
+    if d.drop_p <= 0.0 or d.Lq % 32 or d.Lk % 32 or d.Lq * d.Lk < DROPOUT_BITS_MIN_SCORES:
+        return None
+    n_bh = d.nseg * d.heads
+    dev = torch.device("cuda", torch.cuda.current_device())
+    bits = torch.empty(n_bh * d.Lq * (d.Lk // 32), device=dev, dtype=torch.int32)
+    bitsT = torch.empty(n_bh * d.Lk * (d.Lq // 32), device=dev, dtype=torch.int32)
+    check(load().sam3b_attention_dropout_bits(n_bh, d.Lq, d.Lk, float(d.drop_p), int(d.drop_seed) & 0xFFFFFFFF, ptr(bits), ptr(bitsT),
+                                              current_stream()))
+    d.drop_bits, d.drop_bitsT = ptr(bits), ptr(bitsT)
+    return bits, bitsT
+
+
 def mha_fwd(d):
     check(load().sam3b_attention_fwd(C.byref(d), current_stream()))
 

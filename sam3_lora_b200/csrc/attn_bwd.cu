@@ -73,7 +73,7 @@ struct BwdParams {
   float scale_log2, scale;
   // GEN only
   const float* bias; const uint8_t* kpm;
-  float drop_inv_keep; uint32_t drop_thr, drop_seed;
+  float drop_inv_keep; uint32_t drop_thr, drop_seed; const uint32_t* drop_bits; const uint32_t* drop_bitsT; int bias_vec4;
 };
 
 __device__ __forceinline__ uint32_t attn_drop_base(uint32_t seed, uint32_t bh) { return lowbias32(seed ^ (bh * 0x9E3779B1u + 0x85EBCA6Bu)); }
@@ -401,6 +401,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
         if (p.bias != nullptr) bias_col = p.bias + (int64_t)(seg * p.H + head) * p.Lq * p.Lk + k_in_seg;
         drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
       }
+      const uint32_t* bitsT_row = nullptr;   // precomputed keep-bits of this key column (one word per 32 queries)
+      if constexpr (GEN) {
+        if (p.drop_bitsT != nullptr) bitsT_row = p.drop_bitsT + ((int64_t)(seg * p.H + head) * p.Lk + k_in_seg) * (p.Lq >> 5);
+      }
       for (int j = (B0 + g) & 1; j < n_blocks; j += 2) {   // blocks whose running index has parity g
         const int jb = B0 + j, st = jb % NSI;
         const float* stat = sStat + st * (2 * BI);
@@ -419,7 +423,16 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
         mbar_arrive(&sdp_free[g]);  // S^T/dP^T buffer g may be overwritten by block j+2
         if (tr) TRACE(64 + j * 8 + 2);
         float pv[32], dsv[32];
-        if (!GEN && q_valid == BI) {
+        // predicate-free path: full block, no additive mask, no key padding, and dropout either off or available as keep-bits
+        // (the encoder's 5184 x 5184 self-attention with dropout 0.1 takes it; the general path below costs ~5x more)
+        bool fast = q_valid == BI;
+        if constexpr (GEN) fast = fast && bias_col == nullptr && p.kpm == nullptr && (p.drop_thr == 0 || bitsT_row != nullptr);
+        if (fast) {
+          uint32_t mwf = 0xffffffffu;
+          float inv_keep = 1.f;
+          if constexpr (GEN) {
+            if (p.drop_thr != 0) { mwf = __ldg(bitsT_row + ((j * BI + cc) >> 5)); inv_keep = p.drop_inv_keep; }
+          }
           const float4* l4 = reinterpret_cast<const float4*>(stat + cc);
           const float4* d4 = reinterpret_cast<const float4*>(stat + BI + cc);
 #pragma unroll
@@ -430,11 +443,21 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
             for (int e = 0; e < 4; ++e) {
               const int i = q * 4 + e;
               const float pe = ex2_approx(fmaf(__uint_as_float(s[i]), c, -lv[e]));
-              pv[i] = pe;
-              dsv[i] = pe * (__uint_as_float(d[i]) - dv[e]);
+              if constexpr (GEN) {
+                const float ks = ((mwf >> i) & 1u) ? inv_keep : 0.f;
+                pv[i] = pe * ks;
+                dsv[i] = pe * fmaf(__uint_as_float(d[i]), ks, -dv[e]);
+              } else {
+                pv[i] = pe;
+                dsv[i] = pe * (__uint_as_float(d[i]) - dv[e]);
+              }
             }
           }
         } else {
+          uint32_t mw = 0u;
+          if constexpr (GEN) {
+            if (bitsT_row != nullptr) { const int wi_ = (j * BI + cc) >> 5; mw = wi_ < (p.Lq >> 5) ? __ldg(bitsT_row + wi_) : 0u; }
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int qi = j * BI + cc + i;   // query index inside the segment
@@ -445,8 +468,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
             if constexpr (GEN) {
               if (bias_col != nullptr && !dead) t = fmaf(__ldg(bias_col + (int64_t)qi * p.Lk), 1.4426950408889634f, t);
               dead = dead || key_masked;
-              if (p.drop_thr != 0)
-                keep_scale = attn_drop_keep(drop_base, (uint32_t)qi, (uint32_t)k_in_seg, (uint32_t)p.Lk, p.drop_thr) ? p.drop_inv_keep : 0.f;
+              if (p.drop_thr != 0) {
+                if (bitsT_row != nullptr) keep_scale = ((mw >> i) & 1u) ? p.drop_inv_keep : 0.f;
+                else keep_scale = attn_drop_keep(drop_base, (uint32_t)qi, (uint32_t)k_in_seg, (uint32_t)p.Lk, p.drop_thr) ? p.drop_inv_keep : 0.f;
+              }
             }
             const float pe = dead ? 0.f : ex2_approx(t - stat[cc + i]);
             pv[i] = pe * keep_scale;                                   // dropped probabilities feed dV
@@ -675,6 +700,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
         if (p.kpm != nullptr) kpm_row = p.kpm + (int64_t)seg * p.Lk;
         drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
       }
+      const uint32_t* bits_row = nullptr;
+      if constexpr (GEN) {
+        if (p.drop_bits != nullptr) bits_row = p.drop_bits + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * (p.Lk >> 5);
+      }
       for (int j = (B0 + g) & 1; j < n_blocks; j += 2) {
         const int jb = B0 + j;
         const int k_valid = min(BI, p.Lk - j * BI);
@@ -687,27 +716,53 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
         tc_fence_before();
         mbar_arrive(&sdp_free[g]);
         float dsv[32];
-        if (!GEN && k_valid == BI) {
+        bool fast = k_valid == BI;
+        if constexpr (GEN) fast = fast && bias_row == nullptr && kpm_row == nullptr && (p.drop_thr == 0 || bits_row != nullptr);
+        if (fast) {
+          uint32_t mwf = 0xffffffffu;
+          float inv_keep = 1.f;
+          if constexpr (GEN) {
+            if (p.drop_thr != 0) { mwf = __ldg(bits_row + ((j * BI + cc) >> 5)); inv_keep = p.drop_inv_keep; }
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float pe = ex2_approx(fmaf(__uint_as_float(s[i]), c, -lse));
-            dsv[i] = pe * (__uint_as_float(d[i]) - dlt);
+            if constexpr (GEN) dsv[i] = pe * fmaf(__uint_as_float(d[i]), ((mwf >> i) & 1u) ? inv_keep : 0.f, -dlt);
+            else dsv[i] = pe * (__uint_as_float(d[i]) - dlt);
           }
         } else {
+          uint32_t mw = 0u;
+          bool bias_pre = false;        // the row's 32 bias values come in through 16-byte loads (see attn_fwd.cu)
+          if constexpr (GEN) {
+            if (bits_row != nullptr) { const int wi_ = (j * BI + cc) >> 5; mw = wi_ < (p.Lk >> 5) ? __ldg(bits_row + wi_) : 0u; }
+            bias_pre = bias_row != nullptr && p.bias_vec4 && cc + 32 <= k_valid;
+          }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int ki = j * BI + cc + i;   // key index inside the segment
-            float t = __uint_as_float(s[i]) * c;
-            float dp = __uint_as_float(d[i]);
-            bool dead = (cc + i) >= k_valid;
+          for (int q4 = 0; q4 < 8; ++q4) {
+            float4 b4v = make_float4(0.f, 0.f, 0.f, 0.f);
             if constexpr (GEN) {
-              if (bias_row != nullptr && !dead) t = fmaf(__ldg(bias_row + ki), 1.4426950408889634f, t);
-              if (kpm_row != nullptr && !dead) dead = __ldg(kpm_row + ki) != 0;
-              if (p.drop_thr != 0)
-                dp *= attn_drop_keep(drop_base, (uint32_t)q_in_seg, (uint32_t)ki, (uint32_t)p.Lk, p.drop_thr) ? p.drop_inv_keep : 0.f;
+              if (bias_pre) b4v = __ldg(reinterpret_cast<const float4*>(bias_row + j * BI + cc) + q4);
             }
-            const float pe = dead ? 0.f : ex2_approx(t - lse);
-            dsv[i] = pe * (dp - dlt);
+            const float bq[4] = {b4v.x, b4v.y, b4v.z, b4v.w};
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const int i = q4 * 4 + e4;
+              const int ki = j * BI + cc + i;   // key index inside the segment
+              float t = __uint_as_float(s[i]) * c;
+              float dp = __uint_as_float(d[i]);
+              bool dead = (cc + i) >= k_valid;
+              if constexpr (GEN) {
+                if (bias_pre) t = fmaf(bq[e4], 1.4426950408889634f, t);
+                else if (bias_row != nullptr && !dead) t = fmaf(__ldg(bias_row + ki), 1.4426950408889634f, t);
+                if (kpm_row != nullptr && !dead) dead = __ldg(kpm_row + ki) != 0;
+                if (p.drop_thr != 0) {
+                  if (bits_row != nullptr) dp *= ((mw >> i) & 1u) ? p.drop_inv_keep : 0.f;
+                  else dp *= attn_drop_keep(drop_base, (uint32_t)q_in_seg, (uint32_t)ki, (uint32_t)p.Lk, p.drop_thr) ? p.drop_inv_keep : 0.f;
+                }
+              }
+              const float pe = dead ? 0.f : ex2_approx(t - lse);
+              dsv[i] = pe * (dp - dlt);
+            }
           }
         }
         uint32_t dd[16];
@@ -820,6 +875,12 @@ int attn_bwd_launch(const AttnArgs& a, cudaStream_t stream) {
   p.scale = a.scale; p.scale_log2 = a.scale * 1.4426950408889634f;
   p.bias = a.bias; p.kpm = a.kpm;
   p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_thr = a.drop_p > 0.f ? dropout_threshold(a.drop_p) : 0u; p.drop_seed = a.drop_seed;
+  {
+    const bool bits_ok = a.drop_p > 0.f && a.Lq % 32 == 0 && a.Lk % 32 == 0 && a.drop_bits != nullptr && a.drop_bitsT != nullptr;
+    p.drop_bits = bits_ok ? a.drop_bits : nullptr;
+    p.drop_bitsT = bits_ok ? a.drop_bitsT : nullptr;
+  }
+  p.bias_vec4 = (a.bias != nullptr && a.Lk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0;
   BwdParams pk = p, pq = p;
   pk.tiles = (a.Lk + BT - 1) / BT;
   pq.tiles = (a.Lq + BT - 1) / BT;

@@ -70,7 +70,7 @@ struct FwdParams {
   // GEN only
   const float* bias;     // [nseg*H][Lq][Lk] or null
   const uint8_t* kpm;    // [nseg][Lk] or null
-  float drop_inv_keep; uint32_t drop_thr, drop_seed;
+  float drop_inv_keep; uint32_t drop_thr, drop_seed; const uint32_t* drop_bits; int bias_vec4;
 };
 
 // dropout mask on the attention probabilities: stateless hash of (seed, segment*H + head, query, key)
@@ -196,9 +196,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int q_in_seg = min(q_tile * BQ + r, p.Lq - 1);
     const float* bias_row = nullptr;
     uint32_t drop_base = 0;
+    const uint32_t* bits_row = nullptr;      // precomputed keep-bits of this query row (one word per 32 keys)
     if constexpr (GEN) {
       if (p.bias != nullptr) bias_row = p.bias + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * p.Lk;
       drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
+      if (p.drop_bits != nullptr) bits_row = p.drop_bits + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * (p.Lk >> 5);
     }
     const float c_eff = GEN ? 1.f : c;
 
@@ -223,9 +225,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < 32; ++i) t[i] *= c;
           if (bias_row != nullptr) {
             const float* bp = bias_row + j * BKV + h * 32;
+            if (full && p.bias_vec4) {
+              // every lane reads its OWN row (a gather of 32 lines per instruction): 16-byte loads need a quarter of the
+              // LSU wavefronts of scalar ones (row a7, 401 x 5184 decoder cross-attention: the bias is 532 MB per call)
+              const float4* b4 = reinterpret_cast<const float4*>(bp);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (h * 32 + i < kv_valid) t[i] = fmaf(__ldg(bp + i), 1.4426950408889634f, t[i]);
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 b = __ldg(b4 + q4);
+                t[4 * q4] = fmaf(b.x, 1.4426950408889634f, t[4 * q4]);
+                t[4 * q4 + 1] = fmaf(b.y, 1.4426950408889634f, t[4 * q4 + 1]);
+                t[4 * q4 + 2] = fmaf(b.z, 1.4426950408889634f, t[4 * q4 + 2]);
+                t[4 * q4 + 3] = fmaf(b.w, 1.4426950408889634f, t[4 * q4 + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (h * 32 + i < kv_valid) t[i] = fmaf(__ldg(bp + i), 1.4426950408889634f, t[i]);
+            }
           }
           if (p.kpm != nullptr) {
             const uint8_t* kp = p.kpm + (int64_t)seg * p.Lk + j * BKV + h * 32;
@@ -300,10 +316,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           l_part[q] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
           if constexpr (GEN) {
             if (p.drop_thr != 0) {   // dropout on the probabilities fed to P.V
+              if (bits_row != nullptr) {
+                const int wi_ = j * (BKV / 32) + h;
+                const uint32_t mw = wi_ < (p.Lk >> 5) ? __ldg(bits_row + wi_) : 0u;
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                e[i] = attn_drop_keep(drop_base, (uint32_t)q_in_seg, (uint32_t)(j * BKV + h * 32 + q * 8 + i), (uint32_t)p.Lk, p.drop_thr)
-                           ? e[i] * p.drop_inv_keep : 0.f;
+                for (int i = 0; i < 8; ++i) e[i] = ((mw >> (q * 8 + i)) & 1u) ? e[i] * p.drop_inv_keep : 0.f;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  e[i] = attn_drop_keep(drop_base, (uint32_t)q_in_seg, (uint32_t)(j * BKV + h * 32 + q * 8 + i), (uint32_t)p.Lk, p.drop_thr)
+                             ? e[i] * p.drop_inv_keep : 0.f;
+              }
             }
           }
 #pragma unroll
@@ -351,6 +374,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 5) tmem_dealloc(tmem_S, TCOLS);
 }
 
+// Keep-bits of the attention-dropout mask, both orientations, from the SAME hash the kernels evaluate inline: one warp per
+// 32 x 32 (query, key) tile; lane = query row computes its 32 decisions (its word of `bits`), a ballot per key column gives
+// the transposed word.  Hashing every score once here instead of once in each of the three kernels is what makes dropout
+// on a 5184 x 5184 attention affordable (bench.py, row a7: 12.5 ms with the inline hash vs 2.1 ms without dropout).
+__global__ void __launch_bounds__(256) attn_dropout_bits_kernel(int n_bh, int Lq, int Lk, uint32_t seed, uint32_t thr,
+                                                                uint32_t* __restrict__ bits, uint32_t* __restrict__ bitsT) {
+  const int lane = threadIdx.x & 31;
+  const int qw = Lq >> 5, kw = Lk >> 5;
+  const int64_t n_tiles = (int64_t)n_bh * qw * kw;
+  for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int kt = (int)(t % kw), qt = (int)((t / kw) % qw), bh = (int)(t / ((int64_t)kw * qw));
+    const uint32_t base = attn_drop_base(seed, (uint32_t)bh);
+    const uint32_t q = (uint32_t)(qt * 32 + lane);
+    uint32_t row = 0, col = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const bool keep = attn_drop_keep(base, q, (uint32_t)(kt * 32 + k), (uint32_t)Lk, thr);
+      row |= (keep ? 1u : 0u) << k;
+      const uint32_t b = __ballot_sync(0xffffffffu, keep);      // bit l = keep(query qt*32 + l, key kt*32 + k)
+      if (lane == k) col = b;
+    }
+    bits[((int64_t)bh * Lq + q) * kw + kt] = row;
+    bitsT[((int64_t)bh * Lk + kt * 32 + lane) * qw + qt] = col;
+  }
+}
+
 // one instantiation (and one cached smem attribute) per (operand format, feature set)
 template <int DT, bool GEN>
 static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const FwdParams& p, dim3 grid, cudaStream_t stream) {
@@ -386,7 +435,8 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t stream) {
   p.Lq_stat = attn_lq_stat(a.Lq); p.stat_stride = (int64_t)a.nseg * p.Lq_stat;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.bias = a.bias; p.kpm = a.kpm;
-  p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_thr = a.drop_p > 0.f ? dropout_threshold(a.drop_p) : 0u; p.drop_seed = a.drop_seed;
+  p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_thr = a.drop_p > 0.f ? dropout_threshold(a.drop_p) : 0u; p.drop_seed = a.drop_seed; p.drop_bits = (a.drop_p > 0.f && a.Lq % 32 == 0 && a.Lk % 32 == 0) ? a.drop_bits : nullptr;
+  p.bias_vec4 = (a.bias != nullptr && a.Lk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0;
   dim3 grid(p.q_tiles * a.nseg, a.heads);
   const bool gen = a.bias != nullptr || a.kpm != nullptr || a.drop_p > 0.f;
   if (gen) return a.dtype == 0 ? launch_fwd<0, true>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, true>(tmQ, tmKV, p, grid, stream);
@@ -399,5 +449,15 @@ int attn_trace_read_fwd(unsigned long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, g_attn_trace_fwd, sizeof(unsigned long long) * (size_t)n);
 }
 #endif
+
+int attn_dropout_bits(int n_bh, int Lq, int Lk, float p, uint32_t seed, uint32_t* bits, uint32_t* bitsT, cudaStream_t stream) {
+  SAM3B_REQUIRE(n_bh > 0 && Lq > 0 && Lk > 0 && Lq % 32 == 0 && Lk % 32 == 0, "attn_dropout_bits: Lq and Lk must be multiples of 32 (got %d, %d)", Lq, Lk);
+  SAM3B_REQUIRE(p > 0.f && p < 1.f && bits && bitsT, "attn_dropout_bits: bad arguments");
+  const int64_t tiles = (int64_t)n_bh * (Lq / 32) * (Lk / 32);
+  const int blocks = (int)std::min<int64_t>((tiles + 7) / 8, (int64_t)num_sms() * 16);
+  attn_dropout_bits_kernel<<<blocks, 256, 0, stream>>>(n_bh, Lq, Lk, seed, dropout_threshold(p), bits, bitsT);
+  SAM3B_LAUNCHED();
+  return 0;
+}
 
 }  // namespace sam3b

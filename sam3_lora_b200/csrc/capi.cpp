@@ -71,7 +71,12 @@ static AttnArgs to_attn_args(const sam3b_attn_desc* d) {
   a.dq = d->dq; a.lddq = d->lddq; a.dq_col0 = d->dq_col0;
   a.dkv = d->dkv; a.lddkv = d->lddkv; a.dk_col0 = d->dk_col0; a.dv_col0 = d->dv_col0;
   a.rope = d->rope; a.rope_period = d->rope_period;
+  a.drop_bits = d->drop_bits; a.drop_bitsT = d->drop_bitsT;
   return a;
+}
+int sam3b_attention_dropout_bits(int32_t n_bh, int32_t Lq, int32_t Lk, float p, uint32_t seed, uint32_t* bits, uint32_t* bitsT,
+                                 void* stream) {
+  return attn_dropout_bits(n_bh, Lq, Lk, p, seed, bits, bitsT, static_cast<cudaStream_t>(stream));
 }
 int sam3b_attention_fwd(const sam3b_attn_desc* d, void* stream) {
   if (!d) return fail(-1, "sam3b_attention_fwd: null descriptor");

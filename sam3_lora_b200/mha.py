@@ -53,6 +53,7 @@ class _AttnCoreFn(torch.autograd.Function):
         Ls = (Lq + 63) // 64 * 64
         lse2 = torch.zeros(heads, nseg * Ls, device=dev, dtype=torch.float32)
         d = L.mha_desc(q16, kv16, nseg, Lq, Lk, heads, scale, O16, lse2, bias=bias, kpm=kpm, drop_p=drop_p, drop_seed=seed)
+        ctx.drop_bits = L.attention_dropout_bits(d)       # large problems: the mask as keep-bits, hashed once (None otherwise)
         L.mha_fwd(d)
         ctx.save_for_backward(q16, kv16, O16, lse2, bias if bias is not None else torch.empty(0, device=dev),
                               kpm if kpm is not None else torch.empty(0, device=dev, dtype=torch.uint8))
@@ -77,6 +78,8 @@ class _AttnCoreFn(torch.autograd.Function):
         dkv16 = torch.empty(nseg * Lk, 2 * Ep, device=dev, dtype=q16.dtype)
         d = L.mha_desc(q16, kv16, nseg, Lq, Lk, heads, scale, O16, lse2, bias=bias if has_bias else None,
                        kpm=kpm if has_kpm else None, drop_p=drop_p, drop_seed=seed)
+        if ctx.drop_bits is not None:
+            d.drop_bits, d.drop_bitsT = L.ptr(ctx.drop_bits[0]), L.ptr(ctx.drop_bits[1])
         L.mha_bwd(d, dO16, delta, dq16, dkv16)
         inv = sc[1:2]
         return ((dq16.float() * inv).to(qdt), (dkv16[:, :Ep].float() * inv).to(qdt), (dkv16[:, Ep:].float() * inv).to(qdt),
@@ -133,6 +136,7 @@ class _FusedMHAFn(torch.autograd.Function):
         lse2 = torch.zeros(heads, nseg * Ls, device=dev, dtype=torch.float32)
         d = L.mha_desc(q16, kv16, nseg, Lq, Lk, heads, scale, O16, lse2, q_col0=qc, k_col0=kc, v_col0=vc, bias=bias, kpm=kpm,
                        drop_p=drop_p, drop_seed=seed)
+        ctx.drop_bits = L.attention_dropout_bits(d)
         L.mha_fwd(d)
         out = torch.empty(Mq, E, device=dev, dtype=torch.float32)
         L.gemm(O16, W["Wo"], out, epilogue=L.EPI_STORE32, bias=W["bo"])
@@ -162,6 +166,8 @@ class _FusedMHAFn(torch.autograd.Function):
         delta = torch.zeros_like(lse2)
         d = L.mha_desc(q16, kv16, nseg, Lq, Lk, heads, scale, O16, lse2, q_col0=qc, k_col0=kc, v_col0=vc,
                        bias=bias if has_bias else None, kpm=kpm if has_kpm else None, drop_p=drop_p, drop_seed=seed)
+        if ctx.drop_bits is not None:
+            d.drop_bits, d.drop_bitsT = L.ptr(ctx.drop_bits[0]), L.ptr(ctx.drop_bits[1])
         inv = sc[1:2]
         need_q, need_k, need_v = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
 

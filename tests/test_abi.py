@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.sam3b_abi_version() == 2       # 2: + sam3b_vit_backward_segment / sam3b_vit_lora_grad_range
+    assert lib.sam3b_abi_version() == 3       # 2: backward segments, device dropout seed, polygons; 3: attention dropout bits
     assert lib.sam3b_launch_count() == 0
 
 
