@@ -486,13 +486,14 @@ def run_native(args):
                 L.mha_fwd(d7)
 
             ms_f = timed(fwd7)
+            ms_bits = timed(lambda: L.attention_dropout_bits(d7)) if pd > 0 else 0.0
             dO7 = (torch.randn(B * Lq, Ep, device=dev) * 0.5).to(dt)
             delta7 = torch.zeros_like(lse7)
             dq7 = torch.empty_like(q7)
             dkv7 = torch.empty_like(kv7)
             ms_b = timed(lambda: L.mha_bwd(d7, dO7, delta7, dq7, dkv7))
             fl7 = 4.0 * B * H7 * Lq * Lk * 32            # algorithmic: head_dim 32
-            others.append({"kernel": "row a7 MHA core (attn_fwd / attn_bwd GEN), %s, B=%d" % (name, B), "ms_fwd": ms_f, "ms_bwd": ms_b,
+            others.append({"kernel": "row a7 MHA core (attn_fwd / attn_bwd GEN), %s, B=%d" % (name, B), "ms_fwd": ms_f, "ms_fwd_of_which_mask_bits": ms_bits, "ms_bwd": ms_b,
                            "ms": ms_f + ms_b, "bound": "mufu-ex2 + per-score dropout hash" if pd > 0 else "mufu-ex2",
                            "achieved": 3.5 * fl7 / (ms_f + ms_b) / 1e9, "unit": "TFLOP/s (algorithmic, head_dim 32; executed at 64)"})
             del q7, kv7, O7, lse7, bias7, dO7, delta7, dq7, dkv7

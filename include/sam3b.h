@@ -117,8 +117,9 @@ typedef struct sam3b_attn_desc {
    * as the inline evaluation); the three kernels then read one word per 32 scores instead of hashing each score three times */
   const uint32_t* drop_bits; const uint32_t* drop_bitsT;
 } sam3b_attn_desc;
-/* bits[(bh*Lq + q)*(Lk/32) + k/32] bit (k & 31) and bitsT[(bh*Lk + k)*(Lq/32) + q/32] bit (q & 31) = 1 where probability
- * (q, k) of problem bh = seg*heads + head is kept.  Lq, Lk multiples of 32; n_bh = nseg*heads. */
+/* bits[(bh*Lq + q)*pitch(Lk) + k/32] bit (k & 31) and bitsT[(bh*Lk + k)*pitch(Lq) + q/32] bit (q & 31) = 1 where probability
+ * (q, k) of problem bh = seg*heads + head is kept; pitch(L) = L/32 rounded up to a multiple of 8 words (32-byte rows), so
+ * bits holds n_bh*Lq*pitch(Lk) words and bitsT n_bh*Lk*pitch(Lq); both 32-byte aligned.  Lq, Lk multiples of 32. */
 int sam3b_attention_dropout_bits(int32_t n_bh, int32_t Lq, int32_t Lk, float p, uint32_t seed, uint32_t* bits, uint32_t* bitsT,
                                  void* stream);
 int sam3b_attention_fwd(const sam3b_attn_desc* d, void* stream);

@@ -243,8 +243,9 @@ def attention_dropout_bits(d):
         return None
     n_bh = d.nseg * d.heads
     dev = torch.device("cuda", torch.cuda.current_device())
-    bits = torch.empty(n_bh * d.Lq * (d.Lk // 32), device=dev, dtype=torch.int32)
-    bitsT = torch.empty(n_bh * d.Lk * (d.Lq // 32), device=dev, dtype=torch.int32)
+    pitch = lambda n: (n // 32 + 7) // 8 * 8          # noqa: E731  (attn_bits_pitch: 32-byte rows)
+    bits = torch.empty(n_bh * d.Lq * pitch(d.Lk), device=dev, dtype=torch.int32)
+    bitsT = torch.empty(n_bh * d.Lk * pitch(d.Lq), device=dev, dtype=torch.int32)
     check(load().sam3b_attention_dropout_bits(n_bh, d.Lq, d.Lk, float(d.drop_p), int(d.drop_seed) & 0xFFFFFFFF, ptr(bits), ptr(bitsT),
                                               current_stream()))
     d.drop_bits, d.drop_bitsT = ptr(bits), ptr(bitsT)

@@ -28,8 +28,8 @@ struct AttnArgs {
   const float* bias = nullptr;       // additive attn_mask, fp32 [nseg*heads][Lq][Lk] (natural-log units, like torch)
   const uint8_t* kpm = nullptr;      // key_padding_mask [nseg][Lk], non-zero = ignore key
   float drop_p = 0.f; uint32_t drop_seed = 0;  // dropout on the attention probabilities (training)
-  // optional precomputed keep-bits of that same mask (attn_dropout_bits): bit (k & 31) of drop_bits[(bh*Lq + q)*(Lk/32) + k/32]
-  // and bit (q & 31) of drop_bitsT[(bh*Lk + k)*(Lq/32) + q/32], bh = seg*heads + head.  The three kernels then read one word
+  // optional precomputed keep-bits of that same mask (attn_dropout_bits): bit (k & 31) of drop_bits[(bh*Lq + q)*pitch(Lk) + k/32]
+  // and bit (q & 31) of drop_bitsT[(bh*Lk + k)*pitch(Lq) + q/32], bh = seg*heads + head, pitch = attn_bits_pitch.  The three kernels then read one word
   // per 32 scores instead of hashing every score three times (forward, dK/dV, dQ).  Needs Lq % 32 == 0 and Lk % 32 == 0.
   const uint32_t* drop_bits = nullptr; const uint32_t* drop_bitsT = nullptr;
   // backward only
@@ -44,6 +44,8 @@ inline int attn_lq_stat(int Lq) { return (Lq + 63) / 64 * 64; }
 
 int attn_fwd_launch(const AttnArgs& a, cudaStream_t stream);
 // keep-bits of the attention-dropout mask for bh = 0 .. n_bh-1 in both orientations (see AttnArgs::drop_bits)
+// row pitch (32-bit words) of the keep-bit arrays for a dimension of length L: L/32 rounded up to 8 words (32-byte rows)
+int attn_bits_pitch(int L);
 int attn_dropout_bits(int n_bh, int Lq, int Lk, float p, uint32_t seed, uint32_t* bits, uint32_t* bitsT, cudaStream_t stream);
 int attn_bwd_launch(const AttnArgs& a, cudaStream_t stream);
 

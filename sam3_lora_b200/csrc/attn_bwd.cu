@@ -73,7 +73,7 @@ struct BwdParams {
   float scale_log2, scale;
   // GEN only
   const float* bias; const uint8_t* kpm;
-  float drop_inv_keep; uint32_t drop_thr, drop_seed; const uint32_t* drop_bits; const uint32_t* drop_bitsT; int bias_vec4;
+  float drop_inv_keep; uint32_t drop_thr, drop_seed; const uint32_t* drop_bits; const uint32_t* drop_bitsT; int bias_vec4; int bits_pitch_k, bits_pitch_q;
 };
 
 __device__ __forceinline__ uint32_t attn_drop_base(uint32_t seed, uint32_t bh) { return lowbias32(seed ^ (bh * 0x9E3779B1u + 0x85EBCA6Bu)); }
@@ -236,7 +236,8 @@ __device__ __forceinline__ void store_grad_chunk16(const BwdParams& p, void* out
 constexpr int DKDV_MAIN = 2 * NSI * I_BYTES + NSI * 2 * BI * 4 + 256;  // Q ring | dO ring | [lse2 | delta] ring | barriers
 constexpr int DKDV_SMEM = DKDV_MAIN + 16 * STG_BYTES + 8 * 2 * STG_BYTES;   // + a row tile per compute warp, + 2 rope tiles per dK warp (199 KB)
 
-template <int DT, bool GEN>
+// DROPB (GEN = false): the ViT instantiation + dropout through precomputed keep-bits, full blocks only (see attn_fwd.cu)
+template <int DT, bool GEN, bool DROPB = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box [64][64]
                      const __grid_constant__ CUtensorMap tmdO,  // dO,       box [64][64]
@@ -402,8 +403,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
         drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
       }
       const uint32_t* bitsT_row = nullptr;   // precomputed keep-bits of this key column (one word per 32 queries)
-      if constexpr (GEN) {
-        if (p.drop_bitsT != nullptr) bitsT_row = p.drop_bitsT + ((int64_t)(seg * p.H + head) * p.Lk + k_in_seg) * (p.Lq >> 5);
+      if constexpr (GEN || DROPB) {
+        if (p.drop_bitsT != nullptr) bitsT_row = p.drop_bitsT + ((int64_t)(seg * p.H + head) * p.Lk + k_in_seg) * p.bits_pitch_q;
       }
       for (int j = (B0 + g) & 1; j < n_blocks; j += 2) {   // blocks whose running index has parity g
         const int jb = B0 + j, st = jb % NSI;
@@ -430,8 +431,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
         if (fast) {
           uint32_t mwf = 0xffffffffu;
           float inv_keep = 1.f;
-          if constexpr (GEN) {
-            if (p.drop_thr != 0) { mwf = __ldg(bitsT_row + ((j * BI + cc) >> 5)); inv_keep = p.drop_inv_keep; }
+          if constexpr (GEN || DROPB) {
+            if (DROPB || p.drop_thr != 0) { mwf = __ldg(bitsT_row + ((j * BI + cc) >> 5)); inv_keep = p.drop_inv_keep; }
           }
           const float4* l4 = reinterpret_cast<const float4*>(stat + cc);
           const float4* d4 = reinterpret_cast<const float4*>(stat + BI + cc);
@@ -443,7 +444,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
             for (int e = 0; e < 4; ++e) {
               const int i = q * 4 + e;
               const float pe = ex2_approx(fmaf(__uint_as_float(s[i]), c, -lv[e]));
-              if constexpr (GEN) {
+              if constexpr (GEN || DROPB) {
                 const float ks = ((mwf >> i) & 1u) ? inv_keep : 0.f;
                 pv[i] = pe * ks;
                 dsv[i] = pe * fmaf(__uint_as_float(d[i]), ks, -dv[e]);
@@ -456,7 +457,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmI,   // q buffer, box
         } else {
           uint32_t mw = 0u;
           if constexpr (GEN) {
-            if (bitsT_row != nullptr) { const int wi_ = (j * BI + cc) >> 5; mw = wi_ < (p.Lq >> 5) ? __ldg(bitsT_row + wi_) : 0u; }
+            if (bitsT_row != nullptr) { const int wi_ = (j * BI + cc) >> 5; mw = wi_ < p.bits_pitch_q ? __ldg(bitsT_row + wi_) : 0u; }
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -549,7 +550,8 @@ constexpr int DQ_MAIN = 2 * NSI * I_BYTES + 256;   // K ring | V ring | barriers
 constexpr int DQ_SMEM = DQ_MAIN + 16 * STG_BYTES + 8 * 2 * STG_BYTES;   // + a row tile per compute warp, + 2 rope tiles per dQ warp
 static_assert(DKDV_SMEM <= 227 * 1024 && DQ_SMEM <= 227 * 1024, "attention backward exceeds the 227 KB of shared memory per CTA");
 
-template <int DT, bool GEN>
+// DROPB (GEN = false): the ViT instantiation + dropout through precomputed keep-bits, full blocks only (see attn_fwd.cu)
+template <int DT, bool GEN, bool DROPB = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box [64][64]
                    const BwdParams p) {
@@ -701,8 +703,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
         drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
       }
       const uint32_t* bits_row = nullptr;
-      if constexpr (GEN) {
-        if (p.drop_bits != nullptr) bits_row = p.drop_bits + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * (p.Lk >> 5);
+      if constexpr (GEN || DROPB) {
+        if (p.drop_bits != nullptr) bits_row = p.drop_bits + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * p.bits_pitch_k;
       }
       for (int j = (B0 + g) & 1; j < n_blocks; j += 2) {
         const int jb = B0 + j;
@@ -721,20 +723,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmI,   // kv buffer, box 
         if (fast) {
           uint32_t mwf = 0xffffffffu;
           float inv_keep = 1.f;
-          if constexpr (GEN) {
-            if (p.drop_thr != 0) { mwf = __ldg(bits_row + ((j * BI + cc) >> 5)); inv_keep = p.drop_inv_keep; }
+          if constexpr (GEN || DROPB) {
+            if (DROPB || p.drop_thr != 0) { mwf = __ldg(bits_row + ((j * BI + cc) >> 5)); inv_keep = p.drop_inv_keep; }
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float pe = ex2_approx(fmaf(__uint_as_float(s[i]), c, -lse));
-            if constexpr (GEN) dsv[i] = pe * fmaf(__uint_as_float(d[i]), ((mwf >> i) & 1u) ? inv_keep : 0.f, -dlt);
+            if constexpr (GEN || DROPB) dsv[i] = pe * fmaf(__uint_as_float(d[i]), ((mwf >> i) & 1u) ? inv_keep : 0.f, -dlt);
             else dsv[i] = pe * (__uint_as_float(d[i]) - dlt);
           }
         } else {
           uint32_t mw = 0u;
           bool bias_pre = false;        // the row's 32 bias values come in through 16-byte loads (see attn_fwd.cu)
           if constexpr (GEN) {
-            if (bits_row != nullptr) { const int wi_ = (j * BI + cc) >> 5; mw = wi_ < (p.Lk >> 5) ? __ldg(bits_row + wi_) : 0u; }
+            if (bits_row != nullptr) { const int wi_ = (j * BI + cc) >> 5; mw = wi_ < p.bits_pitch_k ? __ldg(bits_row + wi_) : 0u; }
             bias_pre = bias_row != nullptr && p.bias_vec4 && cc + 32 <= k_valid;
           }
 #pragma unroll
@@ -827,22 +829,22 @@ static int set_smem_once(K kern, int bytes, bool& done) {
   return 0;
 }
 
-template <int DT, bool GEN>
+template <int DT, bool GEN, bool DROPB = false>
 static int launch_bwd(const AttnArgs& a, const BwdParams& pk, const BwdParams& pq, const CUtensorMap& tmQ64, const CUtensorMap& tmdO64,
                       const CUtensorMap& tmKV64, cudaStream_t stream) {
   static bool s1 = false, s2 = false;
-  int rc = set_smem_once(attn_bwd_dkdv_kernel<DT, GEN>, DKDV_SMEM, s1);
+  int rc = set_smem_once(attn_bwd_dkdv_kernel<DT, GEN, DROPB>, DKDV_SMEM, s1);
   if (rc) return rc;
-  rc = set_smem_once(attn_bwd_dq_kernel<DT, GEN>, DQ_SMEM, s2);
+  rc = set_smem_once(attn_bwd_dq_kernel<DT, GEN, DROPB>, DQ_SMEM, s2);
   if (rc) return rc;
   // persistent: one CTA per SM walks the item list (SAM3B_ATTN_PERSIST=0: one CTA per item, for debugging)
   static const bool persist = [] { const char* e = getenv("SAM3B_ATTN_PERSIST"); return !(e && e[0] == '0'); }();
   const int items_k = pk.tiles * a.nseg * a.heads, items_q = pq.tiles * a.nseg * a.heads;
   const int grid_k = persist ? std::min(items_k, num_sms()) : items_k;
   const int grid_q = persist ? std::min(items_q, num_sms()) : items_q;
-  SAM3B_CHECK_CUDA(launch_pdl(attn_bwd_dkdv_kernel<DT, GEN>, dim3(grid_k), dim3(NTHREADS), DKDV_SMEM, stream, tmQ64, tmdO64, pk));
+  SAM3B_CHECK_CUDA(launch_pdl(attn_bwd_dkdv_kernel<DT, GEN, DROPB>, dim3(grid_k), dim3(NTHREADS), DKDV_SMEM, stream, tmQ64, tmdO64, pk));
   SAM3B_LAUNCHED();
-  SAM3B_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel<DT, GEN>, dim3(grid_q), dim3(NTHREADS), DQ_SMEM, stream, tmKV64, pq));
+  SAM3B_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel<DT, GEN, DROPB>, dim3(grid_q), dim3(NTHREADS), DQ_SMEM, stream, tmKV64, pq));
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -880,11 +882,15 @@ int attn_bwd_launch(const AttnArgs& a, cudaStream_t stream) {
     p.drop_bits = bits_ok ? a.drop_bits : nullptr;
     p.drop_bitsT = bits_ok ? a.drop_bitsT : nullptr;
   }
+  p.bits_pitch_k = attn_bits_pitch(a.Lk); p.bits_pitch_q = attn_bits_pitch(a.Lq);
   p.bias_vec4 = (a.bias != nullptr && a.Lk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0;
   BwdParams pk = p, pq = p;
   pk.tiles = (a.Lk + BT - 1) / BT;
   pq.tiles = (a.Lq + BT - 1) / BT;
   const bool gen = a.bias != nullptr || a.kpm != nullptr || a.drop_p > 0.f;
+  if (a.bias == nullptr && a.kpm == nullptr && a.drop_p > 0.f && p.drop_bits != nullptr && a.Lq == a.Lk && a.Lk % BI == 0)
+    return a.dtype == 0 ? launch_bwd<0, false, true>(a, pk, pq, tmQ64, tmdO64, tmKV64, stream)
+                        : launch_bwd<1, false, true>(a, pk, pq, tmQ64, tmdO64, tmKV64, stream);
   if (gen)
     return a.dtype == 0 ? launch_bwd<0, true>(a, pk, pq, tmQ64, tmdO64, tmKV64, stream)
                         : launch_bwd<1, true>(a, pk, pq, tmQ64, tmdO64, tmKV64, stream);

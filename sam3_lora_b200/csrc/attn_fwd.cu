@@ -70,7 +70,7 @@ struct FwdParams {
   // GEN only
   const float* bias;     // [nseg*H][Lq][Lk] or null
   const uint8_t* kpm;    // [nseg][Lk] or null
-  float drop_inv_keep; uint32_t drop_thr, drop_seed; const uint32_t* drop_bits; int bias_vec4;
+  float drop_inv_keep; uint32_t drop_thr, drop_seed; const uint32_t* drop_bits; int bias_vec4; int bits_pitch_k;
 };
 
 // dropout mask on the attention probabilities: stateless hash of (seed, segment*H + head, query, key)
@@ -79,8 +79,11 @@ __device__ __forceinline__ bool attn_drop_keep(uint32_t base, uint32_t q, uint32
   return lowbias32(base ^ (q * Lk + k)) >= thr;
 }
 
-template <int DT, bool GEN>
-__global__ void __launch_bounds__(192, GEN ? 3 : SAM3B_FWD_CTAS)   // the masked / dropout instantiation needs ~95 registers
+// GEN: additive mask / key padding / dropout (hash or keep-bits) / Lq != Lk.  DROPB (with GEN = false): the ViT instantiation
+// plus dropout through precomputed keep-bits and nothing else - the encoder's 5184 x 5184 self-attention in training mode -
+// so that dropout alone does not drag in the general path (log2-domain rescaling, per-half predicates, spills).
+template <int DT, bool GEN, bool DROPB = false>
+__global__ void __launch_bounds__(192, (GEN || DROPB) ? 3 : SAM3B_FWD_CTAS)   // the masked / dropout instantiations need ~95 registers
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // swizzle-128B operands need 1024-byte alignment
@@ -200,7 +203,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if constexpr (GEN) {
       if (p.bias != nullptr) bias_row = p.bias + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * p.Lk;
       drop_base = attn_drop_base(p.drop_seed, (uint32_t)(seg * p.H + head));
-      if (p.drop_bits != nullptr) bits_row = p.drop_bits + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * (p.Lk >> 5);
+    }
+    if constexpr (GEN || DROPB) {
+      if (p.drop_bits != nullptr) bits_row = p.drop_bits + ((int64_t)(seg * p.H + head) * p.Lq + q_in_seg) * p.bits_pitch_k;
     }
     const float c_eff = GEN ? 1.f : c;
 
@@ -314,11 +319,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           // fp32 row sum of the unrounded, un-dropped probabilities
           l_part[q] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+          if constexpr (DROPB && !GEN) {     // keep-bits only (the launcher guarantees bits_row != nullptr)
+            const uint32_t mw = __ldg(bits_row + (j * (BKV / 32) + h));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = ((mw >> (q * 8 + i)) & 1u) ? e[i] * p.drop_inv_keep : 0.f;
+          }
           if constexpr (GEN) {
             if (p.drop_thr != 0) {   // dropout on the probabilities fed to P.V
               if (bits_row != nullptr) {
                 const int wi_ = j * (BKV / 32) + h;
-                const uint32_t mw = wi_ < (p.Lk >> 5) ? __ldg(bits_row + wi_) : 0u;
+                const uint32_t mw = wi_ < p.bits_pitch_k ? __ldg(bits_row + wi_) : 0u;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) e[i] = ((mw >> (q * 8 + i)) & 1u) ? e[i] * p.drop_inv_keep : 0.f;
               } else {
@@ -374,41 +384,63 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 5) tmem_dealloc(tmem_S, TCOLS);
 }
 
-// Keep-bits of the attention-dropout mask, both orientations, from the SAME hash the kernels evaluate inline: one warp per
-// 32 x 32 (query, key) tile; lane = query row computes its 32 decisions (its word of `bits`), a ballot per key column gives
-// the transposed word.  Hashing every score once here instead of once in each of the three kernels is what makes dropout
-// on a 5184 x 5184 attention affordable (bench.py, row a7: 12.5 ms with the inline hash vs 2.1 ms without dropout).
-__global__ void __launch_bounds__(256) attn_dropout_bits_kernel(int n_bh, int Lq, int Lk, uint32_t seed, uint32_t thr,
-                                                                uint32_t* __restrict__ bits, uint32_t* __restrict__ bitsT) {
-  const int lane = threadIdx.x & 31;
-  const int qw = Lq >> 5, kw = Lk >> 5;
-  const int64_t n_tiles = (int64_t)n_bh * qw * kw;
-  for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-    const int kt = (int)(t % kw), qt = (int)((t / kw) % qw), bh = (int)(t / ((int64_t)kw * qw));
+// Keep-bits of the attention-dropout mask, both orientations, from the SAME hash the kernels evaluate inline.  One CTA per
+// 256 x 256 (query, key) tile: warp w owns query rows 32w .. 32w+31 (lane = row) and walks the eight 32-key groups, so a lane
+// ends up with 8 row words = 32 contiguous bytes of `bits`; a ballot per key gives the transposed word, collected in shared
+// memory so that thread t then writes the 8 words = 32 bytes of key t's row of `bitsT`.  Row pitches are padded to 8 words
+// (attn_bits_pitch) so every store is an aligned, full 32-byte sector.  Hashing every score once here instead of once in each
+// of the three kernels is what makes dropout on a 5184 x 5184 attention affordable (bench.py, row a7).
+__global__ void __launch_bounds__(256) attn_dropout_bits_kernel(int n_bh, int Lq, int Lk, int pitch_k, int pitch_q, uint32_t seed,
+                                                                uint32_t thr, uint32_t* __restrict__ bits, uint32_t* __restrict__ bitsT) {
+  __shared__ uint32_t colw[256][9];      // [key in tile][query group], padded against bank conflicts
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qt_n = (Lq + 255) / 256, kt_n = (Lk + 255) / 256;
+  const int64_t n_tiles = (int64_t)n_bh * qt_n * kt_n;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int kt = (int)(t % kt_n), qt = (int)((t / kt_n) % qt_n), bh = (int)(t / ((int64_t)kt_n * qt_n));
     const uint32_t base = attn_drop_base(seed, (uint32_t)bh);
-    const uint32_t q = (uint32_t)(qt * 32 + lane);
-    uint32_t row = 0, col = 0;
+    const int q = qt * 256 + warp * 32 + lane;
+    uint32_t row[8];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const bool keep = attn_drop_keep(base, q, (uint32_t)(kt * 32 + k), (uint32_t)Lk, thr);
-      row |= (keep ? 1u : 0u) << k;
-      const uint32_t b = __ballot_sync(0xffffffffu, keep);      // bit l = keep(query qt*32 + l, key kt*32 + k)
-      if (lane == k) col = b;
+    for (int g = 0; g < 8; ++g) {
+      uint32_t r = 0, col = 0;
+      const int k0 = kt * 256 + g * 32;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const bool keep = attn_drop_keep(base, (uint32_t)q, (uint32_t)(k0 + k), (uint32_t)Lk, thr);
+        r |= (keep ? 1u : 0u) << k;
+        const uint32_t b = __ballot_sync(0xffffffffu, keep);      // bit l = keep(query row of lane l, key k0 + k)
+        if (lane == k) col = b;
+      }
+      row[g] = r;
+      colw[g * 32 + lane][warp] = col;
     }
-    bits[((int64_t)bh * Lq + q) * kw + kt] = row;
-    bitsT[((int64_t)bh * Lk + kt * 32 + lane) * qw + qt] = col;
+    if (q < Lq) {
+      uint4* dst = reinterpret_cast<uint4*>(bits + ((int64_t)bh * Lq + q) * pitch_k + kt * 8);
+      dst[0] = make_uint4(row[0], row[1], row[2], row[3]);
+      dst[1] = make_uint4(row[4], row[5], row[6], row[7]);
+    }
+    __syncthreads();
+    const int key = kt * 256 + threadIdx.x;
+    if (key < Lk) {
+      const uint32_t* c = colw[threadIdx.x];
+      uint4* dst = reinterpret_cast<uint4*>(bitsT + ((int64_t)bh * Lk + key) * pitch_q + qt * 8);
+      dst[0] = make_uint4(c[0], c[1], c[2], c[3]);
+      dst[1] = make_uint4(c[4], c[5], c[6], c[7]);
+    }
+    __syncthreads();
   }
 }
 
 // one instantiation (and one cached smem attribute) per (operand format, feature set)
-template <int DT, bool GEN>
+template <int DT, bool GEN, bool DROPB = false>
 static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const FwdParams& p, dim3 grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SAM3B_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DT, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    SAM3B_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DT, GEN, DROPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr_set = true;
   }
-  SAM3B_CHECK_CUDA(launch_pdl(attn_fwd_kernel<DT, GEN>, grid, dim3(192), FWD_SMEM, stream, tmQ, tmKV, p));
+  SAM3B_CHECK_CUDA(launch_pdl(attn_fwd_kernel<DT, GEN, DROPB>, grid, dim3(192), FWD_SMEM, stream, tmQ, tmKV, p));
   SAM3B_LAUNCHED();
   return 0;
 }
@@ -436,9 +468,13 @@ int attn_fwd_launch(const AttnArgs& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.bias = a.bias; p.kpm = a.kpm;
   p.drop_inv_keep = 1.f / (1.f - a.drop_p); p.drop_thr = a.drop_p > 0.f ? dropout_threshold(a.drop_p) : 0u; p.drop_seed = a.drop_seed; p.drop_bits = (a.drop_p > 0.f && a.Lq % 32 == 0 && a.Lk % 32 == 0) ? a.drop_bits : nullptr;
+  p.bits_pitch_k = attn_bits_pitch(a.Lk);
   p.bias_vec4 = (a.bias != nullptr && a.Lk % 4 == 0 && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) ? 1 : 0;
   dim3 grid(p.q_tiles * a.nseg, a.heads);
   const bool gen = a.bias != nullptr || a.kpm != nullptr || a.drop_p > 0.f;
+  // dropout through keep-bits and nothing else, full blocks only: the ViT instantiation + the bit mask
+  if (a.bias == nullptr && a.kpm == nullptr && a.drop_p > 0.f && p.drop_bits != nullptr && a.Lq == a.Lk && a.Lk % BKV == 0)
+    return a.dtype == 0 ? launch_fwd<0, false, true>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, false, true>(tmQ, tmKV, p, grid, stream);
   if (gen) return a.dtype == 0 ? launch_fwd<0, true>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, true>(tmQ, tmKV, p, grid, stream);
   return a.dtype == 0 ? launch_fwd<0, false>(tmQ, tmKV, p, grid, stream) : launch_fwd<1, false>(tmQ, tmKV, p, grid, stream);
 }
@@ -450,12 +486,15 @@ int attn_trace_read_fwd(unsigned long long* host, int n) {
 }
 #endif
 
+int attn_bits_pitch(int L) { return ((L + 31) / 32 + 7) / 8 * 8; }
+
 int attn_dropout_bits(int n_bh, int Lq, int Lk, float p, uint32_t seed, uint32_t* bits, uint32_t* bitsT, cudaStream_t stream) {
   SAM3B_REQUIRE(n_bh > 0 && Lq > 0 && Lk > 0 && Lq % 32 == 0 && Lk % 32 == 0, "attn_dropout_bits: Lq and Lk must be multiples of 32 (got %d, %d)", Lq, Lk);
   SAM3B_REQUIRE(p > 0.f && p < 1.f && bits && bitsT, "attn_dropout_bits: bad arguments");
-  const int64_t tiles = (int64_t)n_bh * (Lq / 32) * (Lk / 32);
-  const int blocks = (int)std::min<int64_t>((tiles + 7) / 8, (int64_t)num_sms() * 16);
-  attn_dropout_bits_kernel<<<blocks, 256, 0, stream>>>(n_bh, Lq, Lk, seed, dropout_threshold(p), bits, bitsT);
+  SAM3B_REQUIRE((reinterpret_cast<uintptr_t>(bits) & 31) == 0 && (reinterpret_cast<uintptr_t>(bitsT) & 31) == 0, "attn_dropout_bits: buffers must be 32-byte aligned");
+  const int64_t tiles = (int64_t)n_bh * ((Lq + 255) / 256) * ((Lk + 255) / 256);
+  const int blocks = (int)std::min<int64_t>(tiles, (int64_t)num_sms() * 8);
+  attn_dropout_bits_kernel<<<blocks, 256, 0, stream>>>(n_bh, Lq, Lk, attn_bits_pitch(Lk), attn_bits_pitch(Lq), seed, dropout_threshold(p), bits, bitsT);
   SAM3B_LAUNCHED();
   return 0;
 }

@@ -183,6 +183,35 @@ def test_adapter_free_fused_path_matches_oracle(pattern):
     assert rel_l2(b.cpu(), a.cpu()) < 1e-3
 
 
+def test_dropout_keep_bits_equal_the_oracle_mask_in_both_orientations():
+    """sam3b_attention_dropout_bits: bit (k & 31) of bits[(bh*Lq + q)*pitch(Lk) + k/32] and bit (q & 31) of
+    bitsT[(bh*Lk + k)*pitch(Lq) + q/32] are the oracle's keep decisions (same stateless hash as the inline evaluation)."""
+    import numpy as np
+
+    from sam3_lora_b200 import _lib as L
+    from sam3_lora_b200._abi import AttnDesc
+
+    nseg, H, Lq, Lk, p, seed = 2, 3, 288, 320, 0.3, 4321
+    d = AttnDesc()
+    d.nseg, d.heads, d.Lq, d.Lk, d.drop_p, d.drop_seed = nseg, H, Lq, Lk, p, seed
+    old = L.DROPOUT_BITS_MIN_SCORES
+    L.DROPOUT_BITS_MIN_SCORES = 1
+    try:
+        bits, bitsT = L.attention_dropout_bits(d)
+    finally:
+        L.DROPOUT_BITS_MIN_SCORES = old
+    torch.cuda.synchronize()
+    pitch = lambda n: (n // 32 + 7) // 8 * 8          # noqa: E731
+    ref = (MO.attn_drop_scale_mask(seed, nseg, H, Lq, Lk, p) > 0).reshape(nseg * H, Lq, Lk).numpy()
+    b = bits.cpu().numpy().view(np.uint32).reshape(nseg * H, Lq, pitch(Lk))[:, :, :Lk // 32]
+    got = ((b[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(nseg * H, Lq, Lk).astype(bool)
+    assert np.array_equal(got, ref)
+    bt = bitsT.cpu().numpy().view(np.uint32).reshape(nseg * H, Lk, pitch(Lq))[:, :, :Lq // 32]
+    gotT = ((bt[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(nseg * H, Lk, Lq).astype(bool)
+    assert np.array_equal(gotT, ref.transpose(0, 2, 1))
+    assert abs(ref.mean() - (1 - p)) < 5e-3
+
+
 def test_no_adapters_matches_torch_module_directly():
     from sam3_lora_b200.mha import replace_torch_mha
 
