@@ -212,15 +212,9 @@ class _TrunkFn(torch.autograd.Function):
             st.warm = True
         if len(segs) > 1:
             hook.finish()
-            grads = [gflat[a:a + n].view(shape[::-1]).t().clone() if tr else gflat[a:a + n].view(shape).clone()
-                     for (a, n, shape), tr in zip(vit._flat_index, vit._flat_transposed)]
-            return (None, None, None, *grads)
+            return (None, None, None, *vit._grads_from_flat(gflat))
         vit._after_backward(gflat)
-        # clones, not views: autograd's AccumulateGrad may keep the returned tensor as p.grad, and the next backward
-        # overwrites gflat (gradient accumulation / zero_grad(set_to_none=False) would otherwise see aliased memory)
-        grads = [gflat[a:a + n].view(shape[::-1]).t().clone() if tr else gflat[a:a + n].view(shape).clone()
-                 for (a, n, shape), tr in zip(vit._flat_index, vit._flat_transposed)]
-        return (None, None, None, *grads)
+        return (None, None, None, *vit._grads_from_flat(gflat))
 
 
 class ViT(nn.Module):
@@ -429,6 +423,15 @@ class ViT(nn.Module):
             if tr:
                 self._flat[a:a + n] = p.detach().t().reshape(-1).to(device=dev, dtype=torch.float32)
         return self._flat
+
+    def _grads_from_flat(self, gflat: torch.Tensor) -> List[torch.Tensor]:
+        """Per-parameter gradients for autograd.  They are views of ONE fresh copy of the flat buffer (a single 40 MB
+        device copy), never of the persistent buffer itself: autograd's AccumulateGrad may keep what it is handed as p.grad,
+        and the next backward overwrites the persistent buffer (gradient accumulation over micro-batches or
+        zero_grad(set_to_none=False) would otherwise read aliased memory)."""
+        g = gflat.clone()
+        return [g[a:a + n].view(shape[::-1]).t().contiguous() if tr else g[a:a + n].view(shape)
+                for (a, n, shape), tr in zip(self._flat_index, self._flat_transposed)]
 
     def flat_lora(self) -> Optional[torch.Tensor]:
         return self._flat

@@ -400,6 +400,40 @@ def test_vit_module_public_api_train_eval_and_droppath_statistics():
     assert named["blocks.0.attn.qkv.weight"].grad is None
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_gradient_accumulation_over_two_backwards_without_zero_grad(graphs):
+    """Two micro-batches, no zero_grad in between: p.grad must be g1 + g2.  (The autograd node hands out views of a fresh copy
+    of the flat gradient buffer; views of the persistent buffer would alias it and give 2 * g2.)"""
+    from sam3_lora_b200.lora_layers import LoRAConfig, apply_lora_to_model, get_lora_parameters
+    from sam3_lora_b200.vit import ViT
+
+    torch.manual_seed(11)
+    m = ViT(img_size=224, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4.75, window_size=8, global_att_blocks=(1,),
+            pretrain_img_size=112, drop_path_rate=0.0, max_batch=2, cuda_graphs=graphs)
+    apply_lora_to_model(m, LoRAConfig(rank=4, alpha=8, dropout=0.0, target_modules=["q_proj", "v_proj", "fc1", "fc2"]))
+    params = get_lora_parameters(m)
+    for p in params:
+        torch.nn.init.normal_(p, std=0.05)
+    m = m.cuda().train()
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    xs = [torch.randn(2, 3, 224, 224, device="cuda", generator=gen) for _ in range(2)]
+    gs = [torch.randn(2, 128, 16, 16, device="cuda", generator=gen) for _ in range(2)]
+    for _ in range(2 if graphs else 1):          # graph mode: the first pass is the eager warm-up, the second captures
+        singles = []
+        for x, g in zip(xs, gs):
+            for p in params:
+                p.grad = None
+            (m(x)[0] * g).sum().backward()
+            singles.append([p.grad.detach().clone() for p in params])
+    for p in params:
+        p.grad = None
+    for x, g in zip(xs, gs):
+        (m(x)[0] * g).sum().backward()
+    for p, a, b in zip(params, *singles):
+        assert rel_l2(p.grad.cpu(), (a + b).cpu()) < 1e-5
+        assert rel_l2(p.grad.cpu(), (2 * b).cpu()) > 1e-2      # and it is not the aliasing artefact
+
+
 def test_cuda_graph_mode_matches_eager_over_several_steps():
     """ViT(cuda_graphs=True): step 1 eager (warm-up), step 2 captures + replays, later steps replay; outputs and adapter
     gradients must match an eager twin step by step (different inputs each step, DropPath scales injected identically)."""
