@@ -133,3 +133,11 @@ def test_engine_host_object_needs_no_gpu():
     ws8 = eng.workspace_bytes(8, True)
     assert 4.5e10 < ws8 < 7.5e10       # ~55 GB of saved activations at batch 8 (fits 180 GB HBM3e)
     assert eng.workspace_bytes(8, False) < 5e9
+
+
+def test_driver_build_entry_point_passes():
+    """The driver's "does it build" check: make (a no-op when up to date) + ABI version against the header + every
+    declared symbol exported."""
+    import __graft_entry__ as entry
+
+    entry.build()
