@@ -46,7 +46,6 @@ struct GemmParams {
   uint32_t mn_lbo, mn_sbo;
   float* delta; int delta_Lq, delta_Lq_stat; int64_t delta_stride;
   int tma_store;   // gemm2_kernel: bit 0 = C, bit 1 = C2 go out through TMA stores (16-bit outputs); bit 2 = aux comes in by TMA
-  int bal_rows;    // gemm_kernel, one N tile, plain store: rows per CTA when M is cut evenly over the grid (0 = 128-row tiles round-robin)
 };
 
 
@@ -387,18 +386,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int m_tiles = (p.M + 127) / 128;
   const int kb_total = (p.K + 63) / 64;
   const int kb_per_split = (kb_total + p.splitk - 1) / p.splitk;
-  // Balanced mode (skinny down-projections: one N tile, HBM-bound on A): 324 row tiles over 148 CTAs are 2.19 waves paid as 3.
-  // Instead every CTA owns M / grid consecutive rows and covers them with 128-row tiles whose LAST one is pulled back to end
-  // inside the range: the overlap is recomputed (same values stored twice, its A rows come from L2), all CTAs finish together.
-  const int bal = p.bal_rows;
-  const int bal_lo = blockIdx.x * bal, bal_hi = min(p.M, bal_lo + bal);
-  const int total_work = bal ? gridDim.x * ((bal + 127) / 128) : m_tiles * n_tiles * p.splitk;
-  auto work_row0 = [&](int w, int m_blk) -> int {   // first row of work item w; -1 = nothing left in this CTA's range
-    if (!bal) return m_blk * 128;
-    const int r = bal_lo + (w / static_cast<int>(gridDim.x)) * 128;
-    if (r >= bal_hi) return -1;
-    return max(0, min(r, bal_hi - 128));
-  };
+  const int total_work = m_tiles * n_tiles * p.splitk;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -427,9 +415,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int split = w % p.splitk;
         const int tile = w / p.splitk;
-        const int n_blk = bal ? 0 : tile % n_tiles, m_blk = tile / n_tiles;
-        const int a_row0 = work_row0(w, m_blk);
-        if (a_row0 < 0) continue;
+        const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
         const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
@@ -437,7 +423,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* a_dst = sA + stage * Cfg::A_BYTES;
           uint8_t* b_dst = sB + stage * Cfg::B_BYTES;
           if constexpr (!A_MN) {
-            tma_load_2d(a_dst, &tmA, &full[stage], kb * 64, a_row0);
+            tma_load_2d(a_dst, &tmA, &full[stage], kb * 64, m_blk * 128);
           } else {
 #pragma unroll
             for (int c = 0; c < 2; ++c) tma_load_2d(a_dst + c * 8192, &tmA, &full[stage], m_blk * 128 + c * 64, kb * 64);
@@ -460,7 +446,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int acc = 0; uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int split = w % p.splitk;
-        if (work_row0(w, 0) < 0) continue;
         const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
@@ -497,12 +482,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int tile = w / p.splitk;
-      const int n_blk = bal ? 0 : tile % n_tiles, m_blk = tile / n_tiles;
-      const int t_row0 = work_row0(w, m_blk);
-      if (t_row0 < 0) continue;
+      const int n_blk = tile % n_tiles, m_blk = tile / n_tiles;
       mbar_wait(&tfull[acc], acc_phase, 400 + acc);
       tc_fence_after();
-      const int row0 = t_row0 + ew * 32;
+      const int row0 = m_blk * 128 + ew * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = c_lo; c < c_lo + BN / 2; c += 32) {
@@ -944,15 +927,6 @@ int conv3x3_launch(const ConvArgs& a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------
-// SAM3B_GEMM_BALANCE=0 switches the even row split of the skinny GEMMs off (A/B runs)
-static bool balance_rows_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("SAM3B_GEMM_BALANCE");
-    return !(e != nullptr && e[0] == '0');
-  }();
-  return on;
-}
-
 template <int BN, int EPI, int DT, bool A_MN, bool B_MN>
 static int launch_one(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -974,12 +948,7 @@ static int launch_one(const GemmArgs& a, const GemmParams& p, cudaStream_t strea
   const int total = m_tiles * n_tiles * p.splitk;
   int ctas = a.max_ctas > 0 ? a.max_ctas : num_sms();
   if (ctas > total) ctas = total;
-  GemmParams pp = p;
-  if (EPI == EPI_STORE16 && !A_MN && n_tiles == 1 && p.splitk == 1 && m_tiles > ctas && m_tiles % ctas != 0 && balance_rows_enabled()) {
-    pp.bal_rows = (a.M + ctas - 1) / ctas;          // >= 128 because m_tiles > ctas
-    ctas = (a.M + pp.bal_rows - 1) / pp.bal_rows;   // no CTA without rows
-  }
-  SAM3B_CHECK_CUDA(launch_pdl(kern, dim3(ctas), dim3(384), Cfg::SMEM, stream, tmA, tmB, pp));
+  SAM3B_CHECK_CUDA(launch_pdl(kern, dim3(ctas), dim3(384), Cfg::SMEM, stream, tmA, tmB, p));
   SAM3B_LAUNCHED();
   return 0;
 }

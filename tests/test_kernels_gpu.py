@@ -24,7 +24,7 @@ def test_gemm_fp32_outputs(case):
     assert r["err"] < F32_TOL, r
 
 
-@pytest.mark.parametrize("case", ["k_store16", "k_skinny", "k_skinny_balanced", "k_skinny_balanced_ragged", "epi_gelu", "epi_dgelu", "epi_rope", "p_store16"])
+@pytest.mark.parametrize("case", ["k_store16", "k_skinny", "k_skinny_full", "k_skinny_ragged", "epi_gelu", "epi_dgelu", "epi_rope", "p_store16"])
 def test_gemm_16bit_epilogues(case):
     import bringup_gemm
 

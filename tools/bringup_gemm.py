@@ -94,9 +94,9 @@ def run_case(name: str) -> dict:
         res["err"] = basic(640, 1024, 320, epi=L.EPI_STORE16)
     elif name == "k_skinny":
         res["err"] = basic(5184, 64, 1024, epi=L.EPI_STORE16, bn=64)
-    elif name == "k_skinny_balanced":   # more row tiles than SMs, not a multiple: the even row split (overlapping last tile per CTA)
+    elif name == "k_skinny_full":   # the trunk's size: 324 row tiles over 148 persistent CTAs
         res["err"] = basic(41472, 64, 1024, epi=L.EPI_STORE16, bn=64)
-    elif name == "k_skinny_balanced_ragged":   # M not a multiple of 128 nor 8; N = 48 (q|k|v of one rank-16 adapter); short last CTA
+    elif name == "k_skinny_ragged":   # M not a multiple of 128 nor 8; N = 48 (q|k|v of one rank-16 adapter)
         res["err"] = basic(20736 + 1003, 48, 1024 + 16, epi=L.EPI_STORE16, bn=64)
     elif name == "k_persist":  # more tiles than CTAs: exercises phase wrap-around on every barrier
         res["err"] = basic(128 * 40, 256 * 12, 64 * 9, max_ctas=7)
@@ -224,7 +224,7 @@ def run_case(name: str) -> dict:
 
 
 CASES = [
-    "k_tile1", "k_tile1_bn64", "k_multi", "k_ragged", "k_store16", "k_skinny", "k_skinny_balanced", "k_skinny_balanced_ragged", "k_persist", "k_big_f16", "k_big_bf16",
+    "k_tile1", "k_tile1_bn64", "k_multi", "k_ragged", "k_store16", "k_skinny", "k_skinny_full", "k_skinny_ragged", "k_persist", "k_big_f16", "k_big_bf16",
     "epi_residual", "epi_gelu", "epi_dgelu", "epi_rope",
     "mn_8192_1024", "mn_1024_8192", "mn_16_1024", "mn_8192_128",
     "perf_qkv", "perf_fc1", "perf_fc2", "perf_proj", "perf_skinny", "perf_skinny_fc2", "perf_skinny_b4", "perf_gelu", "perf_dgelu",
