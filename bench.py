@@ -2,7 +2,7 @@
 """bench.py — SAM3 ViT trunk + rank-16 LoRA training throughput (images/sec) on B200.
 
     python bench.py --gpus 1 --steps 5 --warmup 3                 # this repo (native sm_100a path)
-    python bench.py --impl reference --steps 2 --warmup 1         # reference arithmetic on the host CPU
+    python bench.py --impl reference --steps 2 --warmup 1         # the unmodified reference trunk (baseline/_ref) on the host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W    # one rank per GPU, weak scaling
 
@@ -11,7 +11,11 @@ adapters (q,k,v,out,fc1,fc2, r=16, alpha=32) + [N>1: one all-reduce of the flat 
 AdamW, batch 8 x 3x1008x1008 per GPU (BASELINE.json configs[1]; "1024 px" is the source size, the
 model computes at 1008, SURVEY.md fact 3).  `value` is timed with the batch resident in HBM;
 `e2e` goes through the public API (vit.ViT + lora_layers + autograd) with the batch copied from
-pinned host memory and the loss read back every step.  Prints ONE JSON line (rank 0).
+pinned host memory and the loss read back every step.  Prints ONE JSON line (rank 0).  Next to the contract's keys the line
+carries `roofline` (dominant kernel + the attention / conv kernels timed alone), `cpu_baseline` (the reference's own trunk on
+the host, bounded sample), `gpu_eager_baseline` (the reference's own trunk on the same GPU) and `other_workloads` (the whole
+detector step, native vs the untouched reference, and the other shipped adapter configs); --no-cpu / --no-gpu-eager /
+--no-whole-model / --no-other-configs skip those legs.
 """
 from __future__ import annotations
 
