@@ -130,8 +130,14 @@ def _native_masks_class():
     return NativeMasks
 
 
-def build_objective(native: bool = True):
-    """(matcher, loss_wrapper) with the weights of train_sam3_lora_native.py:743-793."""
+def build_objective(native: bool = True, normalization: str = "local"):
+    """(matcher, loss_wrapper) with the weights of train_sam3_lora_native.py:743-793.
+
+    `normalization` is Sam3LossWrapper's (sam3_loss.py:74-80): "local" (what the reference CLI passes, `:791`; bit-parity
+    with the single-GPU run) divides by this rank's box count; "global" all-reduces the count over the process group
+    first - the DDP-correct loss scale when the batch is sharded; "none" leaves the sums unscaled."""
+    if normalization not in ("local", "global", "none"):
+        raise ValueError(f"normalization={normalization!r}: expected 'local', 'global' or 'none'")
     bridge.import_reference()
     from sam3.train.loss import loss_fns  # noqa: PLC0415
     from sam3.train.loss.sam3_loss import Sam3LossWrapper  # noqa: PLC0415
@@ -166,7 +172,7 @@ def build_objective(native: bool = True):
     ]
     o2m = ref_matcher.BinaryOneToManyMatcher(alpha=0.3, threshold=0.4, topk=4)
     wrapper = Sam3LossWrapper(loss_fns_find=fns, matcher=matcher, o2m_matcher=o2m, o2m_weight=2.0,
-                              use_o2m_matcher_on_o2m_aux=False, normalization="local", normalize_by_valid_object_num=False)
+                              use_o2m_matcher_on_o2m_aux=False, normalization=normalization, normalize_by_valid_object_num=False)
     return matcher, wrapper
 
 

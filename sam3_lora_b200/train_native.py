@@ -322,7 +322,10 @@ class SAM3TrainerNative:
             self.model = sam3_bridge.build_native_model("cpu", checkpoint_path=ckpt, seed=seed if ckpt is None else None,
                                                         max_batch=self.batch_size,
                                                         cuda_graphs=bool(tc.get("cuda_graphs", False)))
-            self.matcher, self.loss_wrapper = sam3_step.build_objective(native=True)
+            # "local" = the reference CLI's choice (bit-parity with its single-GPU run); "global" all-reduces the box count
+            # so the loss scale is right when the batch is sharded over ranks (training.loss_normalization)
+            self.matcher, self.loss_wrapper = sam3_step.build_objective(native=True,
+                                                                        normalization=str(tc.get("loss_normalization", "local")))
         elif self.objective == "trunk_proxy":
             self.model = TrunkWithProxyHead(max_batch=self.batch_size, **(vit_overrides or {}))
             if ckpt is not None:

@@ -103,3 +103,21 @@ def test_sam3_objective_refuses_random_base_weights(tmp_path, monkeypatch):
     monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
     with pytest.raises(RuntimeError, match="checkpoint"):
         T.SAM3TrainerNative(str(p))
+
+
+def test_objective_normalization_is_validated_and_passed_through():
+    """sam3_loss.py:53: 'global' | 'local' | 'none'; anything else is refused before the reference is imported."""
+    import pytest
+
+    from sam3_lora_b200 import sam3_bridge, sam3_step
+
+    with pytest.raises(ValueError):
+        sam3_step.build_objective(native=False, normalization="per_rank")
+    try:
+        sam3_bridge.import_reference()
+    except Exception:   # noqa: BLE001  (reference not installed under baseline/_ref: nothing more to check here)
+        pytest.skip("reference not importable")
+    _, wrapper = sam3_step.build_objective(native=False, normalization="global")
+    assert wrapper.normalization == "global"
+    _, wrapper = sam3_step.build_objective(native=False)
+    assert wrapper.normalization == "local"      # train_sam3_lora_native.py:791
