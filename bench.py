@@ -469,6 +469,21 @@ def run_native(args):
                            "achieved": 2.5 * fl / ms_b / 1e9, "unit": "TFLOP/s (5 algorithmic matmuls)", "floor_ms": 2 * mufu_s * 1e3,
                            "frac_of_floor": 2 * mufu_s * 1e3 / ms_b})
             del qkv, O, lse2, dO, delta, dqkv
+            # the library kernel on the same shape (torch SDPA, fp16, its flash backend): context only, never on the product path
+            try:
+                import torch.nn.functional as F   # noqa: PLC0415
+
+                q_, k_, v_ = ((torch.randn(segs, heads, Ls, 64, device=dev) * 0.5).to(dt).requires_grad_(True) for _ in range(3))
+                go_ = (torch.randn(segs, heads, Ls, 64, device=dev) * 0.5).to(dt)
+                with torch.no_grad():
+                    lib_f = timed(lambda: F.scaled_dot_product_attention(q_, k_, v_))
+                o_ = F.scaled_dot_product_attention(q_, k_, v_)
+                lib_b = timed(lambda: torch.autograd.grad(o_, (q_, k_, v_), go_, retain_graph=True))
+                others[-2]["library_sdpa_ms"] = lib_f
+                others[-1]["library_sdpa_ms"] = lib_b
+                del q_, k_, v_, go_, o_
+            except Exception as e:   # noqa: BLE001
+                others[-1]["library_sdpa_error"] = f"{type(e).__name__}: {e}"[:200]
         # row a7: the nn.MultiheadAttention core at the DETR sizes (E=256, 8 heads of 32 run as zero-padded 64-wide heads):
         # encoder self-attention over the 5184 image tokens with and without attention dropout, decoder image cross-attention
         # 401 x 5184 with the additive fp32 box-RPB bias
