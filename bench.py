@@ -334,7 +334,7 @@ def run_native(args):
     model.cuda_graphs = not args.e2e_eager and not args.no_graph
     params = model.lora_parameters()
     if world > 1:
-        model.grad_hook = LoRAGradAllReducer(average=False, segments=args.segments)
+        model.grad_hook = LoRAGradAllReducer(average=True, segments=args.segments)   # sum / world on each slice (DDP semantics)
     opt = torch.optim.AdamW(params, lr=args.lr, weight_decay=0.01, fused=True)
     # double-buffered input: the H2D copy of step i+1 (pinned host memory, side stream) overlaps the compute of
     # step i, as an input pipeline would; every step still copies its own batch inside the timed region.
@@ -364,9 +364,6 @@ def run_native(args):
         opt.zero_grad(set_to_none=True)
         loss.backward()
         compute_done[slot].record()
-        if world > 1:
-            for p in params:
-                p.grad.mul_(1.0 / world)
         opt.step()
         return loss.item()                              # D2H read of the step's loss
 
