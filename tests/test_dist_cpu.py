@@ -66,3 +66,50 @@ def test_shard_indices_padding_and_determinism():
 def test_allreducer_is_noop_without_process_group():
     t = torch.ones(4)
     assert LoRAGradAllReducer()(t) is t and torch.equal(t, torch.ones(4))
+
+
+def _trainer_sync_worker(rank, world, port, q):
+    """Replicas built from different RNG states agree after the trainer's rank-0 broadcast, and stay equal over SGD steps
+    on different data when the non-trunk gradients go through _FlatGradSync (the advisor's round-1 finding)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from sam3_lora_b200.dist import init_from_env
+    from sam3_lora_b200.train_native import _broadcast_from_rank0, _FlatGradSync
+
+    init_from_env("gloo")
+    torch.manual_seed(100 + rank)                      # every process draws different initial weights ...
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    model.register_buffer("running", torch.randn(3))
+    model[2].bias.requires_grad_(False)                # a frozen tensor and one that never receives a gradient
+    before = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    _broadcast_from_rank0(model)                       # ... and starts from rank 0's
+    params = [p for p in model.parameters() if p.requires_grad]
+    sync = _FlatGradSync(params)
+    opt = torch.optim.SGD(params, lr=0.1)
+    g = torch.Generator().manual_seed(7 + rank)        # different data per rank
+    for _ in range(3):
+        x = torch.randn(4, 6, generator=g)
+        opt.zero_grad(set_to_none=True)
+        model(x).square().mean().backward()
+        sync()
+        opt.step()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()] + [model.running])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    q.put((rank, bool(all(torch.equal(gathered[0], t) for t in gathered)), bool(rank == 0 or not torch.equal(before, flat[:before.numel()]))))
+    dist.destroy_process_group()
+
+
+def test_trainer_replicas_start_equal_and_stay_equal_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_trainer_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, equal, changed in res:
+        assert equal, f"rank {rank}: replicas diverged"
+        assert changed
