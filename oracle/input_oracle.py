@@ -145,7 +145,9 @@ def rle_mask_resized(counts: Sequence[int], h: int, w: int, out: int) -> np.ndar
 # Polygon masks: pycocotools `frPyObjects` (list of polygons) -> `merge` -> `decode`, the call sequence of
 # train_sam3_lora_native.py:152-156.  Third-party arithmetic restated from the published algorithm of
 # pycocotools/common/maskApi.c `rleFrPoly` (pycocotools >= 2.0.6, requirements.txt; not installed here: PARITY UNPINNED
-# beyond the known answers in tests/test_input_oracle.py - an axis-aligned integer box polygon covers exactly w*h pixels).
+# beyond the known answers in tests/test_input_oracle.py - an axis-aligned integer box polygon covers exactly w*h pixels -
+# and an independent cross-check: against OpenCV's point-in-polygon test at the pixel centres, random star-shaped polygons
+# differ only at pixels whose centre lies within 0.22 px of the boundary, the quantisation of rleFrPoly's 5x grid).
 # ------------------------------------------------------------------------------------------------------------------
 def _c_int(v: float) -> int:
     """C's (int) cast: truncation toward zero."""
